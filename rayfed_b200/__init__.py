@@ -1,0 +1,33 @@
+"""rayfed_b200 — a Blackwell-native cross-party federated execution engine.
+
+Drop-in API of ray-project/rayfed (``import rayfed_b200 as fed``)::
+
+    fed.init(addresses=..., party="alice")
+    @fed.remote
+    def f(x): ...
+    y = f.party("bob").remote(x)      # runs in bob only; alice pushes x
+    fed.get(y)                        # collective: every party gets the value
+    fed.shutdown()
+
+plus the B200-native federated-learning layer (``fed.fl``), the NVLink
+transport and the sm_100a kernels (``fed.ops``).
+"""
+from .api import get, init, kill, remote, shutdown  # noqa: F401
+from .exceptions import FedRemoteError, FedTaskError  # noqa: F401
+from .fed_object import FedObject  # noqa: F401
+from .proxy.barriers import recv, send  # noqa: F401
+
+__all__ = [
+    "get",
+    "init",
+    "kill",
+    "remote",
+    "shutdown",
+    "recv",
+    "send",
+    "FedObject",
+    "FedRemoteError",
+    "FedTaskError",
+]
+
+__version__ = "0.1.0"

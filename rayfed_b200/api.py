@@ -1,0 +1,428 @@
+"""Public API: ``init / shutdown / remote / get / kill``.
+
+Parity: fed/api.py (``init`` :67-296, ``shutdown``/``_shutdown`` :299-360,
+``FedRemoteFunction`` :384-416, ``FedRemoteClass`` :419-448, ``remote``
+:452-528, ``get`` :531-608, ``kill`` :611-623, SIGINT handler :56-64).
+
+Every party runs the same script (multi-controller).  ``init`` brings up the
+party's runtime and its transport; there is no Ray cluster to attach to.  New
+relative to the reference:
+
+* ``config["cross_silo_comm"]["transport"]``: ``auto`` (default; native framed
+  sockets, plus the NVLink device path when the party has a CUDA device and
+  peers share the box), ``native``, ``nvlink``, or ``grpc`` (wire-compatible
+  with the reference; chosen automatically when ``tls_config`` is given).
+* ``config["device"]``: the CUDA device of this party (e.g. ``"cuda:3"``).
+"""
+from __future__ import annotations
+
+import functools
+import inspect
+import logging
+import pickle
+import signal
+import sys
+import threading
+from typing import Any, Callable, Dict, List, Union
+
+from . import config as fed_config
+from . import utils as fed_utils
+from ._private import constants
+from ._private import kv as fed_kv
+from ._private.fed_actor import FedActorHandle
+from ._private.fed_call_holder import FedCallHolder
+from ._private.global_context import clear_global_context, get_global_context, init_global_context
+from .config import CrossSiloMessageConfig
+from .core import get as _local_get
+from .core import get_runtime, is_refs, shutdown_runtime
+from .exceptions import FedRemoteError, FedTaskError
+from .fed_object import FedObject
+from .proxy import barriers
+from .proxy.barriers import (
+    _start_receiver_proxy,
+    _start_sender_proxy,
+    _start_sender_receiver_proxy,
+    ping_others,
+    recv,
+    send,
+    set_proxy_actor_name,
+)
+from .proxy.base_proxy import ReceiverProxy, SenderProxy, SenderReceiverProxy
+from .utils import setup_logger
+
+logger = logging.getLogger(__name__)
+
+original_sigint = signal.getsignal(signal.SIGINT)
+
+
+def _signal_handler(signum, frame):
+    if signum == signal.SIGINT:
+        signal.signal(signal.SIGINT, original_sigint)
+        logger.warning(
+            "Stop signal received (e.g. via SIGINT/Ctrl+C), try to shutdown fed. "
+            "Press CTRL+C (or send SIGINT/SIGKILL/SIGTERM) to skip."
+        )
+        _shutdown(intended=False)
+
+
+def _pick_transport(cross_silo_comm_dict: Dict, tls_config: Dict) -> str:
+    choice = (cross_silo_comm_dict.get("transport") or constants.TRANSPORT_AUTO).lower()
+    if choice not in (
+        constants.TRANSPORT_AUTO, constants.TRANSPORT_NATIVE, constants.TRANSPORT_GRPC, constants.TRANSPORT_NVLINK
+    ):
+        raise ValueError(f"Unknown cross_silo_comm.transport '{choice}'.")
+    if choice == constants.TRANSPORT_AUTO:
+        # TLS and L7-gateway style addresses are only spoken by the gRPC transport.
+        return constants.TRANSPORT_GRPC if tls_config else constants.TRANSPORT_NATIVE
+    return choice
+
+
+def init(
+    addresses: Dict = None,
+    party: str = None,
+    config: Dict = {},
+    tls_config: Dict = None,
+    logging_level: str = "info",
+    sender_proxy_cls: SenderProxy = None,
+    receiver_proxy_cls: ReceiverProxy = None,
+    receiver_sender_proxy_cls: SenderReceiverProxy = None,
+    job_name: str = None,
+    sending_failure_handler: Callable[[Exception], None] = None,
+):
+    """Initialise this party.
+
+    Args:
+        addresses: ``{party: "ip:port" | "host:port" | "http(s)://..." }`` —
+            where each party can be reached by the others.
+        party: this controller's party name; must be a key of ``addresses``.
+        config: ``{"cross_silo_comm": {...}, "barrier_on_initializing": bool,
+            "device": "cuda:N"}``; see :class:`CrossSiloMessageConfig`.
+        tls_config: ``{"ca_cert", "cert", "key"}`` file paths (mutual TLS when
+            ``ca_cert`` is present); selects the gRPC transport.
+        logging_level: debug / info / warning / error / critical.
+        sender_proxy_cls, receiver_proxy_cls, receiver_sender_proxy_cls:
+            custom transport classes (see :mod:`rayfed_b200.proxy.base_proxy`).
+        job_name: must be identical in all parties; messages of other jobs are
+            refused. Defaults to ``"Anonymous_job"``.
+        sending_failure_handler: called with the last sending error when a
+            cross-party send failed and ``exit_on_sending_failure`` is set.
+    """
+    assert addresses, "Addresses should be provided."
+    assert party, "Party should be provided."
+    assert party in addresses, f"Party {party} is not in the addresses {addresses}."
+
+    if job_name is None:
+        job_name = constants.RAYFED_DEFAULT_JOB_NAME
+
+    fed_utils.validate_addresses(addresses)
+
+    config = config or {}
+    cross_silo_comm_dict = config.get("cross_silo_comm", {}) or {}
+    cross_silo_comm_config = CrossSiloMessageConfig.from_dict(cross_silo_comm_dict)
+
+    init_global_context(
+        current_party=party,
+        job_name=job_name,
+        exit_on_sending_failure=cross_silo_comm_config.exit_on_sending_failure,
+        continue_waiting_for_data_sending_on_error=cross_silo_comm_config.continue_waiting_for_data_sending_on_error,
+        sending_failure_handler=sending_failure_handler,
+    )
+
+    tls_config = {} if tls_config is None else tls_config
+    if tls_config:
+        assert "cert" in tls_config and "key" in tls_config, "Cert or key are not in tls_config."
+
+    fed_kv._init_internal_kv(job_name)
+    cluster_config = {
+        constants.KEY_OF_CLUSTER_ADDRESSES: addresses,
+        constants.KEY_OF_CURRENT_PARTY_NAME: party,
+        constants.KEY_OF_TLS_CONFIG: tls_config,
+    }
+    fed_kv.kv.put(constants.KEY_OF_CLUSTER_CONFIG, pickle.dumps(cluster_config))
+    job_config = {constants.KEY_OF_CROSS_SILO_COMM_CONFIG_DICT: cross_silo_comm_dict}
+    fed_kv.kv.put(constants.KEY_OF_JOB_CONFIG, pickle.dumps(job_config))
+
+    setup_logger(
+        logging_level=logging_level,
+        logging_format=constants.RAYFED_LOG_FMT,
+        date_format=constants.RAYFED_DATE_FMT,
+        party_val=_get_party(job_name),
+        job_name=job_name,
+    )
+    logger.info(f"Started rayfed_b200 with {cluster_config}")
+
+    if threading.current_thread() is threading.main_thread():
+        signal.signal(signal.SIGINT, _signal_handler)
+
+    runtime = get_runtime()
+    device = config.get("device")
+    if device is not None:
+        runtime.set_device(str(device))
+
+    get_global_context().get_cleanup_manager().start(
+        exit_on_sending_failure=cross_silo_comm_config.exit_on_sending_failure,
+        expose_error_trace=cross_silo_comm_config.expose_error_trace,
+    )
+
+    ready_timeout = cross_silo_comm_config.timeout_in_ms / 1000
+    use_global_proxy = cross_silo_comm_dict.get("use_global_proxy", True)
+    if receiver_sender_proxy_cls is not None:
+        set_proxy_actor_name(job_name, use_global_proxy, True)
+        _start_sender_receiver_proxy(
+            addresses=addresses, party=party, logging_level=logging_level, tls_config=tls_config,
+            proxy_cls=receiver_sender_proxy_cls, proxy_config=cross_silo_comm_dict,
+            ready_timeout_second=ready_timeout,
+        )
+    else:
+        transport = _pick_transport(cross_silo_comm_dict, tls_config)
+        if receiver_proxy_cls is None:
+            if transport == constants.TRANSPORT_GRPC:
+                from .proxy.grpc.grpc_proxy import GrpcReceiverProxy as receiver_proxy_cls
+            elif transport == constants.TRANSPORT_NVLINK or (
+                transport == constants.TRANSPORT_NATIVE and _device_path_wanted(cross_silo_comm_dict, runtime)
+            ):
+                from .proxy.nvlink.nvlink_proxy import NvlinkReceiverProxy as receiver_proxy_cls
+            else:
+                from .proxy.native.socket_proxy import NativeReceiverProxy as receiver_proxy_cls
+        set_proxy_actor_name(job_name, use_global_proxy)
+        _start_receiver_proxy(
+            addresses=addresses, party=party, logging_level=logging_level, tls_config=tls_config,
+            proxy_cls=receiver_proxy_cls, proxy_config=cross_silo_comm_dict, ready_timeout_second=ready_timeout,
+        )
+        if sender_proxy_cls is None:
+            if transport == constants.TRANSPORT_GRPC:
+                from .proxy.grpc.grpc_proxy import GrpcSenderProxy as sender_proxy_cls
+            elif transport == constants.TRANSPORT_NVLINK or (
+                transport == constants.TRANSPORT_NATIVE and _device_path_wanted(cross_silo_comm_dict, runtime)
+            ):
+                from .proxy.nvlink.nvlink_proxy import NvlinkSenderProxy as sender_proxy_cls
+            else:
+                from .proxy.native.socket_proxy import NativeSenderProxy as sender_proxy_cls
+        _start_sender_proxy(
+            addresses=addresses, party=party, logging_level=logging_level, tls_config=tls_config,
+            proxy_cls=sender_proxy_cls, proxy_config=cross_silo_comm_dict, ready_timeout_second=ready_timeout,
+        )
+
+    if config.get("barrier_on_initializing", False):
+        ping_others(addresses=addresses, self_party=party, max_retries=3600)
+
+
+def _device_path_wanted(cross_silo_comm_dict: Dict, runtime) -> bool:
+    """The NVLink device path is used when the party was given a CUDA device."""
+    return runtime.device is not None and str(runtime.device).startswith("cuda")
+
+
+def shutdown():
+    """Shut this party down (idempotent; safe before/without ``init``)."""
+    global_context = get_global_context()
+    if global_context is not None and global_context.acquire_shutdown_flag():
+        _shutdown(True)
+
+
+def _shutdown(intended=True):
+    """``intended=False`` is the failure path: run the failure handler, do not
+    wait for pending sends, and exit(1) when ``exit_on_sending_failure``."""
+    global_context = get_global_context()
+    if global_context is None:
+        return  # never initialised, or already cleaned
+
+    if intended:
+        logger.info("Shutdowning rayfed_b200 intendedly...")
+    else:
+        logger.warning("Shutdowning rayfed_b200 unintendedly...")
+    last_sending_error = global_context.get_cleanup_manager().get_last_sending_error()
+    last_received_error = global_context.get_last_recevied_error()
+    if last_sending_error is not None:
+        logger.error(f"Cross-silo sending error occured. {last_sending_error}")
+
+    wait_for_sending = True
+    if (
+        last_sending_error is not None or last_received_error is not None
+    ) and not global_context.get_continue_waiting_for_data_sending_on_error():
+        wait_for_sending = False
+    logger.info(f'{"Wait" if wait_for_sending else "No wait"} for data sending.')
+
+    exit_on_sending_failure = global_context.get_exit_on_sending_failure()
+    if not intended:
+        failure_handler = global_context.get_sending_failure_handler()
+        if failure_handler is not None:
+            logger.info(f"Executing failure handler {failure_handler} ...")
+            failure_handler(last_sending_error)
+
+    fed_kv._clear_internal_kv()
+    clear_global_context(wait_for_sending=wait_for_sending)
+    _teardown_runtime(wait_for_sending)
+    logger.info("Shutdowned rayfed_b200.")
+
+    if not intended and exit_on_sending_failure:
+        logger.critical("Exit now due to the previous error.")
+        sys.exit(1)
+
+
+def _teardown_runtime(wait_for_sending: bool):
+    """What ``ray.shutdown()`` did for the reference: stop proxies, then the
+    scheduler.  Pending acks were already drained by the CleanupManager."""
+    try:
+        barriers._stop_proxies()
+    finally:
+        shutdown_runtime(wait=True)
+
+
+def _get_addresses(job_name: str = None):
+    return fed_config.get_cluster_config(job_name).cluster_addresses
+
+
+def _get_party(job_name: str = None):
+    return fed_config.get_cluster_config(job_name).current_party
+
+
+def _get_tls(job_name: str = None):
+    return fed_config.get_cluster_config(job_name).tls_config
+
+
+class FedRemoteFunction:
+    def __init__(self, func_or_class) -> None:
+        self._node_party = None
+        self._func_body = func_or_class
+        self._options = {}
+        self._fed_call_holder = None
+
+    def party(self, party: str):
+        # Mutates and returns self, like the reference (api.py:391-399).
+        self._node_party = party
+        self._fed_call_holder = FedCallHolder(self._node_party, self._execute_impl, self._options)
+        return self
+
+    def options(self, **options):
+        self._options = options
+        if self._fed_call_holder:
+            self._fed_call_holder.options(**options)
+        return self
+
+    def remote(self, *args, **kwargs):
+        if not self._node_party:
+            raise ValueError("You should specify a party name on the fed function.")
+        return self._fed_call_holder.internal_remote(*args, **kwargs)
+
+    def _execute_impl(self, args, kwargs):
+        num_returns = (self._options or {}).get("num_returns", 1) or 1
+        return get_runtime().submit(self._func_body, args, kwargs, num_returns)
+
+
+class FedRemoteClass:
+    def __init__(self, func_or_class) -> None:
+        self._party = None
+        self._cls = func_or_class
+        self._options = {}
+
+    def party(self, party: str):
+        self._party = party
+        return self
+
+    def options(self, **options):
+        self._options = options
+        return self
+
+    def remote(self, *cls_args, **cls_kwargs):
+        ctx = get_global_context()
+        fed_class_task_id = ctx.next_seq_id()  # actor creation burns two ids, like the reference
+        job_name = ctx.get_job_name()
+        fed_actor_handle = FedActorHandle(
+            fed_class_task_id, _get_addresses(job_name), self._cls, _get_party(job_name), self._party,
+            self._options,
+        )
+        fed_call_holder = FedCallHolder(self._party, fed_actor_handle._execute_impl, self._options)
+        fed_call_holder.internal_remote(*cls_args, **cls_kwargs)
+        return fed_actor_handle
+
+
+def remote(*args, **kwargs):
+    """``@fed.remote`` — make a function or class placeable with ``.party(p)``.
+
+    .. code:: python
+
+        @fed.remote
+        def f(a, b): return a + b
+        obj = f.party("alice").remote(1, 2)
+
+        @fed.remote
+        class Counter:
+            def __init__(self, v): self.v = v
+            def inc(self, d): self.v += d; return self.v
+        c = Counter.party("bob").remote(0)
+        fed.get(c.inc.remote(obj))      # -> 3, in every party
+
+    Options (``@fed.remote(num_returns=2)`` or ``.options(num_returns=2)``)
+    replace — not merge — any earlier options.
+    """
+
+    def _make_fed_remote(function_or_class, **options):
+        if inspect.isfunction(function_or_class) or fed_utils.is_cython(function_or_class):
+            return FedRemoteFunction(function_or_class).options(**options)
+        if inspect.isclass(function_or_class):
+            return FedRemoteClass(function_or_class).options(**options)
+        raise TypeError("The @fed.remote decorator must be applied to either a function or a class.")
+
+    if len(args) == 1 and len(kwargs) == 0 and callable(args[0]):
+        return _make_fed_remote(args[0])
+    assert len(args) == 0 and len(kwargs) > 0, "Remote args error."
+    return functools.partial(_make_fed_remote, **kwargs)
+
+
+def get(fed_objects: Union[FedObject, List[FedObject], Any]) -> Any:
+    """Fetch the value(s) behind FedObject(s) — a *collective*: every party calls
+    it at the same program point, the owner pushes the value to all other
+    parties (api.py:564-579), everyone returns it.  Local futures (`Ref`) pass
+    straight through."""
+    if is_refs(fed_objects):
+        return _local_get(fed_objects)
+
+    ctx = get_global_context()
+    fake_fed_task_id = ctx.next_seq_id()  # fed.get is a DAG node too
+    job_name = ctx.get_job_name()
+    addresses = _get_addresses(job_name)
+    current_party = ctx.get_current_party()
+    is_individual_id = isinstance(fed_objects, FedObject)
+    if is_individual_id:
+        fed_objects = [fed_objects]
+
+    refs = []
+    for fed_object in fed_objects:
+        if fed_object.get_party() == current_party:
+            ref = fed_object.get_ref()
+            assert ref is not None
+            refs.append(ref)
+            for party_name in addresses:
+                if party_name == current_party or fed_object._was_sending_or_sent_to_party(party_name):
+                    continue
+                fed_object._mark_is_sending_to_party(party_name)
+                send(
+                    dest_party=party_name,
+                    data=ref,
+                    upstream_seq_id=fed_object.get_fed_task_id(),
+                    downstream_seq_id=fake_fed_task_id,
+                )
+        else:
+            ref = fed_object.get_ref()
+            if ref is None:
+                ref = recv(current_party, fed_object.get_party(), fed_object.get_fed_task_id(), fake_fed_task_id)
+                fed_object._cache_ref(ref)
+            refs.append(ref)
+
+    try:
+        values = _local_get(refs)
+        return values[0] if is_individual_id else values
+    except FedTaskError as e:
+        if isinstance(e.cause, FedRemoteError):
+            logger.warning(f"Encounter RemoteError happend in other parties, error message: {e.cause.cause}")
+            if get_global_context() is not None:
+                get_global_context().set_last_recevied_error(e.cause)
+        raise
+
+
+def kill(actor: FedActorHandle, *, no_restart=True):
+    """Forcefully stop an actor — acts only in the owner party (api.py:619-623)."""
+    ctx = get_global_context()
+    current_party = ctx.get_current_party()
+    if actor._node_party == current_party and actor._actor_handle is not None:
+        actor._actor_handle.kill()

@@ -1,0 +1,344 @@
+"""PartyRuntime — one per controller process.
+
+What Ray supplied to the reference, and where it lives now:
+
+===========================  =================================================
+Ray facility (reference use)  here
+===========================  =================================================
+``ray.remote(f).remote()``    :meth:`PartyRuntime.submit` → C++ ``Executor`` pool
+  (fed/api.py:413-416)          lane; `Ref` args gate the task (no polling)
+actors, ordered mailbox,      :meth:`PartyRuntime.create_actor` → C++ ordered lane
+  ``max_concurrency``           (+ a dedicated CUDA stream when a device is set)
+  (fed/_private/fed_actor.py)
+``ray.get`` / ``ray.wait``    :func:`get` / :func:`wait` (GIL-free waits)
+``ray.kill``                  :meth:`ActorHandle.kill` → mailbox dropped
+named actors                  :meth:`PartyRuntime.register_named` / ``get_named``
+===========================  =================================================
+
+CUDA semantics: a task that runs on a lane with a stream returns its value
+wrapped with the CUDA event recorded after the body; a consumer on another
+stream waits on that event *on the device* (``cudaStreamWaitEvent``) — the host
+never blocks for a device→device dependency, so local tasks overlap in-flight
+pushes.
+"""
+from __future__ import annotations
+
+import atexit
+import importlib
+import os
+import sys
+import threading
+from typing import Any, Callable, Dict, List, Optional, Sequence
+
+from .. import _build
+from ..exceptions import FedActorDiedError, FedGetTimeoutError, FedTaskError
+
+_native = None
+_native_lock = threading.Lock()
+
+
+def native():
+    """Import (building on first use) the ``_fedcore`` extension."""
+    global _native
+    if _native is None:
+        with _native_lock:
+            if _native is None:
+                _build.ensure_core()
+                _native = importlib.import_module("rayfed_b200._fedcore")
+    return _native
+
+
+def _ref_type():
+    return native().Ref
+
+
+class _RefMeta(type):
+    def __instancecheck__(cls, obj):
+        return isinstance(obj, _ref_type())
+
+
+class Ref(metaclass=_RefMeta):
+    """``isinstance(x, Ref)`` works against the native future type; calling
+    ``Ref()`` creates a fresh unresolved native future."""
+
+    def __new__(cls):
+        return _ref_type()()
+
+
+def is_ref(obj) -> bool:
+    return isinstance(obj, _ref_type())
+
+
+def is_refs(objs) -> bool:
+    """True for a Ref or a non-empty list made only of Refs
+    (parity: fed/utils.py:86-96 ``is_ray_object_refs``)."""
+    if is_ref(objs):
+        return True
+    if isinstance(objs, (list, tuple)) and objs:
+        return all(is_ref(o) for o in objs)
+    return False
+
+
+class _Produced:
+    """A value plus the CUDA event that orders it after its producer stream."""
+
+    __slots__ = ("value", "event")
+
+    def __init__(self, value, event):
+        self.value = value
+        self.event = event
+
+
+def _wrap_task_error(exc: BaseException):
+    return FedTaskError.from_exception(exc)
+
+
+class _StreamContext:
+    """Lazily creates a CUDA stream for a lane / pool thread."""
+
+    def __init__(self, device: Optional[str]):
+        self.device = device
+        self._stream = None
+
+    def stream(self):
+        if self.device is None:
+            return None
+        if self._stream is None:
+            import torch
+
+            self._stream = torch.cuda.Stream(device=self.device)
+        return self._stream
+
+
+class ActorHandle:
+    """Local actor: an instance pinned to one ordered lane."""
+
+    def __init__(self, runtime: "PartyRuntime", lane_id: int, name: str, stream_ctx: _StreamContext):
+        self._runtime = runtime
+        self._lane_id = lane_id
+        self._name = name
+        self._stream_ctx = stream_ctx
+        self._instance = None
+        self._dead = False
+        self._ready_ref = None
+
+    @property
+    def name(self) -> str:
+        return self._name
+
+    def submit_method(self, method_name: str, args: tuple, kwargs: dict, num_returns: int = 1):
+        def call(*a, **kw):
+            return getattr(self._instance, method_name)(*a, **kw)
+
+        call.__name__ = f"{self._name}.{method_name}"
+        return self._runtime._submit(self._lane_id, call, args, kwargs, num_returns, self._stream_ctx)
+
+    def submit_call(self, fn: Callable, args: tuple, kwargs: dict, num_returns: int = 1):
+        """Run ``fn(instance, *args)`` in mailbox order (used by proxy hosts)."""
+
+        def call(*a, **kw):
+            return fn(self._instance, *a, **kw)
+
+        return self._runtime._submit(self._lane_id, call, args, kwargs, num_returns, self._stream_ctx)
+
+    def kill(self):
+        if not self._dead:
+            self._dead = True
+            self._runtime._executor.kill_lane(
+                self._lane_id, FedActorDiedError(f"The actor {self._name} was killed by fed.kill().")
+            )
+
+    @property
+    def instance(self):
+        return self._instance
+
+    def backlog(self) -> int:
+        return self._runtime._executor.lane_backlog(self._lane_id)
+
+
+class PartyRuntime:
+    def __init__(self, pool_threads: Optional[int] = None, device: Optional[str] = None):
+        nat = native()
+        if pool_threads is None:
+            pool_threads = int(os.environ.get("RAYFED_B200_POOL_THREADS", "4"))
+        self._executor = nat.Executor(pool_threads, _wrap_task_error)
+        self._device = device
+        self._named: Dict[str, Any] = {}
+        self._named_lock = threading.Lock()
+        self._pool_tls = threading.local()
+        self._actor_count = 0
+        self._closed = False
+
+    # -- configuration ---------------------------------------------------------
+    @property
+    def device(self) -> Optional[str]:
+        return self._device
+
+    def set_device(self, device: Optional[str]):
+        self._device = device
+
+    # -- tasks -----------------------------------------------------------------
+    def _pool_stream_ctx(self) -> Optional[_StreamContext]:
+        if self._device is None:
+            return None
+        return _StreamContext(self._device)  # resolved per pool thread in the trampoline
+
+    def _submit(self, lane_id, fn, args, kwargs, num_returns, stream_ctx):
+        if stream_ctx is not None and stream_ctx.device is not None:
+            fn = _device_trampoline(fn, stream_ctx, self._pool_tls if lane_id == 0 else None)
+        refs = self._executor.submit(lane_id, fn, tuple(args), kwargs or None, num_returns)
+        return refs[0] if num_returns <= 1 else list(refs)
+
+    def submit(self, fn: Callable, args: Sequence = (), kwargs: Optional[dict] = None, num_returns: int = 1):
+        """Stateless task: runs on the shared pool once its `Ref` args resolve."""
+        ctx = _StreamContext(self._device) if self._device is not None else None
+        return self._submit(0, fn, args, kwargs, num_returns, ctx)
+
+    # -- actors ----------------------------------------------------------------
+    def create_actor(self, cls, args: Sequence = (), kwargs: Optional[dict] = None, *, name: str = "",
+                     max_concurrency: int = 1) -> ActorHandle:
+        self._actor_count += 1
+        if not name:
+            name = f"{getattr(cls, '__name__', 'actor')}#{self._actor_count}"
+        lane_id = self._executor.create_lane(name, max_concurrency or 1)
+        handle = ActorHandle(self, lane_id, name, _StreamContext(self._device))
+
+        def construct(*a, **kw):
+            handle._instance = cls(*a, **kw)
+            return True
+
+        construct.__name__ = f"{name}.__init__"
+        handle._ready_ref = self._submit(lane_id, construct, args, kwargs, 1, handle._stream_ctx)
+        return handle
+
+    # -- named registry (ray.get_actor analogue) -------------------------------
+    def register_named(self, name: str, obj) -> None:
+        with self._named_lock:
+            if name in self._named:
+                raise ValueError(f"An actor named '{name}' already exists in this party runtime.")
+            self._named[name] = obj
+
+    def get_named(self, name: str):
+        with self._named_lock:
+            if name not in self._named:
+                raise ValueError(f"Failed to look up actor with name '{name}'.")
+            return self._named[name]
+
+    def has_named(self, name: str) -> bool:
+        with self._named_lock:
+            return name in self._named
+
+    def unregister_named(self, name: str):
+        with self._named_lock:
+            return self._named.pop(name, None)
+
+    def named(self) -> List[str]:
+        with self._named_lock:
+            return list(self._named)
+
+    # -- lifecycle -------------------------------------------------------------
+    def stats(self) -> dict:
+        return dict(self._executor.stats())
+
+    def shutdown(self, wait: bool = True, timeout: float = 5.0):
+        if self._closed:
+            return
+        self._closed = True
+        with self._named_lock:
+            named = list(self._named.values())
+            self._named.clear()
+        for obj in named:
+            stop = getattr(obj, "stop", None)
+            if callable(stop):
+                try:
+                    stop()
+                except Exception:
+                    pass
+        self._executor.shutdown(wait, timeout)
+
+
+def _device_trampoline(fn, stream_ctx: _StreamContext, pool_tls):
+    """Run ``fn`` on the lane's CUDA stream; order device inputs/outputs by events."""
+
+    def run(*args, **kwargs):
+        import torch
+
+        if pool_tls is not None:
+            ctx = getattr(pool_tls, "ctx", None)
+            if ctx is None or ctx.device != stream_ctx.device:
+                ctx = _StreamContext(stream_ctx.device)
+                pool_tls.ctx = ctx
+        else:
+            ctx = stream_ctx
+        stream = ctx.stream()
+        with torch.cuda.stream(stream):
+            args = tuple(_consume(a, stream) for a in args)
+            if kwargs:
+                kwargs = {k: _consume(v, stream) for k, v in kwargs.items()}
+            out = fn(*args, **kwargs)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return _Produced(out, ev)
+
+    run.__name__ = getattr(fn, "__name__", "task")
+    return run
+
+
+def _consume(x, stream):
+    if type(x) is _Produced:
+        if x.event is not None:
+            stream.wait_event(x.event)
+        return x.value
+    return x
+
+
+def _unwrap_for_host(x):
+    """Host-side read of a task result: device work must be complete."""
+    if type(x) is _Produced:
+        if x.event is not None:
+            x.event.synchronize()
+        return x.value
+    return x
+
+
+# ---------------------------------------------------------------------------
+_runtime: Optional[PartyRuntime] = None
+_runtime_lock = threading.Lock()
+
+
+def get_runtime(create: bool = True) -> Optional[PartyRuntime]:
+    global _runtime
+    if _runtime is None and create:
+        with _runtime_lock:
+            if _runtime is None:
+                _runtime = PartyRuntime()
+    return _runtime
+
+
+def shutdown_runtime(wait: bool = True):
+    global _runtime
+    with _runtime_lock:
+        rt, _runtime = _runtime, None
+    if rt is not None:
+        rt.shutdown(wait)
+
+
+atexit.register(lambda: shutdown_runtime(False))
+
+
+def get(refs, timeout: Optional[float] = None):
+    """``ray.get`` analogue for a Ref or a list of Refs."""
+    t = -1.0 if timeout is None else float(timeout)
+    try:
+        if is_ref(refs):
+            return _unwrap_for_host(refs.result(t))
+        return [_unwrap_for_host(r.result(t)) for r in refs]
+    except TimeoutError as e:
+        raise FedGetTimeoutError(str(e)) from None
+
+
+def wait(refs: List, num_returns: int = 1, timeout: Optional[float] = None):
+    """``ray.wait`` analogue → ``(ready, not_ready)``."""
+    t = -1.0 if timeout is None else float(timeout)
+    ready, rest = native().wait_refs(list(refs), num_returns, t)
+    return list(ready), list(rest)

@@ -1,0 +1,235 @@
+// _fedcore: pybind11 surface of the native party runtime.
+//   Ref             one-shot future (replaces ray.ObjectRef)
+//   Executor        task scheduler + actor mailboxes (replaces Ray core worker)
+//   Mailbox         (upstream, downstream) rendezvous table (replaces the
+//                   receiver proxy actor's event tables)
+//   SocketTransport framed TCP/Unix transport with pipelined acks
+//   SeqCounter      the deterministic sequence-id mint
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "executor.h"
+#include "mailbox.h"
+#include "ref.h"
+#include "transport.h"
+
+namespace py = pybind11;
+using namespace fedcore;
+
+namespace {
+
+[[noreturn]] void raise_timeout(const char* what) {
+  PyErr_SetString(PyExc_TimeoutError, what);
+  throw py::error_already_set();
+}
+
+class SeqCounter {
+ public:
+  uint64_t next() { return v_.fetch_add(1, std::memory_order_relaxed) + 1; }
+  uint64_t value() const { return v_.load(std::memory_order_relaxed); }
+  void reset(uint64_t v) { v_.store(v, std::memory_order_relaxed); }
+
+ private:
+  std::atomic<uint64_t> v_{0};
+};
+
+// ray.wait analogue: block until `num_ready` of `refs` resolved or timeout.
+std::pair<std::vector<RefPtr>, std::vector<RefPtr>> wait_refs(const std::vector<RefPtr>& refs, size_t num_ready,
+                                                              double timeout_s) {
+  struct Shared {
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t n = 0;
+  };
+  auto sh = std::make_shared<Shared>();
+  for (auto& r : refs) {
+    r->on_done([sh]() {
+      {
+        std::lock_guard<std::mutex> lk(sh->mu);
+        sh->n++;
+      }
+      sh->cv.notify_all();
+    });
+  }
+  if (num_ready > refs.size()) num_ready = refs.size();
+  {
+    py::gil_scoped_release rel;
+    std::unique_lock<std::mutex> lk(sh->mu);
+    auto pred = [&] { return sh->n >= num_ready; };
+    if (timeout_s < 0)
+      sh->cv.wait(lk, pred);
+    else
+      sh->cv.wait_for(lk, std::chrono::duration<double>(timeout_s), pred);
+  }
+  std::vector<RefPtr> ready, rest;
+  for (auto& r : refs) {
+    if (r->done() && ready.size() < num_ready)
+      ready.push_back(r);
+    else
+      rest.push_back(r);
+  }
+  return {ready, rest};
+}
+
+}  // namespace
+
+PYBIND11_MODULE(_fedcore, m) {
+  m.doc() = "rayfed_b200 native party runtime (scheduler, futures, mailbox, socket transport)";
+
+  py::class_<Ref, RefPtr>(m, "Ref")
+      .def(py::init<>())
+      .def("done", &Ref::done)
+      .def("is_error", &Ref::is_error)
+      .def(
+          "wait",
+          [](Ref& r, double timeout) {
+            py::gil_scoped_release rel;
+            return r.wait(timeout);
+          },
+          py::arg("timeout") = -1.0)
+      .def(
+          "result",
+          [](RefPtr r, double timeout) {
+            bool ok;
+            {
+              py::gil_scoped_release rel;
+              ok = r->wait(timeout);
+            }
+            if (!ok) raise_timeout("timed out waiting for a fed Ref");
+            return r->result();
+          },
+          py::arg("timeout") = -1.0)
+      .def(
+          "exception",
+          [](RefPtr r, double timeout) {
+            bool ok;
+            {
+              py::gil_scoped_release rel;
+              ok = r->wait(timeout);
+            }
+            if (!ok) raise_timeout("timed out waiting for a fed Ref");
+            return r->exception();
+          },
+          py::arg("timeout") = -1.0)
+      .def("set_value", &Ref::set_value)
+      .def("set_error", &Ref::set_error)
+      .def(
+          "set_raw", [](Ref& r, py::bytes b, bool is_error) { return r.set_raw(std::string(b), is_error); },
+          py::arg("data"), py::arg("is_error") = false)
+      .def("set_decoder", &Ref::set_decoder)
+      .def("set_decoded_exc_is_error", &Ref::set_decoded_exc_is_error)
+      .def("add_done_callback", &Ref::add_done_callback);
+
+  m.def("wait_refs", &wait_refs, py::arg("refs"), py::arg("num_ready") = 1, py::arg("timeout") = -1.0);
+
+  py::class_<SeqCounter>(m, "SeqCounter")
+      .def(py::init<>())
+      .def("next", &SeqCounter::next)
+      .def("value", &SeqCounter::value)
+      .def("reset", &SeqCounter::reset, py::arg("value") = 0);
+
+  py::class_<Executor, std::shared_ptr<Executor>>(m, "Executor")
+      .def(py::init<int, py::object>(), py::arg("pool_threads") = 4, py::arg("wrap_error") = py::none())
+      .def("create_lane", &Executor::create_lane, py::arg("name"), py::arg("concurrency") = 1)
+      .def("submit", &Executor::submit, py::arg("lane"), py::arg("fn"), py::arg("args"), py::arg("kwargs"),
+           py::arg("num_returns") = 1)
+      .def("kill_lane", &Executor::kill_lane)
+      .def(
+          "shutdown",
+          [](Executor& e, bool wait, double timeout) {
+            py::gil_scoped_release rel;
+            e.shutdown(wait, timeout);
+          },
+          py::arg("wait") = true, py::arg("timeout") = 5.0)
+      .def("lane_backlog", &Executor::lane_backlog)
+      .def("num_lanes", &Executor::num_lanes)
+      .def("stats", [](Executor& e) {
+        py::dict d;
+        d["submitted"] = e.submitted();
+        d["completed"] = e.completed();
+        d["failed"] = e.failed();
+        return d;
+      });
+
+  py::class_<Mailbox, std::shared_ptr<Mailbox>>(m, "Mailbox")
+      .def(py::init<>())
+      .def("claim", &Mailbox::claim)
+      .def("deliver_obj", &Mailbox::deliver_obj, py::arg("up"), py::arg("down"), py::arg("obj"),
+           py::arg("is_error") = false)
+      .def(
+          "deliver_raw",
+          [](Mailbox& mb, const std::string& up, const std::string& down, py::bytes b, bool is_error) {
+            mb.deliver_raw(up, down, std::string(b), is_error);
+          },
+          py::arg("up"), py::arg("down"), py::arg("data"), py::arg("is_error") = false)
+      .def("pending", &Mailbox::pending)
+      .def("clear", &Mailbox::clear)
+      .def("stats", [](Mailbox& mb) {
+        py::dict d;
+        d["delivered"] = mb.delivered();
+        d["claimed"] = mb.claimed();
+        d["bytes"] = mb.bytes();
+        return d;
+      });
+
+  py::class_<SocketTransport, std::shared_ptr<SocketTransport>>(m, "SocketTransport")
+      .def(py::init<std::string, std::string, std::shared_ptr<Mailbox>>(), py::arg("party"), py::arg("job"),
+           py::arg("mailbox"))
+      .def("listen",
+           [](SocketTransport& t, const std::string& addr) {
+             py::gil_scoped_release rel;
+             return t.listen(addr);
+           })
+      .def(
+          "add_peer",
+          [](SocketTransport& t, const std::string& name, const std::string& addr, int max_attempts,
+             double initial_backoff_s, double max_backoff_s, double multiplier, double timeout_s) {
+            RetryPolicy rp;
+            rp.max_attempts = max_attempts;
+            rp.initial_backoff_s = initial_backoff_s;
+            rp.max_backoff_s = max_backoff_s;
+            rp.multiplier = multiplier;
+            t.add_peer(name, addr, rp, timeout_s);
+          },
+          py::arg("name"), py::arg("addr"), py::arg("max_attempts") = 5, py::arg("initial_backoff_s") = 5.0,
+          py::arg("max_backoff_s") = 30.0, py::arg("multiplier") = 2.0, py::arg("timeout_s") = 60.0)
+      .def(
+          "send",
+          [](SocketTransport& t, const std::string& dest, const std::string& up, const std::string& down,
+             py::bytes data, bool is_error, py::object decoder) {
+            auto ack = std::make_shared<Ref>();
+            if (!decoder.is_none()) ack->set_decoder(decoder);
+            std::string payload(data);
+            bool ok;
+            {
+              py::gil_scoped_release rel;
+              ok = t.send(dest, up, down, std::move(payload), is_error, ack);
+            }
+            if (!ok) throw py::key_error("unknown destination party '" + dest + "'");
+            return ack;
+          },
+          py::arg("dest"), py::arg("up"), py::arg("down"), py::arg("data"), py::arg("is_error") = false,
+          py::arg("decoder") = py::none())
+      .def(
+          "drain",
+          [](SocketTransport& t, double timeout) {
+            py::gil_scoped_release rel;
+            return t.drain(timeout);
+          },
+          py::arg("timeout") = 60.0)
+      .def("stop",
+           [](SocketTransport& t) {
+             py::gil_scoped_release rel;
+             t.stop();
+           })
+      .def("stats", [](SocketTransport& t) {
+        const TransportStats& s = t.stats();
+        py::dict d;
+        d["send_op_count"] = s.send_op_count.load();
+        d["receive_op_count"] = s.receive_op_count.load();
+        d["bytes_sent"] = s.bytes_sent.load();
+        d["bytes_received"] = s.bytes_received.load();
+        d["rejected"] = s.rejected.load();
+        return d;
+      });
+}

@@ -1,0 +1,601 @@
+// fedcore::SocketTransport — native host-side message transport for one party.
+//
+// Plays the role of the reference's gRPC sender/receiver pair
+// (fed/proxy/grpc/grpc_proxy.py:102-220 sender, :223-381 receiver) for parties
+// that share a box: one unary "SendData"-shaped exchange per object
+// {data, upstream_seq_id, downstream_seq_id, job_name} -> {code, result}
+// (schema: fed/grpc/fed.proto:5-19), but as length-prefixed frames over a
+// TCP/Unix stream socket with pipelined acks, delivered by a C++ thread straight
+// into the Mailbox (no actor process, no asyncio loop, no protobuf copy).
+// Semantics kept: job-name check -> 417 (grpc_proxy.py:310-320), 4xx => send
+// failure (:179-190), per-message timeout, connect retry with exponential
+// backoff (grpc_options.py:19-25) so asynchronous party start-up works.
+#pragma once
+#include <arpa/inet.h>
+#include <fcntl.h>
+#include <netdb.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <poll.h>
+#include <sys/socket.h>
+#include <sys/un.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cerrno>
+#include <chrono>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "mailbox.h"
+#include "ref.h"
+
+namespace fedcore {
+
+static constexpr uint32_t kMagic = 0x42444546;  // "FEDB"
+enum : uint8_t { kFrameData = 1, kFrameAck = 2 };
+
+#pragma pack(push, 1)
+struct FrameHeader {
+  uint32_t magic;
+  uint8_t type;
+  uint8_t flags;  // bit0: payload is an error object
+  uint16_t reserved;
+  uint64_t msg_id;
+  uint32_t job_len;
+  uint32_t up_len;
+  uint32_t down_len;
+  int32_t code;  // acks only
+  uint64_t data_len;
+};
+#pragma pack(pop)
+
+struct RetryPolicy {
+  int max_attempts = 5;
+  double initial_backoff_s = 5.0;
+  double max_backoff_s = 30.0;
+  double multiplier = 2.0;
+};
+
+inline bool write_all(int fd, const void* buf, size_t n) {
+  const char* p = (const char*)buf;
+  while (n > 0) {
+    ssize_t w = ::send(fd, p, n, MSG_NOSIGNAL);
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      return false;
+    }
+    p += w;
+    n -= (size_t)w;
+  }
+  return true;
+}
+
+inline bool read_all(int fd, void* buf, size_t n) {
+  char* p = (char*)buf;
+  while (n > 0) {
+    ssize_t r = ::recv(fd, p, n, 0);
+    if (r == 0) return false;
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      return false;
+    }
+    p += r;
+    n -= (size_t)r;
+  }
+  return true;
+}
+
+struct ParsedAddr {
+  bool is_unix = false;
+  std::string host;
+  std::string port;
+  std::string path;
+};
+
+inline ParsedAddr parse_addr(std::string a) {
+  ParsedAddr out;
+  if (a.rfind("unix:", 0) == 0) {
+    out.is_unix = true;
+    out.path = a.substr(5);
+    return out;
+  }
+  auto strip = [&](const char* pre) {
+    size_t n = strlen(pre);
+    if (a.rfind(pre, 0) == 0) a = a.substr(n);
+  };
+  strip("http://");
+  strip("https://");
+  size_t slash = a.find('/');
+  if (slash != std::string::npos) a = a.substr(0, slash);
+  size_t colon = a.rfind(':');
+  if (colon == std::string::npos) {
+    out.host = a;
+    out.port = "80";
+  } else {
+    out.host = a.substr(0, colon);
+    out.port = a.substr(colon + 1);
+  }
+  if (out.host == "local" || out.host == "localhost" || out.host.empty()) out.host = "127.0.0.1";
+  return out;
+}
+
+struct TransportStats {
+  std::atomic<uint64_t> send_op_count{0};
+  std::atomic<uint64_t> receive_op_count{0};
+  std::atomic<uint64_t> bytes_sent{0};
+  std::atomic<uint64_t> bytes_received{0};
+  std::atomic<uint64_t> rejected{0};
+};
+
+// ---------------------------------------------------------------------------
+class Peer {
+ public:
+  struct Outgoing {
+    uint64_t id;
+    std::string up, down, data;
+    bool is_error;
+    RefPtr ack;
+    std::chrono::steady_clock::time_point deadline;
+  };
+
+  Peer(std::string name, std::string addr, std::string job, RetryPolicy retry, double timeout_s,
+       TransportStats* stats)
+      : name_(std::move(name)), addr_(std::move(addr)), job_(std::move(job)), retry_(retry),
+        timeout_s_(timeout_s), stats_(stats) {
+    writer_ = std::thread([this] { writer_loop(); });
+  }
+  ~Peer() { stop(); }
+
+  void push(std::string up, std::string down, std::string data, bool is_error, RefPtr ack) {
+    auto m = std::make_unique<Outgoing>();
+    m->up = std::move(up);
+    m->down = std::move(down);
+    m->data = std::move(data);
+    m->is_error = is_error;
+    m->ack = std::move(ack);
+    m->deadline = std::chrono::steady_clock::now() + std::chrono::duration_cast<std::chrono::steady_clock::duration>(
+                                                         std::chrono::duration<double>(timeout_s_));
+    bool inline_send = false;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      m->id = next_id_++;
+      // Fast path: connection is up and nothing is queued -> write from the
+      // caller's thread and save a thread wake-up per message.
+      if (!stopping_ && fd_.load() >= 0 && q_.empty() && !writing_) {
+        writing_ = true;
+        inline_send = true;
+      } else {
+        q_.push_back(std::move(m));
+      }
+    }
+    if (inline_send) {
+      transmit(std::move(m));
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        writing_ = false;
+      }
+      cv_.notify_all();
+    } else {
+      cv_.notify_one();
+    }
+  }
+
+  void stop() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (stopping_) return;
+      stopping_ = true;
+    }
+    cv_.notify_all();
+    close_conn();
+    if (writer_.joinable()) writer_.join();
+    if (reader_.joinable()) reader_.join();
+    fail_all("transport stopped");
+  }
+
+  // Wait until the queue and all in-flight acks drain (GIL released by caller).
+  bool drain(double timeout_s) {
+    auto deadline = std::chrono::steady_clock::now() + std::chrono::duration<double>(timeout_s);
+    for (;;) {
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (q_.empty() && inflight_.empty() && !writing_) return true;
+      }
+      if (std::chrono::steady_clock::now() > deadline) return false;
+      std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
+  }
+
+ private:
+  int connect_once() {
+    ParsedAddr pa = parse_addr(addr_);
+    int fd = -1;
+    if (pa.is_unix) {
+      fd = ::socket(AF_UNIX, SOCK_STREAM, 0);
+      if (fd < 0) return -1;
+      sockaddr_un sa{};
+      sa.sun_family = AF_UNIX;
+      strncpy(sa.sun_path, pa.path.c_str(), sizeof(sa.sun_path) - 1);
+      if (::connect(fd, (sockaddr*)&sa, sizeof(sa)) != 0) {
+        ::close(fd);
+        return -1;
+      }
+      return fd;
+    }
+    addrinfo hints{}, *res = nullptr;
+    hints.ai_family = AF_UNSPEC;
+    hints.ai_socktype = SOCK_STREAM;
+    if (getaddrinfo(pa.host.c_str(), pa.port.c_str(), &hints, &res) != 0) return -1;
+    for (addrinfo* ai = res; ai; ai = ai->ai_next) {
+      fd = ::socket(ai->ai_family, ai->ai_socktype, ai->ai_protocol);
+      if (fd < 0) continue;
+      if (::connect(fd, ai->ai_addr, ai->ai_addrlen) == 0) {
+        int one = 1;
+        setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+        break;
+      }
+      ::close(fd);
+      fd = -1;
+    }
+    freeaddrinfo(res);
+    return fd;
+  }
+
+  // Retry with exponential backoff; gives up after max_attempts.
+  bool ensure_connected() {
+    if (fd_.load() >= 0) return true;
+    if (reader_.joinable()) reader_.join();
+    double backoff = retry_.initial_backoff_s;
+    for (int attempt = 1; attempt <= retry_.max_attempts; ++attempt) {
+      int fd = connect_once();
+      if (fd >= 0) {
+        fd_.store(fd);
+        reader_ = std::thread([this, fd] { reader_loop(fd); });
+        return true;
+      }
+      if (attempt == retry_.max_attempts) break;
+      std::unique_lock<std::mutex> lk(mu_);
+      if (cv_.wait_for(lk, std::chrono::duration<double>(backoff), [&] { return stopping_; })) return false;
+      backoff = std::min(backoff * retry_.multiplier, retry_.max_backoff_s);
+    }
+    return false;
+  }
+
+  void close_conn() {
+    int fd = fd_.exchange(-1);
+    if (fd >= 0) {
+      ::shutdown(fd, SHUT_RDWR);
+      ::close(fd);
+    }
+  }
+
+  void writer_loop() {
+    for (;;) {
+      std::unique_ptr<Outgoing> m;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stopping_ || (!q_.empty() && !writing_); });
+        if (stopping_) return;
+        m = std::move(q_.front());
+        q_.pop_front();
+        writing_ = true;
+      }
+      if (!ensure_connected()) {
+        m->ack->set_raw("failed to connect to party '" + name_ + "' at " + addr_ + " after " +
+                            std::to_string(retry_.max_attempts) + " attempts",
+                        true);
+      } else {
+        transmit(std::move(m));
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        writing_ = false;
+      }
+      cv_.notify_all();
+    }
+  }
+
+  // Writes one frame on the live connection. Caller owns the `writing_` token.
+  void transmit(std::unique_ptr<Outgoing> m) {
+    FrameHeader h{};
+    h.magic = kMagic;
+    h.type = kFrameData;
+    h.flags = m->is_error ? 1 : 0;
+    h.msg_id = m->id;
+    h.job_len = (uint32_t)job_.size();
+    h.up_len = (uint32_t)m->up.size();
+    h.down_len = (uint32_t)m->down.size();
+    h.data_len = m->data.size();
+    std::string head((const char*)&h, sizeof(h));
+    head += job_;
+    head += m->up;
+    head += m->down;
+    size_t nbytes = m->data.size();
+    if (nbytes <= 4096) head += m->data;  // one syscall for small messages
+    RefPtr ack = m->ack;
+    uint64_t id = m->id;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      inflight_[id] = {ack, m->deadline};
+    }
+    int fd = fd_.load();
+    bool ok = fd >= 0 && write_all(fd, head.data(), head.size()) &&
+              (nbytes <= 4096 || write_all(fd, m->data.data(), nbytes));
+    if (!ok) {
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        inflight_.erase(id);
+      }
+      close_conn();
+      ack->set_raw("connection to party '" + name_ + "' lost while sending", true);
+    } else {
+      stats_->send_op_count.fetch_add(1, std::memory_order_relaxed);
+      stats_->bytes_sent.fetch_add(nbytes, std::memory_order_relaxed);
+    }
+  }
+
+  void reader_loop(int fd) {
+    for (;;) {
+      pollfd p{fd, POLLIN, 0};
+      int pr = ::poll(&p, 1, 100);
+      if (pr < 0 && errno != EINTR) break;
+      sweep_timeouts();
+      if (pr <= 0) {
+        if (fd_.load() != fd) break;
+        continue;
+      }
+      FrameHeader h{};
+      if (!read_all(fd, &h, sizeof(h)) || h.magic != kMagic || h.type != kFrameAck) break;
+      std::string result(h.data_len, '\0');
+      if (h.data_len && !read_all(fd, &result[0], h.data_len)) break;
+      RefPtr ack;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        auto it = inflight_.find(h.msg_id);
+        if (it != inflight_.end()) {
+          ack = it->second.first;
+          inflight_.erase(it);
+        }
+      }
+      if (!ack) continue;
+      if (h.code == 200)
+        ack->set_raw(std::move(result), false);
+      else
+        ack->set_raw(std::move(result), true);
+    }
+    if (fd_.load() == fd) close_conn();
+    fail_inflight("connection to party '" + name_ + "' closed before the message was acknowledged");
+  }
+
+  void sweep_timeouts() {
+    auto now = std::chrono::steady_clock::now();
+    std::vector<RefPtr> dead;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      for (auto it = inflight_.begin(); it != inflight_.end();) {
+        if (it->second.second < now) {
+          dead.push_back(it->second.first);
+          it = inflight_.erase(it);
+        } else {
+          ++it;
+        }
+      }
+    }
+    for (auto& r : dead) r->set_raw("timed out waiting for party '" + name_ + "' to acknowledge", true);
+  }
+
+  void fail_inflight(const std::string& why) {
+    std::map<uint64_t, std::pair<RefPtr, std::chrono::steady_clock::time_point>> dead;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      dead.swap(inflight_);
+    }
+    for (auto& kv : dead) kv.second.first->set_raw(why, true);
+  }
+
+  void fail_all(const std::string& why) {
+    fail_inflight(why);
+    std::deque<std::unique_ptr<Outgoing>> dead;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      dead.swap(q_);
+    }
+    for (auto& m : dead) m->ack->set_raw(why, true);
+  }
+
+  std::string name_, addr_, job_;
+  RetryPolicy retry_;
+  double timeout_s_;
+  TransportStats* stats_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::unique_ptr<Outgoing>> q_;
+  std::map<uint64_t, std::pair<RefPtr, std::chrono::steady_clock::time_point>> inflight_;
+  uint64_t next_id_ = 1;
+  bool stopping_ = false;
+  bool writing_ = false;
+  std::atomic<int> fd_{-1};
+  std::thread writer_, reader_;
+};
+
+// ---------------------------------------------------------------------------
+class SocketTransport {
+ public:
+  SocketTransport(std::string party, std::string job, std::shared_ptr<Mailbox> mailbox)
+      : party_(std::move(party)), job_(std::move(job)), mailbox_(std::move(mailbox)) {}
+  ~SocketTransport() { stop(); }
+
+  // Returns "" on success, else an error description (port in use, ...).
+  std::string listen(const std::string& addr) {
+    ParsedAddr pa = parse_addr(addr);
+    int fd;
+    if (pa.is_unix) {
+      fd = ::socket(AF_UNIX, SOCK_STREAM, 0);
+      sockaddr_un sa{};
+      sa.sun_family = AF_UNIX;
+      strncpy(sa.sun_path, pa.path.c_str(), sizeof(sa.sun_path) - 1);
+      ::unlink(pa.path.c_str());
+      if (::bind(fd, (sockaddr*)&sa, sizeof(sa)) != 0) {
+        std::string e = std::string("bind(") + pa.path + "): " + strerror(errno);
+        ::close(fd);
+        return e;
+      }
+      unix_path_ = pa.path;
+    } else {
+      fd = ::socket(AF_INET, SOCK_STREAM, 0);
+      int one = 1;
+      setsockopt(fd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+      sockaddr_in sa{};
+      sa.sin_family = AF_INET;
+      sa.sin_addr.s_addr = htonl(INADDR_ANY);
+      sa.sin_port = htons((uint16_t)atoi(pa.port.c_str()));
+      if (::bind(fd, (sockaddr*)&sa, sizeof(sa)) != 0) {
+        std::string e = "Failed to listen on port " + pa.port + ": " + strerror(errno);
+        ::close(fd);
+        return e;
+      }
+    }
+    if (::listen(fd, 128) != 0) {
+      std::string e = std::string("listen: ") + strerror(errno);
+      ::close(fd);
+      return e;
+    }
+    listen_fd_.store(fd);
+    accept_thread_ = std::thread([this, fd] { accept_loop(fd); });
+    return "";
+  }
+
+  void add_peer(const std::string& name, const std::string& addr, RetryPolicy retry, double timeout_s) {
+    std::lock_guard<std::mutex> lk(mu_);
+    peers_[name] = std::make_unique<Peer>(name, addr, job_, retry, timeout_s, &stats_);
+  }
+
+  // GIL-free hot path; `ack` resolves raw: b"OK" or error text.
+  bool send(const std::string& dest, std::string up, std::string down, std::string data, bool is_error,
+            RefPtr ack) {
+    Peer* p = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = peers_.find(dest);
+      if (it != peers_.end()) p = it->second.get();
+    }
+    if (!p) return false;
+    p->push(std::move(up), std::move(down), std::move(data), is_error, std::move(ack));
+    return true;
+  }
+
+  bool drain(double timeout_s) {
+    std::vector<Peer*> ps;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      for (auto& kv : peers_) ps.push_back(kv.second.get());
+    }
+    bool ok = true;
+    for (auto* p : ps) ok = p->drain(timeout_s) && ok;
+    return ok;
+  }
+
+  void stop() {
+    if (stopped_.exchange(true)) return;
+    int lfd = listen_fd_.exchange(-1);
+    if (lfd >= 0) {
+      ::shutdown(lfd, SHUT_RDWR);
+      ::close(lfd);
+    }
+    if (accept_thread_.joinable()) accept_thread_.join();
+    std::map<std::string, std::unique_ptr<Peer>> peers;
+    std::vector<std::pair<int, std::thread>> conns;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      peers.swap(peers_);
+      conns.swap(conns_);
+    }
+    for (auto& kv : peers) kv.second->stop();
+    for (auto& c : conns) {
+      ::shutdown(c.first, SHUT_RDWR);
+    }
+    for (auto& c : conns) {
+      if (c.second.joinable()) c.second.join();
+      ::close(c.first);
+    }
+    if (!unix_path_.empty()) ::unlink(unix_path_.c_str());
+  }
+
+  const TransportStats& stats() const { return stats_; }
+  const std::string& job() const { return job_; }
+
+ private:
+  void accept_loop(int lfd) {
+    for (;;) {
+      int cfd = ::accept(lfd, nullptr, nullptr);
+      if (cfd < 0) {
+        if (errno == EINTR) continue;
+        return;
+      }
+      if (stopped_.load()) {
+        ::close(cfd);
+        return;
+      }
+      int one = 1;
+      setsockopt(cfd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+      std::lock_guard<std::mutex> lk(mu_);
+      conns_.emplace_back(cfd, std::thread([this, cfd] { serve(cfd); }));
+    }
+  }
+
+  void serve(int fd) {
+    for (;;) {
+      FrameHeader h{};
+      if (!read_all(fd, &h, sizeof(h))) return;
+      if (h.magic != kMagic || h.type != kFrameData) return;
+      std::string job(h.job_len, '\0'), up(h.up_len, '\0'), down(h.down_len, '\0');
+      if (h.job_len && !read_all(fd, &job[0], h.job_len)) return;
+      if (h.up_len && !read_all(fd, &up[0], h.up_len)) return;
+      if (h.down_len && !read_all(fd, &down[0], h.down_len)) return;
+      std::string data(h.data_len, '\0');
+      if (h.data_len && !read_all(fd, &data[0], h.data_len)) return;
+
+      FrameHeader a{};
+      a.magic = kMagic;
+      a.type = kFrameAck;
+      a.msg_id = h.msg_id;
+      std::string result;
+      if (!job_.empty() && job != job_) {
+        // Same contract as the reference receiver: refuse foreign-job traffic.
+        a.code = 417;
+        result = "JobName mis-match, expected " + job_ + ", got " + job + ".";
+        stats_.rejected.fetch_add(1, std::memory_order_relaxed);
+      } else {
+        stats_.receive_op_count.fetch_add(1, std::memory_order_relaxed);
+        stats_.bytes_received.fetch_add(data.size(), std::memory_order_relaxed);
+        mailbox_->deliver_raw(up, down, std::move(data), (h.flags & 1) != 0);
+        a.code = 200;
+        result = "OK";
+      }
+      a.data_len = result.size();
+      std::string out((const char*)&a, sizeof(a));
+      out += result;
+      if (!write_all(fd, out.data(), out.size())) return;
+    }
+  }
+
+  std::string party_, job_;
+  std::shared_ptr<Mailbox> mailbox_;
+  std::mutex mu_;
+  std::map<std::string, std::unique_ptr<Peer>> peers_;
+  std::vector<std::pair<int, std::thread>> conns_;
+  std::atomic<int> listen_fd_{-1};
+  std::atomic<bool> stopped_{false};
+  std::thread accept_thread_;
+  std::string unix_path_;
+  TransportStats stats_;
+};
+
+}  // namespace fedcore
