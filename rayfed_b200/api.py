@@ -203,8 +203,43 @@ def init(
             proxy_cls=sender_proxy_cls, proxy_config=cross_silo_comm_dict, ready_timeout_second=ready_timeout,
         )
 
+    _maybe_start_device_channel(addresses, party, cross_silo_comm_config, runtime)
+
     if config.get("barrier_on_initializing", False):
         ping_others(addresses=addresses, self_party=party, max_retries=3600)
+
+
+def _maybe_start_device_channel(addresses, party, cfg: CrossSiloMessageConfig, runtime):
+    """Bring up the symmetric heap + DeviceChannel when the NVLink proxies are in
+    use.  Collective: every party reaches this point in ``init``; the handle
+    exchange rides the host transport that was just started (connect retries
+    cover parties that start late)."""
+    rt = get_runtime()
+    recv_host = rt.get_named(barriers.receiver_proxy_actor_name())
+    start_unpackers = getattr(recv_host.proxy, "start_unpackers", None)
+    if start_unpackers is None or len(addresses) < 2:
+        return
+    import torch
+
+    from .parallel.group import FedExchange, PartyGroup
+    from .proxy.nvlink import nvlink_proxy
+    from .proxy.nvlink.channel import DeviceChannel
+
+    dev = torch.device(runtime.device)
+    torch.cuda.set_device(dev)
+    group = PartyGroup(list(addresses.keys()), party, FedExchange(), device_index=dev.index or 0)
+    channel = DeviceChannel(
+        group,
+        region_bytes=cfg.device_arena_bytes or (256 << 20),
+        wire_dtype=cfg.device_wire_dtype,
+        timeout_s=(cfg.timeout_in_ms or 60000) / 1000.0,
+    )
+    nvlink_proxy.attach_channel(channel)
+    start_unpackers(channel)
+    logger.info(
+        f"NVLink device channel up: {group.size} parties, {channel.region_bytes >> 20} MiB/region, "
+        f"backend={channel.buf.backend}"
+    )
 
 
 def _device_path_wanted(cross_silo_comm_dict: Dict, runtime) -> bool:
@@ -264,6 +299,15 @@ def _teardown_runtime(wait_for_sending: bool):
     scheduler.  Pending acks were already drained by the CleanupManager."""
     try:
         barriers._stop_proxies()
+        try:
+            from .proxy.nvlink import nvlink_proxy
+
+            ch = nvlink_proxy.current_channel()
+            if ch is not None:
+                ch.synchronize()
+                nvlink_proxy.detach_channel()
+        except ImportError:
+            pass
     finally:
         shutdown_runtime(wait=True)
 

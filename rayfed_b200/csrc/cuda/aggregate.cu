@@ -1,0 +1,326 @@
+// K2 fed_aggregate_sgd / K3 fed_aggregate_adam(_fp8) / K5 fed_barrier.
+//
+// The federated aggregate.  In the reference this is user code composed from
+// pushes: every party ships its weights to one party over gRPC, that party runs
+// `mean`, and the result is shipped back (fed/tests/test_fed_get.py:45-47,71-78;
+// SURVEY §2.D C4).  Here it is ONE kernel per party that fuses
+//
+//   cross-party all-reduce (two-shot: every party owns 1/N of the elements,
+//   pulls that shard from all N parties over NVLink — P2P loads, or one
+//   multimem.ld_reduce through the NVSwitch when a multicast mapping exists),
+//   the 1/N (or n_k/n weighted) scale,
+//   the server/optimizer update in registers (FedAvg, FedAvgM, SGD+momentum+wd,
+//   Adam/AdamW, FedAdam) against a ZeRO-style *sharded* fp32 master + moments
+//   kept only by the owning party, and
+//   the all-gather of the new weights (P2P stores to every party, or one
+//   multimem.st), optionally re-quantised to block-scaled fp8 e4m3 (UE8M0 / 32)
+//
+// with the cross-GPU synchronisation done inside the kernel on a signal pad
+// (per-CTA flags, st.release.sys / ld.acquire.sys), so there is no host hop and
+// no separate NCCL call or optimizer launch.
+#include "kernels.h"
+
+namespace fedk {
+
+// All CTAs with the same blockIdx on every party rendezvous.  Entry: "my inputs
+// are final" (stream order + release).  Exit: "my reads of your inputs and my
+// writes of your outputs are done".
+__device__ __forceinline__ void cta_party_barrier(const AggArgs& a, uint32_t value) {
+  fence_acq_rel_sys();
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < a.n_parties && t != a.my_rank) {
+    uint32_t* remote = reinterpret_cast<uint32_t*>(a.sig_peers.p[t]) + (size_t)blockIdx.x * kMaxParties + a.my_rank;
+    st_release_sys_u32(remote, value);
+    const uint32_t* mine = a.sig + (size_t)blockIdx.x * kMaxParties + t;
+    if (!spin_wait_ge(mine, value, a.timeout_cycles) && a.status) atomicExch(a.status, 2u);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& x, float* f) {
+  f[0] = bf16_lo(x.x); f[1] = bf16_hi(x.x); f[2] = bf16_lo(x.y); f[3] = bf16_hi(x.y);
+  f[4] = bf16_lo(x.z); f[5] = bf16_hi(x.z); f[6] = bf16_lo(x.w); f[7] = bf16_hi(x.w);
+}
+
+__device__ __forceinline__ uint4 multimem_ld_reduce_bf16x8(const void* mc) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(mc)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ uint4 multimem_ld_reduce_f32x4(const void* mc) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(mc)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st_v4(void* mc, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void multimem_st_v2(void* mc, const uint2& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" ::"l"(mc), "r"(v.x), "r"(v.y) : "memory");
+}
+
+__device__ __forceinline__ uint32_t agg_ue8m0(float amax) {
+  float r = amax * (1.0f / 448.0f);
+  uint32_t bits = __float_as_uint(r);
+  uint32_t e = (bits >> 23) & 0xffu;
+  if (bits & 0x7fffffu) e += 1;
+  return e < 1u ? 1u : (e > 253u ? 253u : e);
+}
+__device__ __forceinline__ uint32_t agg_quant4(float a, float b, float c, float d) {
+  uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+
+template <bool kUseMc>
+__global__ void __launch_bounds__(512) fed_aggregate_kernel(AggArgs a) {
+  cta_party_barrier(a, a.epoch + 1);
+
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t nvec = a.shard_len >> 3;
+  const size_t nvec_rounded = (nvec + 31) & ~(size_t)31;  // keep warps converged for the fp8 shuffles
+  const int N = a.n_parties;
+  const int lane = threadIdx.x & 31;
+
+  for (size_t v = tid; v < nvec_rounded; v += stride) {
+    const bool live = v < nvec;
+    const size_t e0 = a.shard_start + (v << 3);  // first global element of this lane
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+
+    if (live) {
+      if (kUseMc) {
+        // NVLS: the switch adds the N copies; one request per 16 B.
+        if (a.in_fp32) {
+          const char* p = reinterpret_cast<const char*>(a.mc_in) + e0 * 4;
+          uint4 s0 = multimem_ld_reduce_f32x4(p), s1 = multimem_ld_reduce_f32x4(p + 16);
+          acc[0] = __uint_as_float(s0.x); acc[1] = __uint_as_float(s0.y);
+          acc[2] = __uint_as_float(s0.z); acc[3] = __uint_as_float(s0.w);
+          acc[4] = __uint_as_float(s1.x); acc[5] = __uint_as_float(s1.y);
+          acc[6] = __uint_as_float(s1.z); acc[7] = __uint_as_float(s1.w);
+        } else {
+          uint4 s = multimem_ld_reduce_bf16x8(reinterpret_cast<const char*>(a.mc_in) + e0 * 2);
+          unpack_bf16x8(s, acc);
+        }
+        const float w0 = a.w[0];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] *= w0;
+      } else if (a.in_fp32) {
+        uint4 x0[kMaxParties / 2], x1[kMaxParties / 2];
+#pragma unroll
+        for (int j = 0; j < kMaxParties / 2; ++j) {
+          if (j < N) {
+            const char* p = reinterpret_cast<const char*>(a.in.p[(a.my_rank + j) % N]) + e0 * 4;
+            x0[j] = ld_v4(p);
+            x1[j] = ld_v4(p + 16);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxParties / 2; ++j) {
+          if (j < N) {
+            const float wj = a.w[(a.my_rank + j) % N];
+            acc[0] += wj * __uint_as_float(x0[j].x); acc[1] += wj * __uint_as_float(x0[j].y);
+            acc[2] += wj * __uint_as_float(x0[j].z); acc[3] += wj * __uint_as_float(x0[j].w);
+            acc[4] += wj * __uint_as_float(x1[j].x); acc[5] += wj * __uint_as_float(x1[j].y);
+            acc[6] += wj * __uint_as_float(x1[j].z); acc[7] += wj * __uint_as_float(x1[j].w);
+          }
+        }
+        for (int j = kMaxParties / 2; j < N; ++j) {
+          const char* p = reinterpret_cast<const char*>(a.in.p[(a.my_rank + j) % N]) + e0 * 4;
+          uint4 y0 = ld_v4(p), y1 = ld_v4(p + 16);
+          const float wj = a.w[(a.my_rank + j) % N];
+          acc[0] += wj * __uint_as_float(y0.x); acc[1] += wj * __uint_as_float(y0.y);
+          acc[2] += wj * __uint_as_float(y0.z); acc[3] += wj * __uint_as_float(y0.w);
+          acc[4] += wj * __uint_as_float(y1.x); acc[5] += wj * __uint_as_float(y1.y);
+          acc[6] += wj * __uint_as_float(y1.z); acc[7] += wj * __uint_as_float(y1.w);
+        }
+      } else {
+        // All N 16-byte requests (1 local + N-1 over NVLink) are issued before any is used.
+        uint4 x[kMaxParties / 2];
+#pragma unroll
+        for (int j = 0; j < kMaxParties / 2; ++j)
+          if (j < N) x[j] = ld_v4(reinterpret_cast<const char*>(a.in.p[(a.my_rank + j) % N]) + e0 * 2);
+#pragma unroll
+        for (int j = 0; j < kMaxParties / 2; ++j) {
+          if (j < N) {
+            float f[8];
+            unpack_bf16x8(x[j], f);
+            const float wj = a.w[(a.my_rank + j) % N];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += wj * f[k];
+          }
+        }
+        for (int j = kMaxParties / 2; j < N; ++j) {
+          uint4 y = ld_v4(reinterpret_cast<const char*>(a.in.p[(a.my_rank + j) % N]) + e0 * 2);
+          float f[8];
+          unpack_bf16x8(y, f);
+          const float wj = a.w[(a.my_rank + j) % N];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] += wj * f[k];
+        }
+      }
+
+      // ---- optimizer / server update, in registers ---------------------------
+      if (a.kind != kAvg) {
+        const size_t s0 = v << 3;  // index into the local shard state
+        float4 m0 = *reinterpret_cast<const float4*>(a.master + s0);
+        float4 m1 = *reinterpret_cast<const float4*>(a.master + s0 + 4);
+        float ms[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        float4 q0 = *reinterpret_cast<const float4*>(a.mom + s0);
+        float4 q1 = *reinterpret_cast<const float4*>(a.mom + s0 + 4);
+        float mo[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        if (a.kind == kFedAvgM || a.kind == kSgdGrad) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float g = (a.kind == kFedAvgM) ? (ms[k] - acc[k]) : (acc[k] + a.weight_decay * ms[k]);
+            mo[k] = a.momentum * mo[k] + g;
+            ms[k] -= a.lr * mo[k];
+            acc[k] = ms[k];
+          }
+        } else {
+          float4 r0 = *reinterpret_cast<const float4*>(a.var + s0);
+          float4 r1 = *reinterpret_cast<const float4*>(a.var + s0 + 4);
+          float va[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float g = (a.kind == kFedAdam) ? (ms[k] - acc[k]) : acc[k];
+            mo[k] = a.beta1 * mo[k] + (1.f - a.beta1) * g;
+            va[k] = a.beta2 * va[k] + (1.f - a.beta2) * g * g;
+            float mhat = mo[k] * a.bias_c1;               // 1 / (1 - beta1^t)
+            float vhat = va[k] * a.bias_c2;               // 1 / (1 - beta2^t)
+            ms[k] -= a.lr * (mhat / (sqrtf(vhat) + a.eps) + a.weight_decay * ms[k]);
+            acc[k] = ms[k];
+          }
+          *reinterpret_cast<float4*>(a.var + s0) = make_float4(va[0], va[1], va[2], va[3]);
+          *reinterpret_cast<float4*>(a.var + s0 + 4) = make_float4(va[4], va[5], va[6], va[7]);
+        }
+        *reinterpret_cast<float4*>(a.master + s0) = make_float4(ms[0], ms[1], ms[2], ms[3]);
+        *reinterpret_cast<float4*>(a.master + s0 + 4) = make_float4(ms[4], ms[5], ms[6], ms[7]);
+        *reinterpret_cast<float4*>(a.mom + s0) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+        *reinterpret_cast<float4*>(a.mom + s0 + 4) = make_float4(mo[4], mo[5], mo[6], mo[7]);
+      }
+    }
+
+    // ---- all-gather of the new weights ----------------------------------------
+    if (!a.out_fp8) {
+      if (live) {
+        uint4 o;
+        o.x = pack_bf16x2(acc[0], acc[1]);
+        o.y = pack_bf16x2(acc[2], acc[3]);
+        o.z = pack_bf16x2(acc[4], acc[5]);
+        o.w = pack_bf16x2(acc[6], acc[7]);
+        if (kUseMc) {
+          multimem_st_v4(reinterpret_cast<char*>(a.mc_out) + e0 * 2, o);
+        } else {
+          for (int j = 0; j < N; ++j) st_v4(reinterpret_cast<char*>(a.out.p[(a.my_rank + j) % N]) + e0 * 2, o);
+        }
+      }
+    } else {
+      float amax = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(acc[k]));
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+      const uint32_t e = agg_ue8m0(amax);
+      const float inv = __uint_as_float((254u - e) << 23);
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lo |= (__shfl_sync(0xffffffffu, e, k * 4) & 0xffu) << (8 * k);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) hi |= (__shfl_sync(0xffffffffu, e, 16 + k * 4) & 0xffu) << (8 * k);
+      if (live) {
+        uint2 o;
+        o.x = agg_quant4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+        o.y = agg_quant4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+        for (int j = 0; j < N; ++j) st_v2(reinterpret_cast<char*>(a.out.p[(a.my_rank + j) % N]) + e0, o);
+      }
+      if (lane == 0 && (v - lane) < nvec) {
+        const size_t blk0 = (a.shard_start >> 5) + ((v - lane) >> 2);
+        const size_t nblk_here = min((size_t)8, ((nvec - (v - lane)) + 3) >> 2);
+        for (int j = 0; j < N; ++j) {
+          unsigned char* sc = reinterpret_cast<unsigned char*>(a.out_scales.p[(a.my_rank + j) % N]);
+          if (nblk_here == 8 && ((blk0 & 7) == 0)) {
+            st_v2(sc + blk0, make_uint2(lo, hi));
+          } else {
+            for (size_t b = 0; b < nblk_here; ++b)
+              sc[blk0 + b] = (unsigned char)((b < 4 ? (lo >> (8 * b)) : (hi >> (8 * (b - 4)))) & 0xffu);
+          }
+        }
+      }
+    }
+  }
+
+  cta_party_barrier(a, a.epoch + 2);
+}
+
+// K5: N-party device barrier (replaces the reference's ping loop,
+// fed/proxy/barriers.py:497-523, once the symmetric heap is up).
+__global__ void fed_barrier_kernel(AggArgs a) { cta_party_barrier(a, a.epoch + 1); }
+
+// Fused local optimizer step on flat buffers: SGD + momentum + weight decay,
+// optional gradient clear in the same pass (saves a memset of the grad bucket).
+__global__ void __launch_bounds__(512) fed_local_sgd_kernel(LocalSgdArgs a) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t nvec = a.n >> 3;
+  for (size_t v = tid; v < nvec; v += stride) {
+    uint4 wv = *reinterpret_cast<const uint4*>(a.w + (v << 3));
+    uint4 gv = *reinterpret_cast<const uint4*>(a.g + (v << 3));
+    float4 q0 = *reinterpret_cast<const float4*>(a.mom + (v << 3));
+    float4 q1 = *reinterpret_cast<const float4*>(a.mom + (v << 3) + 4);
+    float w[8], g[8];
+    float mo[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    unpack_bf16x8(wv, w);
+    unpack_bf16x8(gv, g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float gg = g[k] * a.grad_scale + a.weight_decay * w[k];
+      mo[k] = a.momentum * mo[k] + gg;
+      w[k] -= a.lr * mo[k];
+    }
+    uint4 o;
+    o.x = pack_bf16x2(w[0], w[1]);
+    o.y = pack_bf16x2(w[2], w[3]);
+    o.z = pack_bf16x2(w[4], w[5]);
+    o.w = pack_bf16x2(w[6], w[7]);
+    *reinterpret_cast<uint4*>(a.w + (v << 3)) = o;
+    *reinterpret_cast<float4*>(a.mom + (v << 3)) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+    *reinterpret_cast<float4*>(a.mom + (v << 3) + 4) = make_float4(mo[4], mo[5], mo[6], mo[7]);
+    if (a.zero_grad) *reinterpret_cast<uint4*>(a.g + (v << 3)) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+extern "C" {
+
+cudaError_t fedk_launch_aggregate(const AggArgs* a, int blocks, cudaStream_t stream) {
+  if (a->mc_in != nullptr && a->mc_out != nullptr && !a->out_fp8)
+    fed_aggregate_kernel<true><<<blocks, 512, 0, stream>>>(*a);
+  else
+    fed_aggregate_kernel<false><<<blocks, 512, 0, stream>>>(*a);
+  return cudaGetLastError();
+}
+
+cudaError_t fedk_launch_barrier(const AggArgs* a, cudaStream_t stream) {
+  fed_barrier_kernel<<<1, 32, 0, stream>>>(*a);
+  return cudaGetLastError();
+}
+
+cudaError_t fedk_launch_local_sgd(const LocalSgdArgs* a, int blocks, cudaStream_t stream) {
+  fed_local_sgd_kernel<<<blocks, 512, 0, stream>>>(*a);
+  return cudaGetLastError();
+}
+
+}  // extern "C"
+
+}  // namespace fedk

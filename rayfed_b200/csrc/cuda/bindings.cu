@@ -1,0 +1,400 @@
+// _fedcuda: pybind11 surface of the sm_100a kernels and the symmetric heap.
+//
+// Pointers and streams cross the boundary as integers (torch gives us
+// tensor.data_ptr() and stream.cuda_stream), so this module has no libtorch
+// dependency and compiles in seconds.  cudart is linked statically and the
+// driver API (cuMem*/cuMulticast* for the VMM + NVLS path) is resolved at run
+// time through cudaGetDriverEntryPoint, so importing the module on a machine
+// without a GPU or libcuda works — only launching needs a device.
+#include <cuda.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace py = pybind11;
+
+using namespace fedk;
+
+namespace {
+
+void check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+template <typename T>
+T* P(uint64_t v) {
+  return reinterpret_cast<T*>(static_cast<uintptr_t>(v));
+}
+
+void fill_peers(PeerPtrs& pp, const std::vector<uint64_t>& v) {
+  if (v.size() > (size_t)kMaxParties) throw std::runtime_error("too many parties");
+  for (int i = 0; i < kMaxParties; ++i) pp.p[i] = i < (int)v.size() ? P<void>(v[i]) : nullptr;
+}
+
+// ---- driver entry points -----------------------------------------------------
+template <typename Fn>
+Fn drv(const char* name) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || fn == nullptr)
+    throw std::runtime_error(std::string("driver entry point not available: ") + name);
+  return reinterpret_cast<Fn>(fn);
+}
+
+void cu_check(CUresult r, const char* what) {
+  if (r != CUDA_SUCCESS) {
+    const char* s = nullptr;
+    try {
+      auto f = drv<CUresult (*)(CUresult, const char**)>("cuGetErrorString");
+      f(r, &s);
+    } catch (...) {
+    }
+    throw std::runtime_error(std::string(what) + ": CUresult " + std::to_string((int)r) + " " + (s ? s : ""));
+  }
+}
+
+size_t round_up(size_t x, size_t g) { return (x + g - 1) / g * g; }
+
+}  // namespace
+
+PYBIND11_MODULE(_fedcuda, m) {
+  m.doc() = "rayfed_b200 sm_100a kernels + symmetric heap";
+  m.attr("MAX_PARTIES") = (int)kMaxParties;
+
+  // ---- cudaIpc symmetric memory (tier A: works everywhere P2P works) ---------
+  m.def("ipc_alloc", [](size_t nbytes, bool zero) {
+    void* p = nullptr;
+    check(cudaMalloc(&p, nbytes), "cudaMalloc");
+    if (zero) check(cudaMemset(p, 0, nbytes), "cudaMemset");
+    cudaIpcMemHandle_t h;
+    check(cudaIpcGetMemHandle(&h, p), "cudaIpcGetMemHandle");
+    return py::make_tuple((uint64_t)(uintptr_t)p, py::bytes(reinterpret_cast<const char*>(&h), sizeof(h)));
+  }, py::arg("nbytes"), py::arg("zero") = true);
+  m.def("ipc_open", [](py::bytes handle) {
+    std::string s = handle;
+    if (s.size() != sizeof(cudaIpcMemHandle_t)) throw std::runtime_error("bad ipc handle size");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, s.data(), sizeof(h));
+    void* p = nullptr;
+    check(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    return (uint64_t)(uintptr_t)p;
+  });
+  m.def("ipc_close", [](uint64_t p) { check(cudaIpcCloseMemHandle(P<void>(p)), "cudaIpcCloseMemHandle"); });
+  m.def("dev_free", [](uint64_t p) { check(cudaFree(P<void>(p)), "cudaFree"); });
+  m.def("dev_malloc", [](size_t nbytes, bool zero) {
+    void* p = nullptr;
+    check(cudaMalloc(&p, nbytes), "cudaMalloc");
+    if (zero) check(cudaMemset(p, 0, nbytes), "cudaMemset");
+    return (uint64_t)(uintptr_t)p;
+  }, py::arg("nbytes"), py::arg("zero") = true);
+  m.def("enable_peer_access", [](int peer) {
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+      cudaGetLastError();
+      return true;
+    }
+    return e == cudaSuccess;
+  });
+  m.def("can_access_peer", [](int dev, int peer) {
+    int ok = 0;
+    check(cudaDeviceCanAccessPeer(&ok, dev, peer), "cudaDeviceCanAccessPeer");
+    return ok != 0;
+  });
+  m.def("set_device", [](int d) { check(cudaSetDevice(d), "cudaSetDevice"); });
+  m.def("current_device", [] {
+    int d = -1;
+    check(cudaGetDevice(&d), "cudaGetDevice");
+    return d;
+  });
+  m.def("device_synchronize", [] {
+    py::gil_scoped_release rel;
+    check(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+  });
+  m.def("sm_count", [](int dev) {
+    int n = 0;
+    check(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+    return n;
+  });
+  // small synchronous host<->device words (credit polling, flag reset)
+  m.def("read_u64", [](uint64_t p) {
+    unsigned long long v = 0;
+    check(cudaMemcpy(&v, P<void>(p), 8, cudaMemcpyDeviceToHost), "cudaMemcpy");
+    return (uint64_t)v;
+  });
+  m.def("read_u32", [](uint64_t p) {
+    uint32_t v = 0;
+    check(cudaMemcpy(&v, P<void>(p), 4, cudaMemcpyDeviceToHost), "cudaMemcpy");
+    return v;
+  });
+  m.def("write_u32", [](uint64_t p, uint32_t v) {
+    check(cudaMemcpy(P<void>(p), &v, 4, cudaMemcpyHostToDevice), "cudaMemcpy");
+  });
+  m.def("memset", [](uint64_t p, int byte, size_t n) { check(cudaMemset(P<void>(p), byte, n), "cudaMemset"); });
+
+  // ---- CUDA VMM + NVLS multicast (tier B) -------------------------------------
+  m.def("vmm_info", [](int dev) {
+    py::dict d;
+    int v = 0;
+    auto attr = drv<CUresult (*)(int*, CUdevice_attribute, CUdevice)>("cuDeviceGetAttribute");
+    cu_check(attr(&v, CU_DEVICE_ATTRIBUTE_VIRTUAL_MEMORY_MANAGEMENT_SUPPORTED, dev), "attr vmm");
+    d["vmm"] = v;
+    cu_check(attr(&v, CU_DEVICE_ATTRIBUTE_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR_SUPPORTED, dev), "attr fd");
+    d["posix_fd"] = v;
+    cu_check(attr(&v, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev), "attr mc");
+    d["multicast"] = v;
+    CUresult r = attr(&v, CU_DEVICE_ATTRIBUTE_HANDLE_TYPE_FABRIC_SUPPORTED, dev);
+    d["fabric"] = r == CUDA_SUCCESS ? v : -1;
+    return d;
+  });
+  // Allocate `nbytes` of device memory with an exportable POSIX-fd handle, map it
+  // locally, return (ptr, fd, mapped_size, mem_handle).
+  m.def("vmm_alloc", [](size_t nbytes, int dev) {
+    auto getGran = drv<CUresult (*)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags)>(
+        "cuMemGetAllocationGranularity");
+    auto create = drv<CUresult (*)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*,
+                                   unsigned long long)>("cuMemCreate");
+    auto exportH = drv<CUresult (*)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType,
+                                    unsigned long long)>("cuMemExportToShareableHandle");
+    auto reserve = drv<CUresult (*)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long)>(
+        "cuMemAddressReserve");
+    auto map = drv<CUresult (*)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long)>(
+        "cuMemMap");
+    auto setAccess = drv<CUresult (*)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t)>("cuMemSetAccess");
+    CUmemAllocationProp prop{};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = dev;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t gran = 0;
+    cu_check(getGran(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED), "cuMemGetAllocationGranularity");
+    size_t size = round_up(nbytes, gran);
+    CUmemGenericAllocationHandle h;
+    cu_check(create(&h, size, &prop, 0), "cuMemCreate");
+    int fd = -1;
+    cu_check(exportH(&fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0), "cuMemExportToShareableHandle");
+    CUdeviceptr va = 0;
+    cu_check(reserve(&va, size, gran, 0, 0), "cuMemAddressReserve");
+    cu_check(map(va, size, 0, h, 0), "cuMemMap");
+    CUmemAccessDesc acc{};
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = dev;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    cu_check(setAccess(va, size, &acc, 1), "cuMemSetAccess");
+    check(cudaMemset(reinterpret_cast<void*>(va), 0, size), "cudaMemset");
+    return py::make_tuple((uint64_t)va, fd, size, (uint64_t)h);
+  });
+  // Import a peer's fd and map it with read/write access for `dev`.
+  m.def("vmm_import", [](int fd, size_t size, int dev) {
+    auto importH = drv<CUresult (*)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType)>(
+        "cuMemImportFromShareableHandle");
+    auto reserve = drv<CUresult (*)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long)>(
+        "cuMemAddressReserve");
+    auto map = drv<CUresult (*)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long)>(
+        "cuMemMap");
+    auto setAccess = drv<CUresult (*)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t)>("cuMemSetAccess");
+    CUmemGenericAllocationHandle h;
+    cu_check(importH(&h, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR),
+             "cuMemImportFromShareableHandle");
+    CUdeviceptr va = 0;
+    cu_check(reserve(&va, size, 0, 0, 0), "cuMemAddressReserve");
+    cu_check(map(va, size, 0, h, 0), "cuMemMap");
+    CUmemAccessDesc acc{};
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = dev;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    cu_check(setAccess(va, size, &acc, 1), "cuMemSetAccess");
+    return py::make_tuple((uint64_t)va, (uint64_t)h);
+  });
+  // Multicast object: rank 0 creates + exports; everyone imports, adds its device,
+  // binds its own physical allocation and maps the multicast VA.
+  m.def("mc_granularity", [](size_t nbytes, int ndev) {
+    auto gran = drv<CUresult (*)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags)>(
+        "cuMulticastGetGranularity");
+    CUmulticastObjectProp prop{};
+    prop.numDevices = ndev;
+    prop.size = nbytes;
+    prop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t g = 0;
+    cu_check(gran(&g, &prop, CU_MULTICAST_GRANULARITY_RECOMMENDED), "cuMulticastGetGranularity");
+    return g;
+  });
+  m.def("mc_create", [](size_t size, int ndev) {
+    auto create = drv<CUresult (*)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*)>("cuMulticastCreate");
+    auto exportH = drv<CUresult (*)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType,
+                                    unsigned long long)>("cuMemExportToShareableHandle");
+    CUmulticastObjectProp prop{};
+    prop.numDevices = ndev;
+    prop.size = size;
+    prop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    CUmemGenericAllocationHandle h;
+    cu_check(create(&h, &prop), "cuMulticastCreate");
+    int fd = -1;
+    cu_check(exportH(&fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0), "cuMemExportToShareableHandle(mc)");
+    return py::make_tuple((uint64_t)h, fd);
+  });
+  m.def("mc_import", [](int fd) {
+    auto importH = drv<CUresult (*)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType)>(
+        "cuMemImportFromShareableHandle");
+    CUmemGenericAllocationHandle h;
+    cu_check(importH(&h, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR),
+             "cuMemImportFromShareableHandle(mc)");
+    return (uint64_t)h;
+  });
+  m.def("mc_add_device", [](uint64_t mc, int dev) {
+    auto add = drv<CUresult (*)(CUmemGenericAllocationHandle, CUdevice)>("cuMulticastAddDevice");
+    cu_check(add((CUmemGenericAllocationHandle)mc, dev), "cuMulticastAddDevice");
+  });
+  m.def("mc_bind_and_map", [](uint64_t mc, uint64_t mem_handle, size_t size, int dev) {
+    auto bind = drv<CUresult (*)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t,
+                                 unsigned long long)>("cuMulticastBindMem");
+    auto reserve = drv<CUresult (*)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long)>(
+        "cuMemAddressReserve");
+    auto map = drv<CUresult (*)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long)>(
+        "cuMemMap");
+    auto setAccess = drv<CUresult (*)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t)>("cuMemSetAccess");
+    cu_check(bind((CUmemGenericAllocationHandle)mc, 0, (CUmemGenericAllocationHandle)mem_handle, 0, size, 0),
+             "cuMulticastBindMem");
+    CUdeviceptr va = 0;
+    cu_check(reserve(&va, size, 0, 0, 0), "cuMemAddressReserve(mc)");
+    cu_check(map(va, size, 0, (CUmemGenericAllocationHandle)mc, 0), "cuMemMap(mc)");
+    CUmemAccessDesc acc{};
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = dev;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    cu_check(setAccess(va, size, &acc, 1), "cuMemSetAccess(mc)");
+    return (uint64_t)va;
+  });
+
+  // ---- kernels -------------------------------------------------------------------
+  m.def(
+      "push",
+      [](uint64_t src, uint64_t dst, uint64_t dst_scales, uint64_t n, float scale, uint64_t flag, uint32_t flag_value,
+         uint64_t done_counter, int mode, int blocks, bool use_bulk, uint64_t stream) {
+        PushArgs a{};
+        a.src = P<const void>(src);
+        a.dst = P<void>(dst);
+        a.dst_scales = P<void>(dst_scales);
+        a.n = n;
+        a.scale = scale;
+        a.flag = P<uint32_t>(flag);
+        a.flag_value = flag_value;
+        a.done_counter = P<uint32_t>(done_counter);
+        check(fedk_launch_push(&a, mode, blocks, use_bulk ? 1 : 0, (cudaStream_t)(uintptr_t)stream), "fed_push launch");
+      },
+      py::arg("src"), py::arg("dst"), py::arg("dst_scales"), py::arg("n"), py::arg("scale"), py::arg("flag"),
+      py::arg("flag_value"), py::arg("done_counter"), py::arg("mode"), py::arg("blocks"), py::arg("use_bulk"),
+      py::arg("stream"));
+  m.def(
+      "unpack",
+      [](uint64_t src, uint64_t dst, uint64_t scales, uint64_t n, float scale, uint64_t flag, uint32_t flag_value,
+         uint64_t done_counter, uint64_t credit, uint64_t credit_value, uint64_t status, long long timeout_cycles,
+         int mode, int blocks, uint64_t stream) {
+        PushArgs a{};
+        a.src = P<const void>(src);
+        a.dst = P<void>(dst);
+        a.dst_scales = P<void>(scales);
+        a.n = n;
+        a.scale = scale;
+        a.flag = P<uint32_t>(flag);
+        a.flag_value = flag_value;
+        a.done_counter = P<uint32_t>(done_counter);
+        a.credit = P<unsigned long long>(credit);
+        a.credit_value = credit_value;
+        a.status = P<uint32_t>(status);
+        a.timeout_cycles = timeout_cycles;
+        check(fedk_launch_unpack(&a, mode, blocks, (cudaStream_t)(uintptr_t)stream), "fed_unpack launch");
+      },
+      py::arg("src"), py::arg("dst"), py::arg("scales"), py::arg("n"), py::arg("scale"), py::arg("flag"),
+      py::arg("flag_value"), py::arg("done_counter"), py::arg("credit"), py::arg("credit_value"), py::arg("status"),
+      py::arg("timeout_cycles"), py::arg("mode"), py::arg("blocks"), py::arg("stream"));
+
+  m.def(
+      "aggregate",
+      [](const std::vector<uint64_t>& in, const std::vector<uint64_t>& out, const std::vector<uint64_t>& out_scales,
+         uint64_t mc_in, uint64_t mc_out, uint64_t master, uint64_t mom, uint64_t var, uint64_t shard_start,
+         uint64_t shard_len, int my_rank, int kind, bool in_fp32, bool out_fp8, const std::vector<float>& weights,
+         float lr, float momentum, float weight_decay, float beta1, float beta2, float eps, float bias_c1,
+         float bias_c2, uint64_t sig, const std::vector<uint64_t>& sig_peers, uint32_t epoch, uint64_t status,
+         long long timeout_cycles, int blocks, uint64_t stream) {
+        AggArgs a{};
+        fill_peers(a.in, in);
+        fill_peers(a.out, out);
+        fill_peers(a.out_scales, out_scales);
+        a.mc_in = P<void>(mc_in);
+        a.mc_out = P<void>(mc_out);
+        a.master = P<float>(master);
+        a.mom = P<float>(mom);
+        a.var = P<float>(var);
+        a.shard_start = shard_start;
+        a.shard_len = shard_len;
+        a.n_parties = (int)in.size();
+        a.my_rank = my_rank;
+        a.kind = kind;
+        a.in_fp32 = in_fp32;
+        a.out_fp8 = out_fp8;
+        for (int i = 0; i < kMaxParties; ++i) a.w[i] = i < (int)weights.size() ? weights[i] : 0.f;
+        a.lr = lr;
+        a.momentum = momentum;
+        a.weight_decay = weight_decay;
+        a.beta1 = beta1;
+        a.beta2 = beta2;
+        a.eps = eps;
+        a.bias_c1 = bias_c1;
+        a.bias_c2 = bias_c2;
+        a.sig = P<uint32_t>(sig);
+        fill_peers(a.sig_peers, sig_peers);
+        a.epoch = epoch;
+        a.status = P<uint32_t>(status);
+        a.timeout_cycles = timeout_cycles;
+        check(fedk_launch_aggregate(&a, blocks, (cudaStream_t)(uintptr_t)stream), "fed_aggregate launch");
+      },
+      py::arg("inputs"), py::arg("outputs"), py::arg("out_scales"), py::arg("mc_in"), py::arg("mc_out"),
+      py::arg("master"), py::arg("mom"), py::arg("var"), py::arg("shard_start"), py::arg("shard_len"),
+      py::arg("my_rank"), py::arg("kind"), py::arg("in_fp32"), py::arg("out_fp8"), py::arg("weights"), py::arg("lr"),
+      py::arg("momentum"), py::arg("weight_decay"), py::arg("beta1"), py::arg("beta2"), py::arg("eps"),
+      py::arg("bias_c1"), py::arg("bias_c2"), py::arg("sig"), py::arg("sig_peers"), py::arg("epoch"),
+      py::arg("status"), py::arg("timeout_cycles"), py::arg("blocks"), py::arg("stream"));
+
+  m.def(
+      "barrier",
+      [](int n_parties, int my_rank, uint64_t sig, const std::vector<uint64_t>& sig_peers, uint32_t epoch,
+         uint64_t status, long long timeout_cycles, uint64_t stream) {
+        AggArgs a{};
+        a.n_parties = n_parties;
+        a.my_rank = my_rank;
+        a.sig = P<uint32_t>(sig);
+        fill_peers(a.sig_peers, sig_peers);
+        a.epoch = epoch;
+        a.status = P<uint32_t>(status);
+        a.timeout_cycles = timeout_cycles;
+        check(fedk_launch_barrier(&a, (cudaStream_t)(uintptr_t)stream), "fed_barrier launch");
+      },
+      py::arg("n_parties"), py::arg("my_rank"), py::arg("sig"), py::arg("sig_peers"), py::arg("epoch"),
+      py::arg("status"), py::arg("timeout_cycles"), py::arg("stream"));
+
+  m.def(
+      "local_sgd",
+      [](uint64_t w, uint64_t g, uint64_t mom, uint64_t n, float lr, float momentum, float weight_decay,
+         float grad_scale, bool zero_grad, int blocks, uint64_t stream) {
+        LocalSgdArgs a{};
+        a.w = P<__nv_bfloat16>(w);
+        a.g = P<__nv_bfloat16>(g);
+        a.mom = P<float>(mom);
+        a.n = n;
+        a.lr = lr;
+        a.momentum = momentum;
+        a.weight_decay = weight_decay;
+        a.grad_scale = grad_scale;
+        a.zero_grad = zero_grad ? 1 : 0;
+        check(fedk_launch_local_sgd(&a, blocks, (cudaStream_t)(uintptr_t)stream), "fed_local_sgd launch");
+      },
+      py::arg("w"), py::arg("g"), py::arg("mom"), py::arg("n"), py::arg("lr"), py::arg("momentum"),
+      py::arg("weight_decay"), py::arg("grad_scale"), py::arg("zero_grad"), py::arg("blocks"), py::arg("stream"));
+}

@@ -1,0 +1,82 @@
+// Argument blocks shared by the kernels (.cu) and the Python bindings.
+#pragma once
+#include "common.cuh"
+
+namespace fedk {
+
+enum PushMode : int {
+  kCopy = 0,         // byte copy
+  kF32ToBF16 = 1,    // cast (x * scale)
+  kBF16ToFP8 = 2,    // block-scaled e4m3, one UE8M0 scale byte per 32 elements
+  kBF16Scale = 3,    // bf16 * scale -> bf16
+  kFP8ToBF16 = 4,    // unpack of mode 2
+  kBF16ToF32 = 5,    // unpack of mode 1
+};
+
+struct PushArgs {
+  const void* src;
+  void* dst;
+  void* dst_scales;         // mode 2: peer scales region; mode 4: local scales region (src side)
+  unsigned long long n;     // bytes for kCopy, elements otherwise
+  float scale;
+  uint32_t* flag;           // push: peer flag (release-stored at the end); unpack: local flag (acquired first)
+  uint32_t flag_value;
+  uint32_t* done_counter;   // local, zero between launches
+  unsigned long long* credit;  // unpack: producer's credit word in peer memory (may be null)
+  unsigned long long credit_value;
+  uint32_t* status;         // local error word (timeout)
+  long long timeout_cycles;
+};
+
+enum AggKind : int {
+  kAvg = 0,        // w <- mean_i x_i
+  kFedAvgM = 1,    // d = master - mean x ; m = mu m + d ; master -= lr m
+  kSgdGrad = 2,    // g = mean x + wd master ; m = mu m + g ; master -= lr m
+  kAdamGrad = 3,   // AdamW on g = mean x
+  kFedAdam = 4,    // AdamW on d = master - mean x
+};
+
+struct AggArgs {
+  PeerPtrs in;             // contribution buffers of every party (peer-mapped)
+  PeerPtrs out;            // weight buffers of every party (may alias `in`)
+  PeerPtrs out_scales;     // fp8 output: UE8M0 scale bytes of every party
+  void* mc_in;             // multicast alias of `in`  (nullptr -> P2P loads)
+  void* mc_out;            // multicast alias of `out` (nullptr -> P2P stores)
+  float* master;           // local fp32 master shard, indexed from 0
+  float* mom;              // local fp32 first moment shard
+  float* var;              // local fp32 second moment shard (Adam)
+  unsigned long long shard_start;  // elements, multiple of 32
+  unsigned long long shard_len;    // elements, multiple of 8 (32 for fp8 out)
+  int n_parties;
+  int my_rank;
+  int kind;
+  int in_fp32;             // contributions are fp32 (else bf16)
+  int out_fp8;             // write block-scaled e4m3 (else bf16)
+  float w[kMaxParties];    // aggregation weights (1/N or n_k/n)
+  float lr, momentum, weight_decay, beta1, beta2, eps, bias_c1, bias_c2;
+  uint32_t* sig;           // my signal pad
+  PeerPtrs sig_peers;      // every party's signal pad
+  uint32_t epoch;          // this launch uses epoch+1 (entry) and epoch+2 (exit)
+  uint32_t* status;
+  long long timeout_cycles;
+};
+
+struct LocalSgdArgs {
+  __nv_bfloat16* w;
+  __nv_bfloat16* g;
+  float* mom;
+  unsigned long long n;  // multiple of 8
+  float lr, momentum, weight_decay, grad_scale;
+  int zero_grad;
+};
+
+
+extern "C" {
+cudaError_t fedk_launch_push(const PushArgs* a, int mode, int blocks, int use_bulk, cudaStream_t stream);
+cudaError_t fedk_launch_unpack(const PushArgs* a, int mode, int blocks, cudaStream_t stream);
+cudaError_t fedk_launch_aggregate(const AggArgs* a, int blocks, cudaStream_t stream);
+cudaError_t fedk_launch_barrier(const AggArgs* a, cudaStream_t stream);
+cudaError_t fedk_launch_local_sgd(const LocalSgdArgs* a, int blocks, cudaStream_t stream);
+}
+
+}  // namespace fedk

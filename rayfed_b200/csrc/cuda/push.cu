@@ -1,0 +1,356 @@
+// K1 fed_push / K4 fed_unpack — the cross-party object push, on the device.
+//
+// Replaces the reference hot path  D2H -> cloudpickle -> protobuf -> HTTP/2 ->
+// event table -> unpickle -> H2D  (fed/proxy/grpc/grpc_proxy.py:193-220 sender,
+// :272-342 receiver) with ONE kernel on the owner party's GPU that
+// reads the tensor, optionally casts / scales / block-quantises it ("serialize")
+// and stores it straight into the consumer party's receive arena in *peer HBM*
+// over NVLink, then publishes a release flag.  The consumer's fed_unpack kernel
+// acquires the flag on its own stream (K4: the wait is on the device, the host
+// never blocks), undoes the wire format into the destination tensor and returns
+// flow-control credit to the producer with a peer store.
+//
+//   fed_push_kernel        SM-issued 16-byte vector stores (all sizes, all modes)
+//   fed_push_bulk_kernel   cp.async.bulk (TMA engine) gmem->smem->peer gmem,
+//                          mbarrier pipelined; plain-copy mode, large messages
+//   fed_unpack_kernel      flag acquire + unpack + credit return
+#include "kernels.h"
+
+namespace fedk {
+
+// Grid-wide "last CTA publishes" epilogue.
+__device__ __forceinline__ void publish_when_grid_done(const PushArgs& a, bool is_unpack) {
+  fence_acq_rel_sys();  // my payload stores are visible before I count myself done
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned prev = atomicAdd(a.done_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *a.done_counter = 0;  // re-arm for the next launch on this stream
+      fence_acq_rel_sys();
+      if (!is_unpack) {
+        if (a.flag) st_release_sys_u32(a.flag, a.flag_value);
+      } else {
+        if (a.credit) st_release_sys_u64(a.credit, a.credit_value);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t ue8m0_from_amax(float amax) {
+  // smallest power of two s with amax / s <= 448 (e4m3 max)
+  float r = amax * (1.0f / 448.0f);
+  uint32_t bits = __float_as_uint(r);
+  uint32_t e = (bits >> 23) & 0xffu;
+  if (bits & 0x7fffffu) e += 1;
+  e = e < 1u ? 1u : (e > 253u ? 253u : e);
+  return e;
+}
+__device__ __forceinline__ float pow2_from_biased(uint32_t e) { return __uint_as_float(e << 23); }
+
+__device__ __forceinline__ uint32_t quant4_e4m3(float a, float b, float c, float d) {
+  uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+
+__device__ __forceinline__ void dequant4_e4m3(uint32_t w, float s, float* out) {
+  __half2_raw lo = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w & 0xffffu), __NV_E4M3);
+  __half2_raw hi = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w >> 16), __NV_E4M3);
+  float2 f0 = __half22float2(*reinterpret_cast<__half2*>(&lo));
+  float2 f1 = __half22float2(*reinterpret_cast<__half2*>(&hi));
+  out[0] = f0.x * s;
+  out[1] = f0.y * s;
+  out[2] = f1.x * s;
+  out[3] = f1.y * s;
+}
+
+template <bool kIsUnpack>
+__global__ void __launch_bounds__(512) fed_push_kernel(PushArgs a, int mode) {
+  if (kIsUnpack) {
+    // K4: device-side receive barrier. Only one lane polls; the CTA parks on bar.sync.
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+      ok = spin_wait_ge(a.flag, a.flag_value, a.timeout_cycles) ? 1 : 0;
+      if (!ok && a.status) atomicExch(a.status, 1u);
+    }
+    __syncthreads();
+  }
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+
+  if (mode == kCopy) {
+    const size_t nvec = a.n >> 4;
+    const uint4* s = reinterpret_cast<const uint4*>(a.src);
+    uint4* d = reinterpret_cast<uint4*>(a.dst);
+    size_t i = tid;
+    // 4 independent 16 B requests in flight per thread before the first store
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+      uint4 v0 = kIsUnpack ? ld_v4(s + i) : ld_stream_v4(s + i);
+      uint4 v1 = kIsUnpack ? ld_v4(s + i + stride) : ld_stream_v4(s + i + stride);
+      uint4 v2 = kIsUnpack ? ld_v4(s + i + 2 * stride) : ld_stream_v4(s + i + 2 * stride);
+      uint4 v3 = kIsUnpack ? ld_v4(s + i + 3 * stride) : ld_stream_v4(s + i + 3 * stride);
+      st_v4(d + i, v0);
+      st_v4(d + i + stride, v1);
+      st_v4(d + i + 2 * stride, v2);
+      st_v4(d + i + 3 * stride, v3);
+    }
+    for (; i < nvec; i += stride) st_v4(d + i, kIsUnpack ? ld_v4(s + i) : ld_stream_v4(s + i));
+    if (tid == 0) {
+      const unsigned char* sb = reinterpret_cast<const unsigned char*>(a.src);
+      unsigned char* db = reinterpret_cast<unsigned char*>(a.dst);
+      for (size_t b = nvec << 4; b < a.n; ++b) db[b] = sb[b];
+    }
+  } else if (mode == kF32ToBF16) {
+    // 8 floats (2 x 16 B loads) -> 8 bf16 (one 16 B store)
+    const size_t nvec = a.n >> 3;
+    const uint4* s = reinterpret_cast<const uint4*>(a.src);
+    uint4* d = reinterpret_cast<uint4*>(a.dst);
+    const float sc = a.scale;
+    for (size_t i = tid; i < nvec; i += stride) {
+      uint4 x = ld_stream_v4(s + 2 * i), y = ld_stream_v4(s + 2 * i + 1);
+      uint4 o;
+      o.x = pack_bf16x2(__uint_as_float(x.x) * sc, __uint_as_float(x.y) * sc);
+      o.y = pack_bf16x2(__uint_as_float(x.z) * sc, __uint_as_float(x.w) * sc);
+      o.z = pack_bf16x2(__uint_as_float(y.x) * sc, __uint_as_float(y.y) * sc);
+      o.w = pack_bf16x2(__uint_as_float(y.z) * sc, __uint_as_float(y.w) * sc);
+      st_v4(d + i, o);
+    }
+    if (tid == 0) {
+      const float* sf = reinterpret_cast<const float*>(a.src);
+      __nv_bfloat16* db = reinterpret_cast<__nv_bfloat16*>(a.dst);
+      for (size_t e = nvec << 3; e < a.n; ++e) db[e] = __float2bfloat16(sf[e] * sc);
+    }
+  } else if (mode == kBF16ToF32) {
+    const size_t nvec = a.n >> 3;
+    const uint4* s = reinterpret_cast<const uint4*>(a.src);
+    uint4* d = reinterpret_cast<uint4*>(a.dst);
+    const float sc = a.scale;
+    for (size_t i = tid; i < nvec; i += stride) {
+      uint4 x = ld_v4(s + i);
+      uint4 o0, o1;
+      o0.x = __float_as_uint(bf16_lo(x.x) * sc);
+      o0.y = __float_as_uint(bf16_hi(x.x) * sc);
+      o0.z = __float_as_uint(bf16_lo(x.y) * sc);
+      o0.w = __float_as_uint(bf16_hi(x.y) * sc);
+      o1.x = __float_as_uint(bf16_lo(x.z) * sc);
+      o1.y = __float_as_uint(bf16_hi(x.z) * sc);
+      o1.z = __float_as_uint(bf16_lo(x.w) * sc);
+      o1.w = __float_as_uint(bf16_hi(x.w) * sc);
+      st_v4(d + 2 * i, o0);
+      st_v4(d + 2 * i + 1, o1);
+    }
+    if (tid == 0) {
+      const __nv_bfloat16* sb = reinterpret_cast<const __nv_bfloat16*>(a.src);
+      float* df = reinterpret_cast<float*>(a.dst);
+      for (size_t e = nvec << 3; e < a.n; ++e) df[e] = __bfloat162float(sb[e]) * sc;
+    }
+  } else if (mode == kBF16Scale) {
+    const size_t nvec = a.n >> 3;
+    const uint4* s = reinterpret_cast<const uint4*>(a.src);
+    uint4* d = reinterpret_cast<uint4*>(a.dst);
+    const float sc = a.scale;
+    for (size_t i = tid; i < nvec; i += stride) {
+      uint4 x = ld_stream_v4(s + i);
+      uint4 o;
+      o.x = pack_bf16x2(bf16_lo(x.x) * sc, bf16_hi(x.x) * sc);
+      o.y = pack_bf16x2(bf16_lo(x.y) * sc, bf16_hi(x.y) * sc);
+      o.z = pack_bf16x2(bf16_lo(x.z) * sc, bf16_hi(x.z) * sc);
+      o.w = pack_bf16x2(bf16_lo(x.w) * sc, bf16_hi(x.w) * sc);
+      st_v4(d + i, o);
+    }
+    if (tid == 0) {
+      const __nv_bfloat16* sb = reinterpret_cast<const __nv_bfloat16*>(a.src);
+      __nv_bfloat16* db = reinterpret_cast<__nv_bfloat16*>(a.dst);
+      for (size_t e = nvec << 3; e < a.n; ++e) db[e] = __float2bfloat16(__bfloat162float(sb[e]) * sc);
+    }
+  } else if (mode == kBF16ToFP8) {
+    // n % 32 == 0 (host guarantees). One lane = 8 elements; 4 lanes = one scale block.
+    const size_t nvec = a.n >> 3;
+    const uint4* s = reinterpret_cast<const uint4*>(a.src);
+    uint2* d = reinterpret_cast<uint2*>(a.dst);
+    unsigned char* sc_out = reinterpret_cast<unsigned char*>(a.dst_scales);
+    const float pre = a.scale;
+    const size_t nvec_warp_rounded = (nvec + 31) & ~(size_t)31;
+    for (size_t i = tid; i < nvec_warp_rounded; i += stride) {
+      const bool live = i < nvec;
+      uint4 x = live ? ld_stream_v4(s + i) : make_uint4(0, 0, 0, 0);
+      float f[8] = {bf16_lo(x.x) * pre, bf16_hi(x.x) * pre, bf16_lo(x.y) * pre, bf16_hi(x.y) * pre,
+                    bf16_lo(x.z) * pre, bf16_hi(x.z) * pre, bf16_lo(x.w) * pre, bf16_hi(x.w) * pre};
+      float amax = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(f[k]));
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+      const uint32_t e = ue8m0_from_amax(amax);
+      const float inv = pow2_from_biased(254u - e);  // 1 / 2^(e-127)
+      if (live) {
+        uint2 o;
+        o.x = quant4_e4m3(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
+        o.y = quant4_e4m3(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
+        st_v2(d + i, o);
+      }
+      // gather the warp's 8 scale bytes into one 8-byte peer store
+      const int lane = threadIdx.x & 31;
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lo |= (__shfl_sync(0xffffffffu, e, k * 4) & 0xffu) << (8 * k);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) hi |= (__shfl_sync(0xffffffffu, e, 16 + k * 4) & 0xffu) << (8 * k);
+      const size_t warp_first = i - lane;
+      if (lane == 0) {
+        const size_t blk0 = warp_first >> 2;
+        const size_t nblk = a.n >> 5;
+        if (blk0 + 8 <= nblk) {
+          st_v2(sc_out + blk0, make_uint2(lo, hi));
+        } else {
+          for (size_t b = blk0; b < nblk; ++b) {
+            uint32_t k = (uint32_t)(b - blk0);
+            sc_out[b] = (unsigned char)((k < 4 ? (lo >> (8 * k)) : (hi >> (8 * (k - 4)))) & 0xffu);
+          }
+        }
+      }
+    }
+  } else if (mode == kFP8ToBF16) {
+    const size_t nvec = a.n >> 3;
+    const uint2* s = reinterpret_cast<const uint2*>(a.src);
+    uint4* d = reinterpret_cast<uint4*>(a.dst);
+    const unsigned char* sc_in = reinterpret_cast<const unsigned char*>(a.dst_scales);
+    const float post = a.scale;
+    for (size_t i = tid; i < nvec; i += stride) {
+      uint2 x = ld_v2(s + i);
+      const float sc = pow2_from_biased((uint32_t)sc_in[i >> 2]) * post;
+      float f[8];
+      dequant4_e4m3(x.x, sc, f);
+      dequant4_e4m3(x.y, sc, f + 4);
+      uint4 o;
+      o.x = pack_bf16x2(f[0], f[1]);
+      o.y = pack_bf16x2(f[2], f[3]);
+      o.z = pack_bf16x2(f[4], f[5]);
+      o.w = pack_bf16x2(f[6], f[7]);
+      st_v4(d + i, o);
+    }
+  }
+  publish_when_grid_done(a, kIsUnpack);
+}
+
+// ---------------------------------------------------------------------------
+// TMA-engine variant: cp.async.bulk global->shared (mbarrier complete_tx) then
+// cp.async.bulk shared->peer global (bulk_group). One elected thread per CTA
+// drives a kStages-deep ring; the SMs issue no per-byte instructions at all.
+constexpr int kBulkStages = 4;
+constexpr int kBulkChunk = 32 * 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(128) fed_push_bulk_kernel(PushArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full[kBulkStages];
+  const size_t nbytes = a.n;
+  const size_t nchunks = (nbytes + kBulkChunk - 1) / kBulkChunk;
+  const char* src = reinterpret_cast<const char*>(a.src);
+  char* dst = reinterpret_cast<char*>(a.dst);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBulkStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    auto chunk_bytes = [&](size_t c) -> uint32_t {
+      size_t off = c * (size_t)kBulkChunk;
+      size_t rem = nbytes - off;
+      return (uint32_t)(rem < (size_t)kBulkChunk ? rem : (size_t)kBulkChunk);
+    };
+    // my chunks: blockIdx.x, +gridDim.x, ...
+    size_t my_n = nchunks > blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // prologue: fill the ring
+    for (size_t it = 0; it < my_n && it < (size_t)kBulkStages; ++it) {
+      size_t c = blockIdx.x + it * gridDim.x;
+      uint32_t b = chunk_bytes(c);
+      mbar_expect_tx(&full[it], b);
+      bulk_g2s(smem + it * kBulkChunk, src + c * (size_t)kBulkChunk, b, &full[it]);
+    }
+    for (size_t it = 0; it < my_n; ++it) {
+      const int s = (int)(it % kBulkStages);
+      const uint32_t parity = (uint32_t)((it / kBulkStages) & 1);
+      size_t c = blockIdx.x + it * gridDim.x;
+      uint32_t b = chunk_bytes(c);
+      mbar_wait(&full[s], parity);
+      bulk_s2g(dst + c * (size_t)kBulkChunk, smem + s * kBulkChunk, b);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      // refill the stage whose store was issued one iteration ago
+      if (it >= 1) {
+        size_t nxt = it - 1 + kBulkStages;
+        if (nxt < my_n) {
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          const int ps = (int)((it - 1) % kBulkStages);
+          size_t c2 = blockIdx.x + nxt * gridDim.x;
+          uint32_t b2 = chunk_bytes(c2);
+          mbar_expect_tx(&full[ps], b2);
+          bulk_g2s(smem + ps * kBulkChunk, src + c2 * (size_t)kBulkChunk, b2, &full[ps]);
+        }
+      }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // writes complete, not just smem reads
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  publish_when_grid_done(a, false);
+}
+
+// ---------------------------------------------------------------------------
+extern "C" {
+
+cudaError_t fedk_launch_push(const PushArgs* a, int mode, int blocks, int use_bulk, cudaStream_t stream) {
+  if (use_bulk && mode == kCopy) {
+    const int smem = kBulkStages * kBulkChunk;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(fed_push_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    fed_push_bulk_kernel<<<blocks, 128, smem, stream>>>(*a);
+  } else {
+    fed_push_kernel<false><<<blocks, 512, 0, stream>>>(*a, mode);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t fedk_launch_unpack(const PushArgs* a, int mode, int blocks, cudaStream_t stream) {
+  fed_push_kernel<true><<<blocks, 512, 0, stream>>>(*a, mode);
+  return cudaGetLastError();
+}
+
+}  // extern "C"
+
+}  // namespace fedk

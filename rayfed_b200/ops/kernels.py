@@ -1,0 +1,164 @@
+"""Thin, allocation-free launch wrappers over ``_fedcuda``.
+
+Pointers are passed as integers; the caller owns lifetime and stream ordering.
+``launch_counter`` counts every kernel launched through this module (bench.py
+reports it as ``gpu_launches``).
+"""
+from __future__ import annotations
+
+import importlib
+import threading
+from typing import Optional, Sequence
+
+from .. import _build
+
+MODE_COPY = 0
+MODE_F32_TO_BF16 = 1
+MODE_BF16_TO_FP8 = 2
+MODE_BF16_SCALE = 3
+MODE_FP8_TO_BF16 = 4
+MODE_BF16_TO_F32 = 5
+
+AGG_AVG = 0
+AGG_FEDAVGM = 1
+AGG_SGD = 2
+AGG_ADAM = 3
+AGG_FEDADAM = 4
+
+_ext = None
+_ext_lock = threading.Lock()
+_sm_count = {}
+
+
+class _LaunchCounter:
+    def __init__(self):
+        self.count = 0
+        self.by_kernel = {}
+
+    def add(self, name: str, n: int = 1):
+        self.count += n
+        self.by_kernel[name] = self.by_kernel.get(name, 0) + n
+
+    def reset(self):
+        self.count = 0
+        self.by_kernel = {}
+
+
+launch_counter = _LaunchCounter()
+
+
+def cuda_ext():
+    """Load (building in-tree if needed) the CUDA extension; raise loudly if absent."""
+    global _ext
+    if _ext is None:
+        with _ext_lock:
+            if _ext is None:
+                _build.ensure_cuda()
+                _ext = importlib.import_module("rayfed_b200._fedcuda")
+    return _ext
+
+
+def sm_count(device_index: int = 0) -> int:
+    if device_index not in _sm_count:
+        _sm_count[device_index] = cuda_ext().sm_count(device_index)
+    return _sm_count[device_index]
+
+
+def _stream_handle(stream) -> int:
+    if stream is None:
+        import torch
+
+        return torch.cuda.current_stream().cuda_stream
+    if isinstance(stream, int):
+        return stream
+    return stream.cuda_stream
+
+
+def _blocks_for(nbytes: int, device_index: int, bytes_per_cta: int = 64 * 1024, max_per_sm: int = 2) -> int:
+    sms = sm_count(device_index)
+    want = max(1, (nbytes + bytes_per_cta - 1) // bytes_per_cta)
+    return int(min(want, sms * max_per_sm))
+
+
+def push(src_ptr: int, dst_ptr: int, n: int, *, mode: int = MODE_COPY, scale: float = 1.0, dst_scales_ptr: int = 0,
+         flag_ptr: int = 0, flag_value: int = 0, done_counter_ptr: int, stream=None, device_index: int = 0,
+         use_bulk: Optional[bool] = None, blocks: Optional[int] = None) -> None:
+    """K1. ``n`` is bytes for MODE_COPY, elements otherwise."""
+    nbytes = n if mode == MODE_COPY else n * (4 if mode == MODE_F32_TO_BF16 else 2)
+    if use_bulk is None:
+        use_bulk = mode == MODE_COPY and nbytes >= (1 << 20) and nbytes % 16 == 0 and _bulk_default()
+    if blocks is None:
+        blocks = sm_count(device_index) if use_bulk else _blocks_for(nbytes, device_index)
+        if use_bulk:
+            blocks = int(min(blocks, max(1, (nbytes + 32 * 1024 - 1) // (32 * 1024))))
+    cuda_ext().push(src_ptr, dst_ptr, dst_scales_ptr, n, float(scale), flag_ptr, flag_value, done_counter_ptr, mode,
+                    blocks, bool(use_bulk), _stream_handle(stream))
+    launch_counter.add("fed_push_bulk" if use_bulk else "fed_push")
+
+
+_BULK_DEFAULT = None
+
+
+def _bulk_default() -> bool:
+    global _BULK_DEFAULT
+    if _BULK_DEFAULT is None:
+        import os
+
+        _BULK_DEFAULT = os.environ.get("RAYFED_B200_PUSH_BULK", "0") == "1"
+    return _BULK_DEFAULT
+
+
+def unpack(src_ptr: int, dst_ptr: int, n: int, *, mode: int = MODE_COPY, scale: float = 1.0, scales_ptr: int = 0,
+           flag_ptr: int, flag_value: int, done_counter_ptr: int, credit_ptr: int = 0, credit_value: int = 0,
+           status_ptr: int = 0, timeout_cycles: int = 0, stream=None, device_index: int = 0,
+           blocks: Optional[int] = None) -> None:
+    """K4 + unpack: wait for the flag on the device, undo the wire format, return credit."""
+    nbytes = n if mode == MODE_COPY else n * 2
+    if blocks is None:
+        blocks = _blocks_for(nbytes, device_index)
+    cuda_ext().unpack(src_ptr, dst_ptr, scales_ptr, n, float(scale), flag_ptr, flag_value, done_counter_ptr,
+                      credit_ptr, credit_value, status_ptr, timeout_cycles, mode, blocks, _stream_handle(stream))
+    launch_counter.add("fed_unpack")
+
+
+def aggregate(*, inputs: Sequence[int], outputs: Sequence[int], my_rank: int, shard_start: int, shard_len: int,
+              kind: int = AGG_AVG, weights: Optional[Sequence[float]] = None, in_fp32: bool = False,
+              out_fp8: bool = False, out_scales: Sequence[int] = (), mc_in: int = 0, mc_out: int = 0,
+              master_ptr: int = 0, mom_ptr: int = 0, var_ptr: int = 0, lr: float = 1.0, momentum: float = 0.0,
+              weight_decay: float = 0.0, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, step: int = 1,
+              sig_ptr: int, sig_peers: Sequence[int], epoch: int, status_ptr: int = 0, timeout_cycles: int = 0,
+              stream=None, device_index: int = 0, blocks: Optional[int] = None) -> None:
+    """K2/K3. Every party launches this with the same arguments (SPMD)."""
+    n = len(inputs)
+    if weights is None:
+        weights = [1.0 / n] * n
+    if blocks is None:
+        blocks = int(min(sm_count(device_index), max(1, (shard_len // 8 + 511) // 512)))
+    bias_c1 = 1.0 / (1.0 - beta1 ** step) if beta1 < 1.0 else 1.0
+    bias_c2 = 1.0 / (1.0 - beta2 ** step) if beta2 < 1.0 else 1.0
+    cuda_ext().aggregate(list(inputs), list(outputs), list(out_scales), mc_in, mc_out, master_ptr, mom_ptr, var_ptr,
+                         shard_start, shard_len, my_rank, kind, in_fp32, out_fp8, [float(w) for w in weights],
+                         float(lr), float(momentum), float(weight_decay), float(beta1), float(beta2), float(eps),
+                         float(bias_c1), float(bias_c2), sig_ptr, list(sig_peers), epoch, status_ptr, timeout_cycles,
+                         blocks, _stream_handle(stream))
+    launch_counter.add("fed_aggregate")
+
+
+def barrier(*, n_parties: int, my_rank: int, sig_ptr: int, sig_peers: Sequence[int], epoch: int, status_ptr: int = 0,
+            timeout_cycles: int = 0, stream=None) -> None:
+    """K5."""
+    cuda_ext().barrier(n_parties, my_rank, sig_ptr, list(sig_peers), epoch, status_ptr, timeout_cycles,
+                       _stream_handle(stream))
+    launch_counter.add("fed_barrier")
+
+
+def local_sgd(w_ptr: int, g_ptr: int, mom_ptr: int, n: int, *, lr: float, momentum: float = 0.0,
+              weight_decay: float = 0.0, grad_scale: float = 1.0, zero_grad: bool = True, stream=None,
+              device_index: int = 0, blocks: Optional[int] = None) -> None:
+    if n % 8:
+        raise ValueError("local_sgd needs a flat bucket whose length is a multiple of 8")
+    if blocks is None:
+        blocks = int(min(sm_count(device_index) * 2, max(1, (n // 8 + 511) // 512)))
+    cuda_ext().local_sgd(w_ptr, g_ptr, mom_ptr, n, float(lr), float(momentum), float(weight_decay),
+                         float(grad_scale), bool(zero_grad), blocks, _stream_handle(stream))
+    launch_counter.add("fed_local_sgd")

@@ -1,0 +1,219 @@
+"""Symmetric heap: the same buffer in every party, addressable by every party.
+
+This replaces "a TCP connection per peer" (SURVEY §5.8): after set-up a party
+holds a *device pointer* to each peer's copy of the buffer and kernels move data
+with plain loads/stores over NVLink.
+
+Backends
+--------
+``ipc``   cudaMalloc + cudaIpcGetMemHandle; the 64-byte handle travels over any
+          PartyGroup exchange.  Works wherever CUDA P2P works.  (default)
+``vmm``   cuMemCreate with a POSIX-fd handle, fds passed over a Unix socket
+          (SCM_RIGHTS), cuMemMap on every peer, and — when the device supports
+          it — a cuMulticast object bound to all copies, giving one *multicast*
+          address for ``multimem.ld_reduce`` / ``multimem.st`` (NVLS).
+"""
+from __future__ import annotations
+
+import array
+import os
+import pickle
+import socket
+import time
+from typing import List, Optional
+
+from ..ops.kernels import cuda_ext
+from .group import PartyGroup
+
+
+class _CudaArrayView:
+    """``__cuda_array_interface__`` shim so torch can wrap raw device memory."""
+
+    def __init__(self, ptr: int, nbytes: int, owner=None):
+        self._owner = owner
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,),
+            "typestr": "|u1",
+            "data": (ptr, False),
+            "version": 3,
+            "strides": None,
+        }
+
+
+class SymmetricBuffer:
+    def __init__(self, name: str, nbytes: int, local_ptr: int, peer_ptrs: List[int], rank: int,
+                 device_index: int, mc_ptr: int = 0, backend: str = "ipc"):
+        self.name = name
+        self.nbytes = nbytes
+        self.local_ptr = local_ptr
+        self.peer_ptrs = peer_ptrs  # party order; peer_ptrs[rank] == local_ptr
+        self.rank = rank
+        self.device_index = device_index
+        self.mc_ptr = mc_ptr
+        self.backend = backend
+        self._bytes_tensor = None
+
+    def bytes_tensor(self):
+        """uint8 torch view of the local copy."""
+        if self._bytes_tensor is None:
+            import torch
+
+            self._bytes_tensor = torch.as_tensor(
+                _CudaArrayView(self.local_ptr, self.nbytes, self), device=f"cuda:{self.device_index}"
+            )
+        return self._bytes_tensor
+
+    def tensor(self, dtype, numel: int, byte_offset: int = 0):
+        """Typed view ``[byte_offset, byte_offset + numel*itemsize)`` of the local copy."""
+        import torch
+
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        assert byte_offset % itemsize == 0 and byte_offset + numel * itemsize <= self.nbytes
+        return self.bytes_tensor()[byte_offset: byte_offset + numel * itemsize].view(dtype)
+
+    def ptrs(self, byte_offset: int = 0) -> List[int]:
+        return [p + byte_offset for p in self.peer_ptrs]
+
+
+class SymmetricHeap:
+    def __init__(self, group: PartyGroup, backend: Optional[str] = None):
+        self.group = group
+        self.backend = backend or os.environ.get("RAYFED_B200_SYMM_BACKEND", "ipc")
+        self._buffers = {}
+        self._ext = cuda_ext()
+        self._ext.set_device(group.device_index)
+        self.multicast_ok = False
+        self._vmm_info = None
+
+    # -- public -----------------------------------------------------------------
+    def alloc(self, name: str, nbytes: int, multicast: bool = False) -> SymmetricBuffer:
+        """Collective: every party calls with the same ``name`` and ``nbytes``."""
+        nbytes = (nbytes + 255) // 256 * 256
+        if self.backend == "vmm" or multicast:
+            try:
+                buf = self._alloc_vmm(name, nbytes, multicast)
+            except Exception as e:  # noqa: BLE001
+                if self.backend == "vmm":
+                    raise
+                import logging
+
+                logging.getLogger(__name__).warning(f"VMM/multicast allocation failed ({e}); using cudaIpc.")
+                # every party must take the same branch: agree on the outcome
+                buf = None
+            ok = self.group.all_gather(self.group.next_tag(f"symm-ok/{name}"), b"1" if buf is not None else b"0")
+            if all(x == b"1" for x in ok):
+                self._buffers[name] = buf
+                return buf
+        buf = self._alloc_ipc(name, nbytes)
+        self._buffers[name] = buf
+        return buf
+
+    def get(self, name: str) -> SymmetricBuffer:
+        return self._buffers[name]
+
+    # -- cudaIpc ------------------------------------------------------------------
+    def _alloc_ipc(self, name: str, nbytes: int) -> SymmetricBuffer:
+        g = self.group
+        ptr, handle = self._ext.ipc_alloc(nbytes, True)
+        self._ext.device_synchronize()
+        blobs = g.all_gather(g.next_tag(f"symm-ipc/{name}"), pickle.dumps((nbytes, handle, os.getpid())))
+        peers = []
+        for r, blob in enumerate(blobs):
+            if r == g.rank:
+                peers.append(ptr)
+                continue
+            pn, ph, ppid = pickle.loads(blob)
+            assert pn == nbytes, f"symmetric alloc size mismatch for {name}: {pn} vs {nbytes}"
+            if ppid == os.getpid():
+                raise RuntimeError("cudaIpc handles cannot be opened in the exporting process")
+            peers.append(self._ext.ipc_open(ph))
+        g.barrier(g.next_tag(f"symm-ipc-open/{name}"))
+        return SymmetricBuffer(name, nbytes, ptr, peers, g.rank, g.device_index, 0, "ipc")
+
+    # -- VMM + multicast ------------------------------------------------------------
+    def vmm_info(self) -> dict:
+        if self._vmm_info is None:
+            self._vmm_info = dict(self._ext.vmm_info(self.group.device_index))
+        return self._vmm_info
+
+    def _sock_path(self, party: str) -> str:
+        base = os.environ.get("RAYFED_B200_SOCK_DIR", "/tmp")
+        return os.path.join(base, f"rayfed_b200_fd_{os.getuid()}_{party}.sock")
+
+    def _exchange_fds(self, tag: str, fd: int) -> List[int]:
+        """All-gather one fd per party over Unix sockets (SCM_RIGHTS)."""
+        g = self.group
+        path = self._sock_path(g.me)
+        try:
+            os.unlink(path)
+        except FileNotFoundError:
+            pass
+        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        srv.bind(path)
+        srv.listen(g.size)
+        g.barrier(g.next_tag(f"fdsock/{tag}"))
+        # send my fd to every peer
+        for p in g.parties:
+            if p == g.me:
+                continue
+            c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            deadline = time.time() + 30
+            while True:
+                try:
+                    c.connect(self._sock_path(p))
+                    break
+                except (FileNotFoundError, ConnectionRefusedError):
+                    if time.time() > deadline:
+                        raise
+                    time.sleep(0.01)
+            socket.send_fds(c, [g.me.encode()], [fd])
+            c.close()
+        got = {}
+        while len(got) < g.size - 1:
+            conn, _ = srv.accept()
+            msg, fds, _, _ = socket.recv_fds(conn, 256, 1)
+            got[msg.decode()] = fds[0]
+            conn.close()
+        srv.close()
+        try:
+            os.unlink(path)
+        except FileNotFoundError:
+            pass
+        return [fd if p == g.me else got[p] for p in g.parties]
+
+    def _alloc_vmm(self, name: str, nbytes: int, multicast: bool) -> SymmetricBuffer:
+        g = self.group
+        info = self.vmm_info()
+        if not info.get("vmm") or not info.get("posix_fd"):
+            raise RuntimeError(f"CUDA VMM with POSIX fds is not supported here: {info}")
+        want_mc = multicast and bool(info.get("multicast")) and g.size > 1
+        size = nbytes
+        if want_mc:
+            gran = self._ext.mc_granularity(nbytes, g.size)
+            size = (nbytes + gran - 1) // gran * gran
+        ptr, fd, mapped, mem_handle = self._ext.vmm_alloc(size, g.device_index)
+        fds = self._exchange_fds(name, fd)
+        peers = []
+        for r, pfd in enumerate(fds):
+            if r == g.rank:
+                peers.append(ptr)
+            else:
+                va, _h = self._ext.vmm_import(pfd, mapped, g.device_index)
+                peers.append(va)
+                os.close(pfd)
+        mc_ptr = 0
+        if want_mc:
+            if g.rank == 0:
+                mc_handle, mc_fd = self._ext.mc_create(mapped, g.size)
+            else:
+                mc_handle, mc_fd = 0, -1
+            mc_fds = self._exchange_fds(name + "/mc", mc_fd if g.rank == 0 else fd)
+            if g.rank != 0:
+                mc_handle = self._ext.mc_import(mc_fds[0])
+            self._ext.mc_add_device(mc_handle, g.device_index)
+            g.barrier(g.next_tag(f"mc-added/{name}"))  # all devices added before any bind
+            mc_ptr = self._ext.mc_bind_and_map(mc_handle, mem_handle, mapped, g.device_index)
+            g.barrier(g.next_tag(f"mc-bound/{name}"))
+            self.multicast_ok = True
+        os.close(fd)
+        return SymmetricBuffer(name, mapped, ptr, peers, g.rank, g.device_index, mc_ptr, "vmm")
