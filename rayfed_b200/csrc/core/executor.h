@@ -328,8 +328,10 @@ class Executor : public std::enable_shared_from_this<Executor> {
         } else {
           py::list parts(res);
           if (parts.size() != n) {
-            throw py::value_error("task declared num_returns=" + std::to_string(n) + " but returned " +
-                                  std::to_string(parts.size()) + " values");
+            std::string msg = "task declared num_returns=" + std::to_string(n) + " but returned " +
+                              std::to_string(parts.size()) + " values";
+            PyErr_SetString(PyExc_ValueError, msg.c_str());
+            throw py::error_already_set();
           }
           for (size_t i = 0; i < n; ++i) t.outs[i]->set_value(parts[i]);
         }

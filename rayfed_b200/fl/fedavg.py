@@ -1,0 +1,268 @@
+"""FedAvg on the B200 path: fused local optimizer + fused cross-party aggregate."""
+from __future__ import annotations
+
+import logging
+from typing import Callable, List, Optional, Sequence
+
+import torch
+
+from ..ops import kernels as K
+from ..parallel.group import FedExchange, PartyGroup
+from ..parallel.symmetric import SymmetricHeap
+from .bucket import FlatBucket
+
+logger = logging.getLogger(__name__)
+
+_KINDS = {"fedavg": K.AGG_AVG, "fedavgm": K.AGG_FEDAVGM, "fedsgd": K.AGG_SGD, "adam": K.AGG_ADAM,
+          "fedadam": K.AGG_FEDADAM}
+
+
+def device_context(parties: Optional[Sequence[str]] = None, me: Optional[str] = None, device: Optional[str] = None):
+    """(group, heap, channel) of this party.
+
+    Inside a fed job this is the DeviceChannel that ``fed.init`` created for the
+    NVLink transport; stand-alone (tests, single party) a private one-party
+    context is built.
+    """
+    from ..proxy.nvlink import nvlink_proxy
+
+    ch = nvlink_proxy.current_channel()
+    if ch is not None:
+        return ch.group, ch.heap, ch
+    dev = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+    group = PartyGroup(list(parties or ["solo"]), me or (parties[0] if parties else "solo"), FedExchange(),
+                       device_index=dev.index or 0)
+    if group.size != 1:
+        raise RuntimeError("multi-party device_context needs the NVLink transport (fed.init with a device)")
+    return group, SymmetricHeap(group), None
+
+
+class LocalSGD:
+    """Fused SGD(+momentum, +wd) step on a :class:`FlatBucket`; clears grads in the same pass."""
+
+    def __init__(self, bucket: FlatBucket, lr: float, momentum: float = 0.9, weight_decay: float = 0.0):
+        assert bucket.dtype == torch.bfloat16, "the fused local optimizer works on bf16 buckets"
+        self.bucket = bucket
+        self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+        self.mom = torch.zeros(bucket.numel, dtype=torch.float32, device=bucket.flat_w.device)
+        self._dev = bucket.flat_w.device.index or 0
+
+    def step(self, grad_scale: float = 1.0, stream=None):
+        b = self.bucket
+        K.local_sgd(b.flat_w.data_ptr(), b.flat_g.data_ptr(), self.mom.data_ptr(), b.numel, lr=self.lr,
+                    momentum=self.momentum, weight_decay=self.weight_decay, grad_scale=grad_scale, zero_grad=True,
+                    stream=stream, device_index=self._dev)
+
+    def reset_momentum(self):
+        self.mom.zero_()
+
+
+class FedAggregator:
+    """One fused launch per round: all-reduce + scale + server optimizer + all-gather.
+
+    ``kind``:
+      ``fedavg``   w ← Σ wₖ·xₖ (xₖ = party k's weights)
+      ``fedavgm``  server momentum on the pseudo-gradient (master − mean)
+      ``fedsgd``   xₖ are gradients: SGD(+momentum, +wd) on the sharded fp32 master
+      ``adam``     xₖ are gradients: AdamW on the sharded master
+      ``fedadam``  AdamW on the pseudo-gradient
+    Optimizer state is sharded: each party keeps fp32 master/moments only for the
+    1/N of the elements it owns.
+    """
+
+    def __init__(self, bucket: FlatBucket, group: PartyGroup, channel=None, kind: str = "fedavg",
+                 weights: Optional[Sequence[float]] = None, lr: float = 1.0, momentum: float = 0.0,
+                 weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8, out_fp8: bool = False,
+                 grads: bool = False, use_multicast: Optional[bool] = None, timeout_s: float = 120.0):
+        self.bucket, self.group, self.channel = bucket, group, channel
+        self.kind = _KINDS[kind]
+        self.kind_name = kind
+        n = group.size
+        self.weights = list(weights) if weights is not None else [1.0 / n] * n
+        self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+        self.betas, self.eps = betas, eps
+        self.step_count = 0
+        self.dev = bucket.flat_w.device
+        self.shard_len = bucket.numel // n
+        self.shard_start = group.rank * self.shard_len
+        self.in_is_grad = grads or kind in ("fedsgd", "adam")
+        self.src = bucket.flat_g if self.in_is_grad else bucket.flat_w
+        self.master = self.mom = self.var = None
+        if self.kind != K.AGG_AVG:
+            sl = slice(self.shard_start, self.shard_start + self.shard_len)
+            self.master = bucket.flat_w[sl].float().clone()
+            self.mom = torch.zeros_like(self.master)
+            if self.kind in (K.AGG_ADAM, K.AGG_FEDADAM):
+                self.var = torch.zeros_like(self.master)
+        self.out_fp8 = out_fp8
+        self._timeout_cycles = int(timeout_s * 1.9e9)
+        # signal pad: the channel's when inside a fed job, else a private one
+        if channel is not None:
+            self._sig_ptr, self._sig_peers = channel.signal_ptr, channel.signal_peers
+            self._status = channel._local(512)
+            self._next_epoch = channel.next_epoch
+        else:
+            self._pad = torch.zeros(16384, dtype=torch.int32, device=self.dev)
+            self._sig_ptr = self._pad.data_ptr()
+            self._sig_peers = [self._sig_ptr] * n
+            self._status = self._pad.data_ptr() + 60000
+            self._epoch = 0
+
+            def _ne(k=2):
+                e = self._epoch
+                self._epoch += k
+                return e
+
+            self._next_epoch = _ne
+        if self.in_is_grad and n > 1:
+            raise NotImplementedError(
+                "gradient aggregation across parties needs the grad bucket in the symmetric heap; "
+                "use FlatBucket(grads_symmetric=True)"
+            ) if getattr(bucket, "grad_buffer", None) is None else None
+        mc = bucket.buffer.mc_ptr if (bucket.buffer is not None and not self.in_is_grad) else 0
+        if use_multicast is False:
+            mc = 0
+        uniform = all(abs(w - self.weights[0]) < 1e-12 for w in self.weights)
+        self._mc = mc if (mc and uniform and not out_fp8) else 0
+
+    def aggregate(self, stream=None):
+        """Enqueue the fused aggregate on ``stream`` (default: current). Collective."""
+        b = self.bucket
+        self.step_count += 1
+        if self.in_is_grad:
+            gb = getattr(b, "grad_buffer", None)
+            ins = gb.peer_ptrs if gb is not None else [b.flat_g.data_ptr()]
+        else:
+            ins = b.weight_ptrs()
+        outs = b.weight_ptrs()
+        K.aggregate(
+            inputs=ins, outputs=outs, my_rank=self.group.rank, shard_start=self.shard_start,
+            shard_len=self.shard_len, kind=self.kind, weights=self.weights,
+            mc_in=self._mc, mc_out=self._mc,
+            master_ptr=self.master.data_ptr() if self.master is not None else 0,
+            mom_ptr=self.mom.data_ptr() if self.mom is not None else 0,
+            var_ptr=self.var.data_ptr() if self.var is not None else 0,
+            lr=self.lr, momentum=self.momentum, weight_decay=self.weight_decay, beta1=self.betas[0],
+            beta2=self.betas[1], eps=self.eps, step=self.step_count, sig_ptr=self._sig_ptr,
+            sig_peers=self._sig_peers, epoch=self._next_epoch(2), status_ptr=self._status,
+            timeout_cycles=self._timeout_cycles, stream=stream, device_index=self.dev.index or 0,
+        )
+
+    @property
+    def uses_multicast(self) -> bool:
+        return bool(self._mc)
+
+
+def aggregate_reference(worker_weights: List, fed, server_party: str, parties: Sequence[str]):
+    """Reference-style FedAvg round through the public DAG API (the baseline):
+    every party's weights are pushed to ``server_party``, averaged there, and the
+    mean is pushed back to every party."""
+
+    @fed.remote
+    def _mean(*ws):
+        return torch.stack([w.float() for w in ws]).mean(0).to(ws[0].dtype)
+
+    return _mean.party(server_party).remote(*worker_weights)
+
+
+class FedAvgWorker:
+    """Actor body: one party's model, optimizer, data and aggregator.
+
+    Typical use (same script in every party)::
+
+        Worker = fed.remote(FedAvgWorker)
+        workers = {p: Worker.party(p).remote(model_fn, parties=parties, party=p, ...) for p in parties}
+        for r in range(rounds):
+            losses = [workers[p].local_round.remote(steps) for p in parties]
+            for p in parties: workers[p].aggregate.remote()
+            fed.get(losses)
+    """
+
+    def __init__(self, model_fn: Callable[[], torch.nn.Module], parties: Sequence[str], party: str,
+                 batch_fn: Optional[Callable] = None, lr: float = 0.05, momentum: float = 0.9,
+                 weight_decay: float = 5e-5, kind: str = "fedavg", server_lr: float = 1.0,
+                 server_momentum: float = 0.0, channels_last: bool = True, multicast: bool = True,
+                 seed: int = 0, loss_fn=None, use_cuda_graph: bool = False):
+        group, heap, channel = device_context(parties, party)
+        self.group, self.heap, self.channel = group, heap, channel
+        dev = torch.device(f"cuda:{group.device_index}")
+        torch.cuda.set_device(dev)
+        torch.manual_seed(seed)  # identical initial weights in every party
+        model = model_fn().to(dev)
+        if channels_last:
+            model = model.to(memory_format=torch.channels_last)
+        self.model = model.to(torch.bfloat16)
+        self.bucket = FlatBucket(self.model, heap, name="fedavg", n_parties=group.size, multicast=multicast)
+        self.opt = LocalSGD(self.bucket, lr, momentum, weight_decay)
+        self.agg = FedAggregator(self.bucket, group, channel, kind=kind, lr=server_lr, momentum=server_momentum)
+        self.loss_fn = loss_fn or torch.nn.functional.cross_entropy
+        self.batch_fn = batch_fn
+        self.channels_last = channels_last
+        self.dev = dev
+        self.rounds = 0
+        self._graph = None
+        self._use_graph = use_cuda_graph
+        self._static = None
+
+    # -- one local optimisation step ------------------------------------------------
+    def _train_step(self, x, y):
+        out = self.model(x)
+        loss = self.loss_fn(out.float(), y)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def local_step(self, x, y):
+        """x, y: host (pinned) or device tensors."""
+        x = x.to(self.dev, non_blocking=True)
+        y = y.to(self.dev, non_blocking=True)
+        if x.dtype != torch.bfloat16:
+            x = x.to(torch.bfloat16)
+        if self.channels_last and x.dim() == 4:
+            x = x.contiguous(memory_format=torch.channels_last)
+        if not self._use_graph:
+            return self._train_step(x, y)
+        return self._graphed_step(x, y)
+
+    def _graphed_step(self, x, y):
+        if self._graph is None:
+            self._static = (x.clone(), y.clone())
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):  # warm-up outside capture (cudnn autotune, allocator)
+                    self._train_step(*self._static)
+            torch.cuda.current_stream().wait_stream(s)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._static_loss = self._train_step(*self._static)
+        self._static[0].copy_(x, non_blocking=True)
+        self._static[1].copy_(y, non_blocking=True)
+        self._graph.replay()
+        return self._static_loss
+
+    def local_round(self, steps: int = 1, batches=None):
+        """``steps`` local SGD steps; returns the last loss as a 0-d device tensor."""
+        loss = None
+        for i in range(steps):
+            x, y = batches[i] if batches is not None else self.batch_fn(self.rounds, i)
+            loss = self.local_step(x, y)
+        self.rounds += 1
+        return loss
+
+    def aggregate(self):
+        self.agg.aggregate()
+        return True
+
+    def loss_value(self, loss):
+        return float(loss)
+
+    def weights_checksum(self):
+        return float(self.bucket.flat_w.float().sum())
+
+    def get_flat_weights(self):
+        return self.bucket.flat_w
+
+    def set_flat_weights(self, w):
+        self.bucket.flat_w.copy_(w)
+        return True

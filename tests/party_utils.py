@@ -1,0 +1,59 @@
+"""Helpers for multi-party tests: one OS process per party, exit-code asserts
+(same shape as the reference's suite, fed/tests/test_fed_get.py:88-95)."""
+import multiprocessing
+import os
+import socket
+import sys
+
+_CTX = multiprocessing.get_context("spawn")
+
+FAST_RETRY = {
+    "retry_max_attempts": 40,
+    "retry_initial_backoff_s": 0.05,
+    "retry_max_backoff_s": 0.5,
+    "retry_backoff_multiplier": 1.5,
+}
+
+
+def free_ports(n):
+    socks, ports = [], []
+    for _ in range(n):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        socks.append(s)
+        ports.append(s.getsockname()[1])
+    for s in socks:
+        s.close()
+    return ports
+
+
+def make_addresses(parties):
+    ports = free_ports(len(parties))
+    return {p: f"127.0.0.1:{port}" for p, port in zip(parties, ports)}
+
+
+def comm_config(transport="native", **extra):
+    cfg = dict(FAST_RETRY)
+    cfg["transport"] = transport
+    cfg.update(extra)
+    return cfg
+
+
+def run_parties(target, parties, args=(), timeout=90, expect=0, kwargs=None):
+    """Run ``target(party, *args)`` in one process per party; assert exit codes."""
+    procs = [_CTX.Process(target=target, args=(p, *args), kwargs=kwargs or {}) for p in parties]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout)
+    codes = []
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+            p.join()
+            codes.append("timeout")
+        else:
+            codes.append(p.exitcode)
+    expected = expect if isinstance(expect, (list, tuple)) else [expect] * len(procs)
+    assert codes == list(expected), f"party exit codes {codes}, expected {list(expected)}"
+    return codes
