@@ -81,7 +81,105 @@ __device__ __forceinline__ uint32_t agg_quant4(float a, float b, float c, float 
   return lo | (hi << 16);
 }
 
+// Optimizer/server update for 8 consecutive elements held in registers, then the
+// all-gather store of the result to every party (or one multicast store).
 template <bool kUseMc>
+__device__ __forceinline__ void finish_vector(const AggArgs& a, size_t v, size_t nvec, bool live, float* acc,
+                                              int lane) {
+  const int N = a.n_parties;
+  const size_t e0 = a.shard_start + (v << 3);
+  if (live && a.kind != kAvg) {
+    const size_t s0 = v << 3;  // index into the local shard state
+    float4 m0 = *reinterpret_cast<const float4*>(a.master + s0);
+    float4 m1 = *reinterpret_cast<const float4*>(a.master + s0 + 4);
+    float ms[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    float4 q0 = *reinterpret_cast<const float4*>(a.mom + s0);
+    float4 q1 = *reinterpret_cast<const float4*>(a.mom + s0 + 4);
+    float mo[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    if (a.kind == kFedAvgM || a.kind == kSgdGrad) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float g = (a.kind == kFedAvgM) ? (ms[k] - acc[k]) : (acc[k] + a.weight_decay * ms[k]);
+        mo[k] = a.momentum * mo[k] + g;
+        ms[k] -= a.lr * mo[k];
+        acc[k] = ms[k];
+      }
+    } else {
+      float4 r0 = *reinterpret_cast<const float4*>(a.var + s0);
+      float4 r1 = *reinterpret_cast<const float4*>(a.var + s0 + 4);
+      float va[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float g = (a.kind == kFedAdam) ? (ms[k] - acc[k]) : acc[k];
+        mo[k] = a.beta1 * mo[k] + (1.f - a.beta1) * g;
+        va[k] = a.beta2 * va[k] + (1.f - a.beta2) * g * g;
+        float mhat = mo[k] * a.bias_c1;  // 1 / (1 - beta1^t)
+        float vhat = va[k] * a.bias_c2;  // 1 / (1 - beta2^t)
+        ms[k] -= a.lr * (mhat / (sqrtf(vhat) + a.eps) + a.weight_decay * ms[k]);
+        acc[k] = ms[k];
+      }
+      *reinterpret_cast<float4*>(a.var + s0) = make_float4(va[0], va[1], va[2], va[3]);
+      *reinterpret_cast<float4*>(a.var + s0 + 4) = make_float4(va[4], va[5], va[6], va[7]);
+    }
+    *reinterpret_cast<float4*>(a.master + s0) = make_float4(ms[0], ms[1], ms[2], ms[3]);
+    *reinterpret_cast<float4*>(a.master + s0 + 4) = make_float4(ms[4], ms[5], ms[6], ms[7]);
+    *reinterpret_cast<float4*>(a.mom + s0) = make_float4(mo[0], mo[1], mo[2], mo[3]);
+    *reinterpret_cast<float4*>(a.mom + s0 + 4) = make_float4(mo[4], mo[5], mo[6], mo[7]);
+  }
+
+  if (!a.out_fp8) {
+    if (live) {
+      uint4 o;
+      o.x = pack_bf16x2(acc[0], acc[1]);
+      o.y = pack_bf16x2(acc[2], acc[3]);
+      o.z = pack_bf16x2(acc[4], acc[5]);
+      o.w = pack_bf16x2(acc[6], acc[7]);
+      if (kUseMc) {
+        multimem_st_v4(reinterpret_cast<char*>(a.mc_out) + e0 * 2, o);
+      } else {
+        for (int j = 0; j < N; ++j) st_v4(reinterpret_cast<char*>(a.out.p[(a.my_rank + j) % N]) + e0 * 2, o);
+      }
+    }
+  } else {
+    // block-scaled e4m3: 4 lanes share one UE8M0 scale (32 elements)
+    float amax = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(acc[k]));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+    const uint32_t e = agg_ue8m0(amax);
+    const float inv = __uint_as_float((254u - e) << 23);
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) lo |= (__shfl_sync(0xffffffffu, e, k * 4) & 0xffu) << (8 * k);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hi |= (__shfl_sync(0xffffffffu, e, 16 + k * 4) & 0xffu) << (8 * k);
+    if (live) {
+      uint2 o;
+      o.x = agg_quant4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+      o.y = agg_quant4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+      for (int j = 0; j < N; ++j) st_v2(reinterpret_cast<char*>(a.out.p[(a.my_rank + j) % N]) + e0, o);
+    }
+    if (lane == 0 && (v - lane) < nvec) {
+      const size_t blk0 = (a.shard_start >> 5) + ((v - lane) >> 2);
+      const size_t nblk_here = min((size_t)8, ((nvec - (v - lane)) + 3) >> 2);
+      for (int j = 0; j < N; ++j) {
+        unsigned char* sc = reinterpret_cast<unsigned char*>(a.out_scales.p[(a.my_rank + j) % N]);
+        if (nblk_here == 8 && ((blk0 & 7) == 0)) {
+          st_v2(sc + blk0, make_uint2(lo, hi));
+        } else {
+          for (size_t b = 0; b < nblk_here; ++b)
+            sc[blk0 + b] = (unsigned char)((b < 4 ? (lo >> (8 * b)) : (hi >> (8 * (b - 4)))) & 0xffu);
+        }
+      }
+    }
+  }
+}
+
+// kNP = parties whose 16-byte requests are preloaded per vector, kU = vectors per
+// thread per trip; kNP * kU outstanding 16 B loads per thread (8 => 32 registers),
+// all issued before the first use, so ~1 MB/SM is in flight against NVLink latency.
+template <bool kUseMc, int kNP, int kU>
 __global__ void __launch_bounds__(512) fed_aggregate_kernel(AggArgs a) {
   cta_party_barrier(a, a.epoch + 1);
 
@@ -92,171 +190,107 @@ __global__ void __launch_bounds__(512) fed_aggregate_kernel(AggArgs a) {
   const int N = a.n_parties;
   const int lane = threadIdx.x & 31;
 
-  for (size_t v = tid; v < nvec_rounded; v += stride) {
-    const bool live = v < nvec;
-    const size_t e0 = a.shard_start + (v << 3);  // first global element of this lane
-    float acc[8];
+  if (a.in_fp32) {
+    // fp32 contributions (gradient buckets): two 16 B requests per party per vector
+    for (size_t v = tid; v < nvec_rounded; v += stride) {
+      const bool live = v < nvec;
+      const size_t e0 = a.shard_start + (v << 3);
+      float acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-
-    if (live) {
-      if (kUseMc) {
-        // NVLS: the switch adds the N copies; one request per 16 B.
-        if (a.in_fp32) {
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+      if (live) {
+        if (kUseMc) {
           const char* p = reinterpret_cast<const char*>(a.mc_in) + e0 * 4;
           uint4 s0 = multimem_ld_reduce_f32x4(p), s1 = multimem_ld_reduce_f32x4(p + 16);
-          acc[0] = __uint_as_float(s0.x); acc[1] = __uint_as_float(s0.y);
-          acc[2] = __uint_as_float(s0.z); acc[3] = __uint_as_float(s0.w);
-          acc[4] = __uint_as_float(s1.x); acc[5] = __uint_as_float(s1.y);
-          acc[6] = __uint_as_float(s1.z); acc[7] = __uint_as_float(s1.w);
+          const float w0 = a.w[0];
+          acc[0] = w0 * __uint_as_float(s0.x); acc[1] = w0 * __uint_as_float(s0.y);
+          acc[2] = w0 * __uint_as_float(s0.z); acc[3] = w0 * __uint_as_float(s0.w);
+          acc[4] = w0 * __uint_as_float(s1.x); acc[5] = w0 * __uint_as_float(s1.y);
+          acc[6] = w0 * __uint_as_float(s1.z); acc[7] = w0 * __uint_as_float(s1.w);
         } else {
-          uint4 s = multimem_ld_reduce_bf16x8(reinterpret_cast<const char*>(a.mc_in) + e0 * 2);
-          unpack_bf16x8(s, acc);
-        }
-        const float w0 = a.w[0];
+          for (int j0 = 0; j0 < N; j0 += 4) {
+            uint4 x0[4], x1[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] *= w0;
-      } else if (a.in_fp32) {
-        uint4 x0[kMaxParties / 2], x1[kMaxParties / 2];
+            for (int j = 0; j < 4; ++j) {
+              if (j0 + j < N) {
+                const char* p = reinterpret_cast<const char*>(a.in.p[(a.my_rank + j0 + j) % N]) + e0 * 4;
+                x0[j] = ld_v4(p);
+                x1[j] = ld_v4(p + 16);
+              }
+            }
 #pragma unroll
-        for (int j = 0; j < kMaxParties / 2; ++j) {
-          if (j < N) {
-            const char* p = reinterpret_cast<const char*>(a.in.p[(a.my_rank + j) % N]) + e0 * 4;
-            x0[j] = ld_v4(p);
-            x1[j] = ld_v4(p + 16);
+            for (int j = 0; j < 4; ++j) {
+              if (j0 + j < N) {
+                const float wj = a.w[(a.my_rank + j0 + j) % N];
+                acc[0] += wj * __uint_as_float(x0[j].x); acc[1] += wj * __uint_as_float(x0[j].y);
+                acc[2] += wj * __uint_as_float(x0[j].z); acc[3] += wj * __uint_as_float(x0[j].w);
+                acc[4] += wj * __uint_as_float(x1[j].x); acc[5] += wj * __uint_as_float(x1[j].y);
+                acc[6] += wj * __uint_as_float(x1[j].z); acc[7] += wj * __uint_as_float(x1[j].w);
+              }
+            }
           }
-        }
-#pragma unroll
-        for (int j = 0; j < kMaxParties / 2; ++j) {
-          if (j < N) {
-            const float wj = a.w[(a.my_rank + j) % N];
-            acc[0] += wj * __uint_as_float(x0[j].x); acc[1] += wj * __uint_as_float(x0[j].y);
-            acc[2] += wj * __uint_as_float(x0[j].z); acc[3] += wj * __uint_as_float(x0[j].w);
-            acc[4] += wj * __uint_as_float(x1[j].x); acc[5] += wj * __uint_as_float(x1[j].y);
-            acc[6] += wj * __uint_as_float(x1[j].z); acc[7] += wj * __uint_as_float(x1[j].w);
-          }
-        }
-        for (int j = kMaxParties / 2; j < N; ++j) {
-          const char* p = reinterpret_cast<const char*>(a.in.p[(a.my_rank + j) % N]) + e0 * 4;
-          uint4 y0 = ld_v4(p), y1 = ld_v4(p + 16);
-          const float wj = a.w[(a.my_rank + j) % N];
-          acc[0] += wj * __uint_as_float(y0.x); acc[1] += wj * __uint_as_float(y0.y);
-          acc[2] += wj * __uint_as_float(y0.z); acc[3] += wj * __uint_as_float(y0.w);
-          acc[4] += wj * __uint_as_float(y1.x); acc[5] += wj * __uint_as_float(y1.y);
-          acc[6] += wj * __uint_as_float(y1.z); acc[7] += wj * __uint_as_float(y1.w);
-        }
-      } else {
-        // All N 16-byte requests (1 local + N-1 over NVLink) are issued before any is used.
-        uint4 x[kMaxParties / 2];
-#pragma unroll
-        for (int j = 0; j < kMaxParties / 2; ++j)
-          if (j < N) x[j] = ld_v4(reinterpret_cast<const char*>(a.in.p[(a.my_rank + j) % N]) + e0 * 2);
-#pragma unroll
-        for (int j = 0; j < kMaxParties / 2; ++j) {
-          if (j < N) {
-            float f[8];
-            unpack_bf16x8(x[j], f);
-            const float wj = a.w[(a.my_rank + j) % N];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] += wj * f[k];
-          }
-        }
-        for (int j = kMaxParties / 2; j < N; ++j) {
-          uint4 y = ld_v4(reinterpret_cast<const char*>(a.in.p[(a.my_rank + j) % N]) + e0 * 2);
-          float f[8];
-          unpack_bf16x8(y, f);
-          const float wj = a.w[(a.my_rank + j) % N];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] += wj * f[k];
         }
       }
-
-      // ---- optimizer / server update, in registers ---------------------------
-      if (a.kind != kAvg) {
-        const size_t s0 = v << 3;  // index into the local shard state
-        float4 m0 = *reinterpret_cast<const float4*>(a.master + s0);
-        float4 m1 = *reinterpret_cast<const float4*>(a.master + s0 + 4);
-        float ms[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-        float4 q0 = *reinterpret_cast<const float4*>(a.mom + s0);
-        float4 q1 = *reinterpret_cast<const float4*>(a.mom + s0 + 4);
-        float mo[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-        if (a.kind == kFedAvgM || a.kind == kSgdGrad) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float g = (a.kind == kFedAvgM) ? (ms[k] - acc[k]) : (acc[k] + a.weight_decay * ms[k]);
-            mo[k] = a.momentum * mo[k] + g;
-            ms[k] -= a.lr * mo[k];
-            acc[k] = ms[k];
-          }
-        } else {
-          float4 r0 = *reinterpret_cast<const float4*>(a.var + s0);
-          float4 r1 = *reinterpret_cast<const float4*>(a.var + s0 + 4);
-          float va[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float g = (a.kind == kFedAdam) ? (ms[k] - acc[k]) : acc[k];
-            mo[k] = a.beta1 * mo[k] + (1.f - a.beta1) * g;
-            va[k] = a.beta2 * va[k] + (1.f - a.beta2) * g * g;
-            float mhat = mo[k] * a.bias_c1;               // 1 / (1 - beta1^t)
-            float vhat = va[k] * a.bias_c2;               // 1 / (1 - beta2^t)
-            ms[k] -= a.lr * (mhat / (sqrtf(vhat) + a.eps) + a.weight_decay * ms[k]);
-            acc[k] = ms[k];
-          }
-          *reinterpret_cast<float4*>(a.var + s0) = make_float4(va[0], va[1], va[2], va[3]);
-          *reinterpret_cast<float4*>(a.var + s0 + 4) = make_float4(va[4], va[5], va[6], va[7]);
-        }
-        *reinterpret_cast<float4*>(a.master + s0) = make_float4(ms[0], ms[1], ms[2], ms[3]);
-        *reinterpret_cast<float4*>(a.master + s0 + 4) = make_float4(ms[4], ms[5], ms[6], ms[7]);
-        *reinterpret_cast<float4*>(a.mom + s0) = make_float4(mo[0], mo[1], mo[2], mo[3]);
-        *reinterpret_cast<float4*>(a.mom + s0 + 4) = make_float4(mo[4], mo[5], mo[6], mo[7]);
-      }
+      finish_vector<kUseMc>(a, v, nvec, live, acc, lane);
     }
-
-    // ---- all-gather of the new weights ----------------------------------------
-    if (!a.out_fp8) {
-      if (live) {
-        uint4 o;
-        o.x = pack_bf16x2(acc[0], acc[1]);
-        o.y = pack_bf16x2(acc[2], acc[3]);
-        o.z = pack_bf16x2(acc[4], acc[5]);
-        o.w = pack_bf16x2(acc[6], acc[7]);
-        if (kUseMc) {
-          multimem_st_v4(reinterpret_cast<char*>(a.mc_out) + e0 * 2, o);
-        } else {
-          for (int j = 0; j < N; ++j) st_v4(reinterpret_cast<char*>(a.out.p[(a.my_rank + j) % N]) + e0 * 2, o);
-        }
-      }
-    } else {
-      float amax = 0.f;
+  } else {
+    for (size_t v0 = tid; v0 < nvec_rounded; v0 += stride * kU) {
+      uint4 x[kU][kNP];
+      bool live[kU];
+      // ---- phase 1: issue every request of this trip ------------------------------
 #pragma unroll
-      for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(acc[k]));
-      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-      const uint32_t e = agg_ue8m0(amax);
-      const float inv = __uint_as_float((254u - e) << 23);
-      uint32_t lo = 0, hi = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) lo |= (__shfl_sync(0xffffffffu, e, k * 4) & 0xffu) << (8 * k);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) hi |= (__shfl_sync(0xffffffffu, e, 16 + k * 4) & 0xffu) << (8 * k);
-      if (live) {
-        uint2 o;
-        o.x = agg_quant4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
-        o.y = agg_quant4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
-        for (int j = 0; j < N; ++j) st_v2(reinterpret_cast<char*>(a.out.p[(a.my_rank + j) % N]) + e0, o);
-      }
-      if (lane == 0 && (v - lane) < nvec) {
-        const size_t blk0 = (a.shard_start >> 5) + ((v - lane) >> 2);
-        const size_t nblk_here = min((size_t)8, ((nvec - (v - lane)) + 3) >> 2);
-        for (int j = 0; j < N; ++j) {
-          unsigned char* sc = reinterpret_cast<unsigned char*>(a.out_scales.p[(a.my_rank + j) % N]);
-          if (nblk_here == 8 && ((blk0 & 7) == 0)) {
-            st_v2(sc + blk0, make_uint2(lo, hi));
+      for (int u = 0; u < kU; ++u) {
+        const size_t v = v0 + (size_t)u * stride;
+        live[u] = v < nvec;
+        if (live[u]) {
+          const size_t e0 = a.shard_start + (v << 3);
+          if (kUseMc) {
+            x[u][0] = multimem_ld_reduce_bf16x8(reinterpret_cast<const char*>(a.mc_in) + e0 * 2);
           } else {
-            for (size_t b = 0; b < nblk_here; ++b)
-              sc[blk0 + b] = (unsigned char)((b < 4 ? (lo >> (8 * b)) : (hi >> (8 * (b - 4)))) & 0xffu);
+#pragma unroll
+            for (int j = 0; j < kNP; ++j)
+              if (j < N) x[u][j] = ld_v4(reinterpret_cast<const char*>(a.in.p[(a.my_rank + j) % N]) + e0 * 2);
           }
         }
+      }
+      // ---- phase 2: reduce, update, all-gather ---------------------------------------
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const size_t v = v0 + (size_t)u * stride;
+        if (v >= nvec_rounded) break;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        if (live[u]) {
+          if (kUseMc) {
+            float f[8];
+            unpack_bf16x8(x[u][0], f);
+            const float w0 = a.w[0];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = w0 * f[k];
+          } else {
+#pragma unroll
+            for (int j = 0; j < kNP; ++j) {
+              if (j < N) {
+                float f[8];
+                unpack_bf16x8(x[u][j], f);
+                const float wj = a.w[(a.my_rank + j) % N];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += wj * f[k];
+              }
+            }
+            const size_t e0 = a.shard_start + (v << 3);
+            for (int j = kNP; j < N; ++j) {  // more parties than preload slots
+              uint4 y = ld_v4(reinterpret_cast<const char*>(a.in.p[(a.my_rank + j) % N]) + e0 * 2);
+              float f[8];
+              unpack_bf16x8(y, f);
+              const float wj = a.w[(a.my_rank + j) % N];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[k] += wj * f[k];
+            }
+          }
+        }
+        finish_vector<kUseMc>(a, v, nvec, live[u], acc, lane);
       }
     }
   }
@@ -304,10 +338,16 @@ __global__ void __launch_bounds__(512) fed_local_sgd_kernel(LocalSgdArgs a) {
 extern "C" {
 
 cudaError_t fedk_launch_aggregate(const AggArgs* a, int blocks, cudaStream_t stream) {
-  if (a->mc_in != nullptr && a->mc_out != nullptr && !a->out_fp8)
-    fed_aggregate_kernel<true><<<blocks, 512, 0, stream>>>(*a);
+  const bool mc = a->mc_in != nullptr && a->mc_out != nullptr && !a->out_fp8;
+  const int n = a->n_parties;
+  if (mc)
+    fed_aggregate_kernel<true, 1, 8><<<blocks, 512, 0, stream>>>(*a);
+  else if (n <= 2)
+    fed_aggregate_kernel<false, 2, 4><<<blocks, 512, 0, stream>>>(*a);
+  else if (n <= 4)
+    fed_aggregate_kernel<false, 4, 2><<<blocks, 512, 0, stream>>>(*a);
   else
-    fed_aggregate_kernel<false><<<blocks, 512, 0, stream>>>(*a);
+    fed_aggregate_kernel<false, 8, 1><<<blocks, 512, 0, stream>>>(*a);
   return cudaGetLastError();
 }
 

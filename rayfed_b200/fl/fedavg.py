@@ -239,6 +239,7 @@ class FedAvgWorker:
         self._static[0].copy_(x, non_blocking=True)
         self._static[1].copy_(y, non_blocking=True)
         self._graph.replay()
+        K.launch_counter.add("fed_local_sgd", 1)  # the captured step launches it once per replay
         return self._static_loss
 
     def local_round(self, steps: int = 1, batches=None):

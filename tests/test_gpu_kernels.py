@@ -1,0 +1,253 @@
+"""GPU numerics: every hand-written kernel vs a plain PyTorch fp32 reference.
+
+Single-GPU tests use loopback (the "peer" pointer is local memory) — the kernels
+do not care which GPU a pointer maps to.  Multi-party tests spawn one process
+per party and need >= 2 GPUs.
+"""
+import json
+import os
+import tempfile
+
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("CUDA device required", allow_module_level=True)
+
+from rayfed_b200.ops import kernels as K  # noqa: E402
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ctrl():
+    t = torch.zeros(4096, dtype=torch.int32, device=DEV)
+    return t
+
+
+def _flags(ctrl):
+    base = ctrl.data_ptr()
+    return dict(flag=base, done=base + 64, undone=base + 68, status=base + 72, sig=base + 1024)
+
+
+def test_extension_is_native_and_loaded():
+    ext = K.cuda_ext()
+    assert ext.__file__.endswith(".so")
+    assert K.sm_count(0) == 148 or K.sm_count(0) > 0
+
+
+@pytest.mark.parametrize("nbytes", [16, 1000, 4096 + 7, 1 << 20, (1 << 22) + 16])
+@pytest.mark.parametrize("bulk", [False, True])
+def test_push_unpack_bit_exact(ctrl, nbytes, bulk):
+    if bulk and nbytes % 16:
+        pytest.skip("bulk path needs 16-byte multiples")
+    f = _flags(ctrl)
+    ctrl.zero_()
+    src = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device=DEV)
+    arena = torch.zeros(nbytes + 64, dtype=torch.uint8, device=DEV)
+    dst = torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
+    K.push(src.data_ptr(), arena.data_ptr(), nbytes, flag_ptr=f["flag"], flag_value=7, done_counter_ptr=f["done"],
+           use_bulk=bulk)
+    K.unpack(arena.data_ptr(), dst.data_ptr(), nbytes, flag_ptr=f["flag"], flag_value=7,
+             done_counter_ptr=f["undone"], status_ptr=f["status"], timeout_cycles=int(5e9))
+    torch.cuda.synchronize()
+    assert torch.equal(src, dst)
+    assert ctrl[0].item() == 7  # flag published
+    assert ctrl[18].item() == 0  # no timeout
+    assert arena[nbytes:].sum().item() == 0  # no overrun
+
+
+def test_unpack_waits_for_flag_on_device(ctrl):
+    """K4: the unpack kernel parks on the flag; data published later by another stream."""
+    f = _flags(ctrl)
+    ctrl.zero_()
+    n = 1 << 16
+    src = torch.arange(n, dtype=torch.int32, device=DEV)
+    arena = torch.zeros(n, dtype=torch.int32, device=DEV)
+    dst = torch.zeros(n, dtype=torch.int32, device=DEV)
+    s_recv, s_send = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s_recv):
+        K.unpack(arena.data_ptr(), dst.data_ptr(), n * 4, flag_ptr=f["flag"], flag_value=1,
+                 done_counter_ptr=f["undone"], status_ptr=f["status"], timeout_cycles=int(10e9), stream=s_recv)
+    assert not s_recv.query()  # still waiting
+    with torch.cuda.stream(s_send):
+        K.push(src.data_ptr(), arena.data_ptr(), n * 4, flag_ptr=f["flag"], flag_value=1,
+               done_counter_ptr=f["done"], stream=s_send)
+    s_recv.synchronize()
+    assert torch.equal(src, dst)
+
+
+def test_unpack_timeout_sets_status(ctrl):
+    f = _flags(ctrl)
+    ctrl.zero_()
+    a = torch.zeros(64, dtype=torch.uint8, device=DEV)
+    K.unpack(a.data_ptr(), a.data_ptr(), 16, flag_ptr=f["flag"], flag_value=5, done_counter_ptr=f["undone"],
+             status_ptr=f["status"], timeout_cycles=int(2e6))
+    torch.cuda.synchronize()
+    assert ctrl[18].item() == 1
+
+
+def test_push_cast_f32_to_bf16_and_back(ctrl):
+    f = _flags(ctrl)
+    ctrl.zero_()
+    n = 100_003
+    x = torch.randn(n, device=DEV)
+    wire = torch.zeros(n, dtype=torch.bfloat16, device=DEV)
+    K.push(x.data_ptr(), wire.data_ptr(), n, mode=K.MODE_F32_TO_BF16, scale=0.5, flag_ptr=f["flag"], flag_value=1,
+           done_counter_ptr=f["done"])
+    y = torch.zeros(n, device=DEV)
+    K.unpack(wire.data_ptr(), y.data_ptr(), n, mode=K.MODE_BF16_TO_F32, flag_ptr=f["flag"], flag_value=1,
+             done_counter_ptr=f["undone"], status_ptr=f["status"], timeout_cycles=int(5e9))
+    torch.cuda.synchronize()
+    ref = (x * 0.5).to(torch.bfloat16)
+    assert torch.equal(wire, ref)
+    assert torch.equal(y, ref.float())
+
+
+def test_push_bf16_scale(ctrl):
+    f = _flags(ctrl)
+    ctrl.zero_()
+    n = 8 * 1000 + 3
+    x = torch.randn(n, device=DEV).to(torch.bfloat16)
+    out = torch.zeros_like(x)
+    K.push(x.data_ptr(), out.data_ptr(), n, mode=K.MODE_BF16_SCALE, scale=0.25, flag_ptr=f["flag"], flag_value=1,
+           done_counter_ptr=f["done"])
+    torch.cuda.synchronize()
+    assert torch.equal(out, (x.float() * 0.25).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("n", [32, 32 * 7, 1 << 16, (1 << 18) + 32 * 5])
+def test_fp8_block_scaled_wire_format_matches_torch(ctrl, n):
+    f = _flags(ctrl)
+    ctrl.zero_()
+    x = (torch.randn(n, device=DEV) * torch.logspace(-3, 3, n, device=DEV)).to(torch.bfloat16)
+    payload = torch.zeros(n, dtype=torch.uint8, device=DEV)
+    scales = torch.zeros(n // 32, dtype=torch.uint8, device=DEV)
+    K.push(x.data_ptr(), payload.data_ptr(), n, mode=K.MODE_BF16_TO_FP8, dst_scales_ptr=scales.data_ptr(),
+           flag_ptr=f["flag"], flag_value=1, done_counter_ptr=f["done"])
+    y = torch.zeros(n, dtype=torch.bfloat16, device=DEV)
+    K.unpack(payload.data_ptr(), y.data_ptr(), n, mode=K.MODE_FP8_TO_BF16, scales_ptr=scales.data_ptr(),
+             flag_ptr=f["flag"], flag_value=1, done_counter_ptr=f["undone"], status_ptr=f["status"],
+             timeout_cycles=int(5e9))
+    torch.cuda.synchronize()
+    xf = x.float().view(-1, 32)
+    amax = xf.abs().amax(dim=1, keepdim=True)
+    e = torch.ceil(torch.log2(amax.clamp_min(2.0 ** -120) / 448.0)).clamp(-126, 126)
+    sc = torch.exp2(e)
+    ref_q = (xf / sc).to(torch.float8_e4m3fn)
+    assert torch.equal(scales.view(-1, 1).int() - 127, e.int())
+    assert torch.equal(payload.view(torch.float8_e4m3fn).view(-1, 32).float(), ref_q.float())
+    assert torch.equal(y.float().view(-1, 32), (ref_q.float() * sc).to(torch.bfloat16).float())
+
+
+def test_local_sgd_matches_torch():
+    n = 8 * 12345
+    w = torch.randn(n, device=DEV).to(torch.bfloat16)
+    g = torch.randn(n, device=DEV).to(torch.bfloat16)
+    m = torch.randn(n, device=DEV)
+    w0, g0, m0 = w.float().clone(), g.float().clone(), m.clone()
+    K.local_sgd(w.data_ptr(), g.data_ptr(), m.data_ptr(), n, lr=0.1, momentum=0.9, weight_decay=0.01,
+                grad_scale=0.5, zero_grad=True)
+    torch.cuda.synchronize()
+    gg = g0 * 0.5 + 0.01 * w0
+    m_ref = 0.9 * m0 + gg
+    w_ref = (w0 - 0.1 * m_ref).to(torch.bfloat16)
+    assert torch.allclose(m, m_ref, rtol=1e-6, atol=1e-6)
+    assert torch.equal(w, w_ref)
+    assert g.abs().sum().item() == 0
+
+
+def _agg_single(kind, n=32 * 1000, **kw):
+    """N=1 degenerate aggregate: exercises the optimizer math and the store path."""
+    pad = torch.zeros(16384, dtype=torch.int32, device=DEV)
+    x = torch.randn(n, device=DEV).to(torch.bfloat16)
+    buf = x.clone()
+    K.aggregate(inputs=[buf.data_ptr()], outputs=[buf.data_ptr()], my_rank=0, shard_start=0, shard_len=n, kind=kind,
+                sig_ptr=pad.data_ptr(), sig_peers=[pad.data_ptr()], epoch=0, status_ptr=pad.data_ptr() + 60000,
+                timeout_cycles=int(5e9), **kw)
+    torch.cuda.synchronize()
+    return x, buf
+
+
+def test_aggregate_avg_identity_n1():
+    x, out = _agg_single(K.AGG_AVG)
+    assert torch.equal(x, out)
+
+
+def test_aggregate_fedavgm_n1():
+    n = 32 * 999
+    master = torch.randn(n, device=DEV)
+    mom = torch.randn(n, device=DEV)
+    m0, q0 = master.clone(), mom.clone()
+    x, out = _agg_single(K.AGG_FEDAVGM, n=n, master_ptr=master.data_ptr(), mom_ptr=mom.data_ptr(), lr=0.7,
+                         momentum=0.5)
+    d = m0 - x.float()
+    q = 0.5 * q0 + d
+    ref = m0 - 0.7 * q
+    assert torch.allclose(master, ref, rtol=1e-6, atol=1e-6)
+    assert torch.equal(out, ref.to(torch.bfloat16))
+
+
+def test_aggregate_adam_n1_matches_torch_adamw():
+    n = 32 * 500
+    w0 = torch.randn(n, device=DEV)
+    master = w0.clone()
+    mom = torch.zeros(n, device=DEV)
+    var = torch.zeros(n, device=DEV)
+    p = torch.nn.Parameter(w0.clone())
+    opt = torch.optim.AdamW([p], lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.1)
+    pad = torch.zeros(16384, dtype=torch.int32, device=DEV)
+    out = torch.zeros(n, dtype=torch.bfloat16, device=DEV)
+    for step in range(1, 4):
+        g = torch.randn(n, device=DEV).to(torch.bfloat16)
+        p.grad = g.float()
+        opt.step()
+        K.aggregate(inputs=[g.data_ptr()], outputs=[out.data_ptr()], my_rank=0, shard_start=0, shard_len=n,
+                    kind=K.AGG_ADAM, master_ptr=master.data_ptr(), mom_ptr=mom.data_ptr(), var_ptr=var.data_ptr(),
+                    lr=1e-2, beta1=0.9, beta2=0.99, eps=1e-8, weight_decay=0.1, step=step, sig_ptr=pad.data_ptr(),
+                    sig_peers=[pad.data_ptr()], epoch=2 * step, status_ptr=pad.data_ptr() + 60000,
+                    timeout_cycles=int(5e9))
+        torch.cuda.synchronize()
+        assert torch.allclose(master, p.detach(), rtol=2e-5, atol=2e-6), step
+    assert torch.equal(out, master.to(torch.bfloat16))
+
+
+def test_aggregate_fp8_out_n1():
+    n = 32 * 64
+    pad = torch.zeros(16384, dtype=torch.int32, device=DEV)
+    x = (torch.randn(n, device=DEV) * 2).to(torch.bfloat16)
+    out = torch.zeros(n, dtype=torch.uint8, device=DEV)
+    scales = torch.zeros(n // 32, dtype=torch.uint8, device=DEV)
+    K.aggregate(inputs=[x.data_ptr()], outputs=[out.data_ptr()], out_scales=[scales.data_ptr()], out_fp8=True,
+                my_rank=0, shard_start=0, shard_len=n, kind=K.AGG_AVG, sig_ptr=pad.data_ptr(),
+                sig_peers=[pad.data_ptr()], epoch=0, status_ptr=pad.data_ptr() + 60000, timeout_cycles=int(5e9))
+    torch.cuda.synchronize()
+    xf = x.float().view(-1, 32)
+    e = torch.ceil(torch.log2(xf.abs().amax(1, keepdim=True).clamp_min(2.0 ** -120) / 448.0))
+    ref = (xf / torch.exp2(e)).to(torch.float8_e4m3fn)
+    assert torch.equal(scales.int() - 127, e.view(-1).int())
+    assert torch.equal(out.view(torch.float8_e4m3fn).view(-1, 32).float(), ref.float())
+
+
+def test_two_virtual_parties_on_one_gpu_rendezvous_in_kernel():
+    """Two 'parties' = two streams on one GPU: the in-kernel signal-pad barrier and
+    the cross-party reduce are exercised without a second device."""
+    n = 32 * 2 * 4096
+    shard = n // 2
+    xs = [torch.randn(n, device=DEV).to(torch.bfloat16) for _ in range(2)]
+    bufs = [x.clone() for x in xs]
+    pads = [torch.zeros(16384, dtype=torch.int32, device=DEV) for _ in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for r in range(2):
+        K.aggregate(inputs=[b.data_ptr() for b in bufs], outputs=[b.data_ptr() for b in bufs], my_rank=r,
+                    shard_start=r * shard, shard_len=shard, kind=K.AGG_AVG, sig_ptr=pads[r].data_ptr(),
+                    sig_peers=[p.data_ptr() for p in pads], epoch=0, status_ptr=pads[r].data_ptr() + 60000,
+                    timeout_cycles=int(10e9), stream=streams[r], blocks=32)
+    torch.cuda.synchronize()
+    ref = ((xs[0].float() + xs[1].float()) * 0.5).to(torch.bfloat16)
+    assert torch.equal(bufs[0], ref) and torch.equal(bufs[1], ref)
+    assert pads[0][15000].item() == 0 and pads[1][15000].item() == 0
