@@ -181,6 +181,7 @@ __device__ __forceinline__ void finish_vector(const AggArgs& a, size_t v, size_t
 // all issued before the first use, so ~1 MB/SM is in flight against NVLink latency.
 template <bool kUseMc, int kNP, int kU>
 __global__ void __launch_bounds__(512) fed_aggregate_kernel(AggArgs a) {
+  if (a.epoch_dev) a.epoch = ld_relaxed_sys_u32(a.epoch_dev);  // graph-replayable epoch
   cta_party_barrier(a, a.epoch + 1);
 
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,6 +297,13 @@ __global__ void __launch_bounds__(512) fed_aggregate_kernel(AggArgs a) {
   }
 
   cta_party_barrier(a, a.epoch + 2);
+  if (a.epoch_dev && threadIdx.x == 0) {
+    unsigned prev = atomicAdd(a.agg_done, 1u);
+    if (prev == gridDim.x - 1) {  // every CTA has read the epoch and passed both barriers
+      *a.agg_done = 0;
+      *a.epoch_dev = a.epoch + 2;
+    }
+  }
 }
 
 // K5: N-party device barrier (replaces the reference's ping loop,

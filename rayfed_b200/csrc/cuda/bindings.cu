@@ -362,6 +362,70 @@ PYBIND11_MODULE(_fedcuda, m) {
       py::arg("bias_c1"), py::arg("bias_c2"), py::arg("sig"), py::arg("sig_peers"), py::arg("epoch"),
       py::arg("status"), py::arg("timeout_cycles"), py::arg("blocks"), py::arg("stream"));
 
+  // Pre-baked argument block: per-round launches only patch the scalars that change.
+  struct AggPlan {
+    AggArgs a;
+    int blocks;
+  };
+  py::class_<AggPlan>(m, "AggPlan")
+      .def(py::init([](const std::vector<uint64_t>& in, const std::vector<uint64_t>& out,
+                       const std::vector<uint64_t>& out_scales, uint64_t mc_in, uint64_t mc_out, uint64_t master,
+                       uint64_t mom, uint64_t var, uint64_t shard_start, uint64_t shard_len, int my_rank, int kind,
+                       bool in_fp32, bool out_fp8, const std::vector<float>& weights, float lr, float momentum,
+                       float weight_decay, float beta1, float beta2, float eps, uint64_t sig,
+                       const std::vector<uint64_t>& sig_peers, uint64_t epoch_dev, uint64_t agg_done,
+                       uint64_t status, long long timeout_cycles, int blocks) {
+             AggPlan p{};
+             AggArgs& a = p.a;
+             fill_peers(a.in, in);
+             fill_peers(a.out, out);
+             fill_peers(a.out_scales, out_scales);
+             a.mc_in = P<void>(mc_in);
+             a.mc_out = P<void>(mc_out);
+             a.master = P<float>(master);
+             a.mom = P<float>(mom);
+             a.var = P<float>(var);
+             a.shard_start = shard_start;
+             a.shard_len = shard_len;
+             a.n_parties = (int)in.size();
+             a.my_rank = my_rank;
+             a.kind = kind;
+             a.in_fp32 = in_fp32;
+             a.out_fp8 = out_fp8;
+             for (int i = 0; i < kMaxParties; ++i) a.w[i] = i < (int)weights.size() ? weights[i] : 0.f;
+             a.lr = lr;
+             a.momentum = momentum;
+             a.weight_decay = weight_decay;
+             a.beta1 = beta1;
+             a.beta2 = beta2;
+             a.eps = eps;
+             a.bias_c1 = 1.f;
+             a.bias_c2 = 1.f;
+             a.sig = P<uint32_t>(sig);
+             fill_peers(a.sig_peers, sig_peers);
+             a.epoch_dev = P<uint32_t>(epoch_dev);
+             a.agg_done = P<uint32_t>(agg_done);
+             a.status = P<uint32_t>(status);
+             a.timeout_cycles = timeout_cycles;
+             p.blocks = blocks;
+             return p;
+           }),
+           py::arg("inputs"), py::arg("outputs"), py::arg("out_scales"), py::arg("mc_in"), py::arg("mc_out"),
+           py::arg("master"), py::arg("mom"), py::arg("var"), py::arg("shard_start"), py::arg("shard_len"),
+           py::arg("my_rank"), py::arg("kind"), py::arg("in_fp32"), py::arg("out_fp8"), py::arg("weights"),
+           py::arg("lr"), py::arg("momentum"), py::arg("weight_decay"), py::arg("beta1"), py::arg("beta2"),
+           py::arg("eps"), py::arg("sig"), py::arg("sig_peers"), py::arg("epoch_dev"), py::arg("agg_done"),
+           py::arg("status"), py::arg("timeout_cycles"), py::arg("blocks"))
+      .def("launch",
+           [](AggPlan& p, uint32_t epoch, float lr, float bias_c1, float bias_c2, uint64_t stream) {
+             p.a.epoch = epoch;
+             p.a.lr = lr;
+             p.a.bias_c1 = bias_c1;
+             p.a.bias_c2 = bias_c2;
+             check(fedk_launch_aggregate(&p.a, p.blocks, (cudaStream_t)(uintptr_t)stream), "fed_aggregate launch");
+           },
+           py::arg("epoch"), py::arg("lr"), py::arg("bias_c1"), py::arg("bias_c2"), py::arg("stream"));
+
   m.def(
       "barrier",
       [](int n_parties, int my_rank, uint64_t sig, const std::vector<uint64_t>& sig_peers, uint32_t epoch,

@@ -57,6 +57,9 @@ struct AggArgs {
   uint32_t* sig;           // my signal pad
   PeerPtrs sig_peers;      // every party's signal pad
   uint32_t epoch;          // this launch uses epoch+1 (entry) and epoch+2 (exit)
+  uint32_t* epoch_dev;     // if set: epoch is read from this device word and advanced by 2 by the
+                           // last CTA, so an identical launch can be replayed from a CUDA graph
+  uint32_t* agg_done;      // device counter for "last CTA" detection (zero between launches)
   uint32_t* status;
   long long timeout_cycles;
 };

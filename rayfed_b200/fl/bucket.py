@@ -23,8 +23,10 @@ class FlatBucket:
     """
 
     def __init__(self, model: torch.nn.Module, heap: Optional[SymmetricHeap], name: str = "model",
-                 dtype=torch.bfloat16, n_parties: int = 1, multicast: bool = False, device=None):
+                 dtype=torch.bfloat16, n_parties: int = 1, multicast: bool = False, device=None,
+                 grads_symmetric: bool = False):
         params = [p for p in model.parameters() if p.requires_grad]
+        self.name = name
         self.params: List[torch.nn.Parameter] = params
         self.dtype = dtype
         self.n_parties = n_parties
@@ -45,7 +47,14 @@ class FlatBucket:
             self.buffer = None
             device = device or params[0].device
             self.flat_w = torch.zeros(self.numel, dtype=dtype, device=device)
-        self.flat_g = torch.zeros(self.numel, dtype=dtype, device=device)
+        self.grad_buffer = None
+        if grads_symmetric and heap is not None:
+            # gradients readable by peers (FedSGD / cross-party Adam on averaged grads)
+            self.grad_buffer = heap.alloc(f"bucket-grad/{name}", self.numel * itemsize, multicast=multicast)
+            self.flat_g = self.grad_buffer.tensor(dtype, self.numel)
+        else:
+            self.flat_g = torch.zeros(self.numel, dtype=dtype, device=device)
+        self._fp8 = None
         with torch.no_grad():
             for p, off in zip(params, offs):
                 n = p.numel()
@@ -70,6 +79,28 @@ class FlatBucket:
 
     def weight_ptrs(self) -> List[int]:
         return self.buffer.peer_ptrs if self.buffer is not None else [self.flat_w.data_ptr()]
+
+    def ensure_fp8_buffers(self, heap):
+        """Block-scaled e4m3 copy of the weights (+ UE8M0 scale per 32) written by the
+        fp8 aggregate; symmetric so every party receives the re-quantised weights."""
+        if self._fp8 is None:
+            if heap is not None and self.n_parties > 1:
+                pay = heap.alloc(f"bucket-fp8/{self.name}", self.numel)
+                sc = heap.alloc(f"bucket-fp8s/{self.name}", self.numel // 32)
+                self.fp8_payload = pay.tensor(torch.uint8, self.numel)
+                self.fp8_scales = sc.tensor(torch.uint8, self.numel // 32)
+                self._fp8 = (list(pay.peer_ptrs), list(sc.peer_ptrs))
+            else:
+                self.fp8_payload = torch.zeros(self.numel, dtype=torch.uint8, device=self.flat_w.device)
+                self.fp8_scales = torch.zeros(self.numel // 32, dtype=torch.uint8, device=self.flat_w.device)
+                self._fp8 = ([self.fp8_payload.data_ptr()], [self.fp8_scales.data_ptr()])
+        return self._fp8
+
+    def dequantized_fp8(self):
+        """fp32 view of the fp8 weights (test / debugging helper)."""
+        q = self.fp8_payload.view(torch.float8_e4m3fn).float().view(-1, 32)
+        s = torch.exp2(self.fp8_scales.float() - 127.0).view(-1, 1)
+        return (q * s).view(-1)
 
     def zero_grad(self):
         self.flat_g.zero_()

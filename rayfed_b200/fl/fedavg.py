@@ -73,7 +73,7 @@ class FedAggregator:
     def __init__(self, bucket: FlatBucket, group: PartyGroup, channel=None, kind: str = "fedavg",
                  weights: Optional[Sequence[float]] = None, lr: float = 1.0, momentum: float = 0.0,
                  weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8, out_fp8: bool = False,
-                 grads: bool = False, use_multicast: Optional[bool] = None, timeout_s: float = 120.0):
+                 grads: bool = False, use_multicast: Optional[bool] = None, timeout_s: float = 120.0, heap=None):
         self.bucket, self.group, self.channel = bucket, group, channel
         self.kind = _KINDS[kind]
         self.kind_name = kind
@@ -96,57 +96,60 @@ class FedAggregator:
                 self.var = torch.zeros_like(self.master)
         self.out_fp8 = out_fp8
         self._timeout_cycles = int(timeout_s * 1.9e9)
-        # signal pad: the channel's when inside a fed job, else a private one
-        if channel is not None:
-            self._sig_ptr, self._sig_peers = channel.signal_ptr, channel.signal_peers
-            self._status = channel._local(512)
-            self._next_epoch = channel.next_epoch
+        # A private signal pad per aggregator (symmetric when there are peers) and a
+        # device-resident epoch: the launch is identical every round => graph-replayable.
+        heap = heap or (channel.heap if channel is not None else None)
+        self._ctl = torch.zeros(64, dtype=torch.int32, device=self.dev)  # [0]=epoch [1]=done [2]=status
+        if n > 1:
+            assert heap is not None, "multi-party aggregation needs the symmetric heap"
+            self._pad = heap.alloc(f"aggpad/{bucket.name}/{kind}", 64 * 1024)
+            sig_ptr, sig_peers = self._pad.local_ptr, list(self._pad.peer_ptrs)
         else:
-            self._pad = torch.zeros(16384, dtype=torch.int32, device=self.dev)
-            self._sig_ptr = self._pad.data_ptr()
-            self._sig_peers = [self._sig_ptr] * n
-            self._status = self._pad.data_ptr() + 60000
-            self._epoch = 0
-
-            def _ne(k=2):
-                e = self._epoch
-                self._epoch += k
-                return e
-
-            self._next_epoch = _ne
-        if self.in_is_grad and n > 1:
-            raise NotImplementedError(
-                "gradient aggregation across parties needs the grad bucket in the symmetric heap; "
-                "use FlatBucket(grads_symmetric=True)"
-            ) if getattr(bucket, "grad_buffer", None) is None else None
-        mc = bucket.buffer.mc_ptr if (bucket.buffer is not None and not self.in_is_grad) else 0
-        if use_multicast is False:
-            mc = 0
-        uniform = all(abs(w - self.weights[0]) < 1e-12 for w in self.weights)
-        self._mc = mc if (mc and uniform and not out_fp8) else 0
-
-    def aggregate(self, stream=None):
-        """Enqueue the fused aggregate on ``stream`` (default: current). Collective."""
-        b = self.bucket
-        self.step_count += 1
+            self._pad_t = torch.zeros(16384, dtype=torch.int32, device=self.dev)
+            sig_ptr, sig_peers = self._pad_t.data_ptr(), [self._pad_t.data_ptr()]
         if self.in_is_grad:
-            gb = getattr(b, "grad_buffer", None)
-            ins = gb.peer_ptrs if gb is not None else [b.flat_g.data_ptr()]
+            gb = getattr(bucket, "grad_buffer", None)
+            if gb is None and n > 1:
+                raise NotImplementedError(
+                    "gradient aggregation across parties needs FlatBucket(grads_symmetric=True)")
+            ins = gb.peer_ptrs if gb is not None else [bucket.flat_g.data_ptr()]
+            mc = gb.mc_ptr if gb is not None else 0
         else:
-            ins = b.weight_ptrs()
-        outs = b.weight_ptrs()
-        K.aggregate(
-            inputs=ins, outputs=outs, my_rank=self.group.rank, shard_start=self.shard_start,
-            shard_len=self.shard_len, kind=self.kind, weights=self.weights,
-            mc_in=self._mc, mc_out=self._mc,
+            ins = bucket.weight_ptrs()
+            mc = bucket.buffer.mc_ptr if bucket.buffer is not None else 0
+        mc_out = bucket.buffer.mc_ptr if bucket.buffer is not None else 0
+        if use_multicast is False or n == 1:
+            mc = mc_out = 0
+        uniform = all(abs(w - self.weights[0]) < 1e-12 for w in self.weights)
+        if not (mc and mc_out and uniform and not out_fp8):
+            mc = mc_out = 0
+        self._mc = mc
+        self._scales = None
+        out_ptrs, out_scales = bucket.weight_ptrs(), ()
+        if out_fp8:
+            fb = bucket.ensure_fp8_buffers(heap)
+            out_ptrs, out_scales = fb[0], fb[1]
+        base = self._ctl.data_ptr()
+        self._plan = K.AggregatePlan(
+            inputs=ins, outputs=out_ptrs, out_scales=out_scales, my_rank=group.rank, shard_start=self.shard_start,
+            shard_len=self.shard_len, kind=self.kind, weights=self.weights, in_fp32=False, out_fp8=out_fp8,
+            mc_in=mc, mc_out=mc_out,
             master_ptr=self.master.data_ptr() if self.master is not None else 0,
             mom_ptr=self.mom.data_ptr() if self.mom is not None else 0,
             var_ptr=self.var.data_ptr() if self.var is not None else 0,
-            lr=self.lr, momentum=self.momentum, weight_decay=self.weight_decay, beta1=self.betas[0],
-            beta2=self.betas[1], eps=self.eps, step=self.step_count, sig_ptr=self._sig_ptr,
-            sig_peers=self._sig_peers, epoch=self._next_epoch(2), status_ptr=self._status,
-            timeout_cycles=self._timeout_cycles, stream=stream, device_index=self.dev.index or 0,
+            lr=lr, momentum=momentum, weight_decay=weight_decay, beta1=betas[0], beta2=betas[1], eps=eps,
+            sig_ptr=sig_ptr, sig_peers=sig_peers, epoch_dev_ptr=base, agg_done_ptr=base + 4, status_ptr=base + 8,
+            timeout_cycles=self._timeout_cycles, device_index=self.dev.index or 0,
         )
+
+    def aggregate(self, stream=None, lr: Optional[float] = None):
+        """Enqueue the fused aggregate on ``stream`` (default: current). Collective."""
+        self.step_count += 1
+        self._plan.launch(0, self.step_count, lr, stream)
+
+    def status(self) -> int:
+        """0 = healthy; 2 = an in-kernel party barrier timed out."""
+        return int(self._ctl[2].item())
 
     @property
     def uses_multicast(self) -> bool:
@@ -194,7 +197,8 @@ class FedAvgWorker:
         self.model = model.to(torch.bfloat16)
         self.bucket = FlatBucket(self.model, heap, name="fedavg", n_parties=group.size, multicast=multicast)
         self.opt = LocalSGD(self.bucket, lr, momentum, weight_decay)
-        self.agg = FedAggregator(self.bucket, group, channel, kind=kind, lr=server_lr, momentum=server_momentum)
+        self.agg = FedAggregator(self.bucket, group, channel, kind=kind, lr=server_lr, momentum=server_momentum,
+                                 heap=heap)
         self.loss_fn = loss_fn or torch.nn.functional.cross_entropy
         self.batch_fn = batch_fn
         self.channels_last = channels_last

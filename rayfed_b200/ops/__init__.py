@@ -28,6 +28,7 @@ from .kernels import (  # noqa: F401
     MODE_COPY,
     MODE_F32_TO_BF16,
     MODE_FP8_TO_BF16,
+    AggregatePlan,
     aggregate,
     barrier,
     cuda_ext,

@@ -74,7 +74,7 @@ def _stream_handle(stream) -> int:
     return stream.cuda_stream
 
 
-def _blocks_for(nbytes: int, device_index: int, bytes_per_cta: int = 64 * 1024, max_per_sm: int = 2) -> int:
+def _blocks_for(nbytes: int, device_index: int, bytes_per_cta: int = 64 * 1024, max_per_sm: int = 4) -> int:
     sms = sm_count(device_index)
     want = max(1, (nbytes + bytes_per_cta - 1) // bytes_per_cta)
     return int(min(want, sms * max_per_sm))
@@ -144,6 +144,36 @@ def aggregate(*, inputs: Sequence[int], outputs: Sequence[int], my_rank: int, sh
     launch_counter.add("fed_aggregate")
 
 
+class AggregatePlan:
+    """Pre-baked K2/K3 launch: argument marshalling happens once, a round costs one
+    pybind call.  With ``epoch_dev_ptr`` the epoch lives on the device and the launch
+    is CUDA-graph replayable."""
+
+    def __init__(self, *, inputs, outputs, my_rank, shard_start, shard_len, kind=AGG_AVG, weights=None,
+                 in_fp32=False, out_fp8=False, out_scales=(), mc_in=0, mc_out=0, master_ptr=0, mom_ptr=0, var_ptr=0,
+                 lr=1.0, momentum=0.0, weight_decay=0.0, beta1=0.9, beta2=0.999, eps=1e-8, sig_ptr, sig_peers,
+                 epoch_dev_ptr=0, agg_done_ptr=0, status_ptr=0, timeout_cycles=0, device_index=0, blocks=None):
+        n = len(inputs)
+        if weights is None:
+            weights = [1.0 / n] * n
+        if blocks is None:
+            blocks = int(min(sm_count(device_index), max(1, (shard_len // 8 + 511) // 512)))
+        self.lr, self.beta1, self.beta2 = float(lr), float(beta1), float(beta2)
+        self._plan = cuda_ext().AggPlan(list(inputs), list(outputs), list(out_scales), mc_in, mc_out, master_ptr,
+                                        mom_ptr, var_ptr, shard_start, shard_len, my_rank, kind, bool(in_fp32),
+                                        bool(out_fp8), [float(w) for w in weights], float(lr), float(momentum),
+                                        float(weight_decay), float(beta1), float(beta2), float(eps), sig_ptr,
+                                        list(sig_peers), epoch_dev_ptr, agg_done_ptr, status_ptr, timeout_cycles,
+                                        blocks)
+
+    def launch(self, epoch: int = 0, step: int = 1, lr: Optional[float] = None, stream=None):
+        b1, b2 = self.beta1, self.beta2
+        c1 = 1.0 / (1.0 - b1 ** step) if b1 < 1.0 else 1.0
+        c2 = 1.0 / (1.0 - b2 ** step) if b2 < 1.0 else 1.0
+        self._plan.launch(epoch, self.lr if lr is None else float(lr), c1, c2, _stream_handle(stream))
+        launch_counter.add("fed_aggregate")
+
+
 def barrier(*, n_parties: int, my_rank: int, sig_ptr: int, sig_peers: Sequence[int], epoch: int, status_ptr: int = 0,
             timeout_cycles: int = 0, stream=None) -> None:
     """K5."""
@@ -158,7 +188,7 @@ def local_sgd(w_ptr: int, g_ptr: int, mom_ptr: int, n: int, *, lr: float, moment
     if n % 8:
         raise ValueError("local_sgd needs a flat bucket whose length is a multiple of 8")
     if blocks is None:
-        blocks = int(min(sm_count(device_index) * 2, max(1, (n // 8 + 511) // 512)))
+        blocks = int(min(sm_count(device_index) * 8, max(1, (n // 8 + 511) // 512)))
     cuda_ext().local_sgd(w_ptr, g_ptr, mom_ptr, n, float(lr), float(momentum), float(weight_decay),
                          float(grad_scale), bool(zero_grad), blocks, _stream_handle(stream))
     launch_counter.add("fed_local_sgd")
