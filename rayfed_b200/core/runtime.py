@@ -271,7 +271,7 @@ def _device_trampoline(fn, stream_ctx: _StreamContext, pool_tls):
         else:
             ctx = stream_ctx
         stream = ctx.stream()
-        with torch.cuda.stream(stream):
+        with torch.cuda.device(stream.device), torch.cuda.stream(stream):
             args = tuple(_consume(a, stream) for a in args)
             if kwargs:
                 kwargs = {k: _consume(v, stream) for k, v in kwargs.items()}

@@ -89,6 +89,7 @@ class SymmetricHeap:
     def alloc(self, name: str, nbytes: int, multicast: bool = False) -> SymmetricBuffer:
         """Collective: every party calls with the same ``name`` and ``nbytes``."""
         nbytes = (nbytes + 255) // 256 * 256
+        self._ext.set_device(self.group.device_index)  # cudaSetDevice is per thread
         if self.backend == "vmm" or multicast:
             try:
                 buf = self._alloc_vmm(name, nbytes, multicast)

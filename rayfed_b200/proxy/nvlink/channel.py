@@ -122,6 +122,12 @@ class DeviceChannel:
         """Launch K1 for one CUDA tensor; returns the descriptor the host frame carries."""
         import torch
 
+        with torch.cuda.device(self.device_index):  # callers are arbitrary runtime threads
+            return self._push_tensor(dest_rank, tensor, ready_event, scale)
+
+    def _push_tensor(self, dest_rank: int, tensor, ready_event=None, scale: float = 1.0) -> dict:
+        import torch
+
         t = tensor if tensor.is_contiguous() else tensor.contiguous()
         if t.data_ptr() % 16:
             t = t.clone()
@@ -167,6 +173,12 @@ class DeviceChannel:
         """Launch K4+unpack for one descriptor → (tensor, event)."""
         import torch
 
+        with torch.cuda.device(self.device_index):
+            return self._unpack_tensor(src_rank, desc)
+
+    def _unpack_tensor(self, src_rank: int, desc: dict):
+        import torch
+
         dtype = getattr(torch, desc["dtype"])
         out = torch.empty(desc["shape"], dtype=dtype, device=self._dev)
         region = OFF_ARENA + src_rank * self.region_bytes
@@ -198,6 +210,7 @@ class DeviceChannel:
     # -- misc --------------------------------------------------------------------------
     def device_barrier(self, stream=None):
         """K5 on the given (default: current) stream."""
+        K.cuda_ext().set_device(self.device_index)
         K.barrier(n_parties=self.group.size, my_rank=self.group.rank, sig_ptr=self.signal_ptr,
                   sig_peers=self.signal_peers, epoch=self.next_epoch(1), status_ptr=self._local(OFF_STATUS),
                   timeout_cycles=self._timeout_cycles, stream=stream)

@@ -19,7 +19,7 @@ def _init(party, addresses, **comm):
     dev = parties.index(party) % torch.cuda.device_count()
     torch.cuda.set_device(dev)
     fed.init(addresses=addresses, party=party, logging_level="warning",
-             config={"cross_silo_comm": comm_config("nvlink", device_arena_bytes=64 << 20, **comm),
+             config={"cross_silo_comm": comm_config("nvlink", device_arena_bytes=64 << 20, exit_on_sending_failure=True, timeout_in_ms=30000, **comm),
                      "device": f"cuda:{dev}", "barrier_on_initializing": True})
     return fed, dev
 
@@ -71,7 +71,7 @@ def _tensor_dag(party, addresses, wire):
 @pytest.mark.parametrize("wire", [None, "bf16"])
 def test_cuda_tensors_travel_over_nvlink(wire):
     addresses = make_addresses(["alice", "bob"])
-    run_parties(_tensor_dag, ["alice", "bob"], args=(addresses, wire), timeout=240)
+    run_parties(_tensor_dag, ["alice", "bob"], args=(addresses, wire), timeout=120)
 
 
 def _fedavg(party, addresses, kind):
@@ -110,4 +110,4 @@ def _fedavg(party, addresses, kind):
 @pytest.mark.parametrize("kind", ["fedavg", "fedavgm"])
 def test_fedavg_two_parties_fused_aggregate(kind):
     addresses = make_addresses(["alice", "bob"])
-    run_parties(_fedavg, ["alice", "bob"], args=(addresses, kind), timeout=300)
+    run_parties(_fedavg, ["alice", "bob"], args=(addresses, kind), timeout=150)
