@@ -323,7 +323,16 @@ def shutdown_runtime(wait: bool = True):
         rt.shutdown(wait)
 
 
-atexit.register(lambda: shutdown_runtime(False))
+def _atexit_shutdown():
+    # Join worker/transport threads while the interpreter is still fully alive:
+    # a native thread that wakes up during finalisation cannot take the GIL.
+    try:
+        shutdown_runtime(True)
+    except Exception:  # noqa: BLE001
+        pass
+
+
+atexit.register(_atexit_shutdown)
 
 
 def get(refs, timeout: Optional[float] = None):

@@ -33,6 +33,30 @@ class SeqCounter {
   std::atomic<uint64_t> v_{0};
 };
 
+// Block on a Ref without starving Python signal handlers: the wait is sliced and
+// PyErr_CheckSignals() runs between slices, so SIGINT (the exit-on-failure path,
+// fed/cleanup.py:112-128) interrupts a blocked fed.get like it interrupts ray.get.
+bool wait_interruptible(Ref& r, double timeout_s) {
+  if (r.done()) return true;
+  const double slice = 0.05;
+  auto start = std::chrono::steady_clock::now();
+  for (;;) {
+    double remaining = slice;
+    if (timeout_s >= 0) {
+      double left = timeout_s - std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+      if (left <= 0) return r.done();
+      remaining = std::min(slice, left);
+    }
+    bool ok;
+    {
+      py::gil_scoped_release rel;
+      ok = r.wait(remaining);
+    }
+    if (ok) return true;
+    if (PyErr_CheckSignals() != 0) throw py::error_already_set();
+  }
+}
+
 // ray.wait analogue: block until `num_ready` of `refs` resolved or timeout.
 std::pair<std::vector<RefPtr>, std::vector<RefPtr>> wait_refs(const std::vector<RefPtr>& refs, size_t num_ready,
                                                               double timeout_s) {
@@ -82,32 +106,19 @@ PYBIND11_MODULE(_fedcore, m) {
       .def("is_error", &Ref::is_error)
       .def(
           "wait",
-          [](Ref& r, double timeout) {
-            py::gil_scoped_release rel;
-            return r.wait(timeout);
-          },
+          [](Ref& r, double timeout) { return wait_interruptible(r, timeout); },
           py::arg("timeout") = -1.0)
       .def(
           "result",
           [](RefPtr r, double timeout) {
-            bool ok;
-            {
-              py::gil_scoped_release rel;
-              ok = r->wait(timeout);
-            }
-            if (!ok) raise_timeout("timed out waiting for a fed Ref");
+            if (!wait_interruptible(*r, timeout)) raise_timeout("timed out waiting for a fed Ref");
             return r->result();
           },
           py::arg("timeout") = -1.0)
       .def(
           "exception",
           [](RefPtr r, double timeout) {
-            bool ok;
-            {
-              py::gil_scoped_release rel;
-              ok = r->wait(timeout);
-            }
-            if (!ok) raise_timeout("timed out waiting for a fed Ref");
+            if (!wait_interruptible(*r, timeout)) raise_timeout("timed out waiting for a fed Ref");
             return r->exception();
           },
           py::arg("timeout") = -1.0)

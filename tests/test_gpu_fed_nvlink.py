@@ -103,7 +103,9 @@ def _fedavg(party, addresses, kind):
     assert not torch.equal(b[0], b[1])  # parties diverged during local training
     exp = ((b[0] + b[1]) * 0.5).to(torch.bfloat16).float()
     assert torch.equal(a[0], a[1])  # every party holds the same global model
-    assert torch.allclose(a[0], exp, rtol=0, atol=1e-2 if kind != "fedavg" else 0)
+    # NVLS (multimem.ld_reduce) rounds the switch-side sum to bf16 before the 1/N
+    # scale, so allow one bf16 ulp; the P2P path is exact.
+    assert torch.allclose(a[0], exp, rtol=2.0 ** -7, atol=1e-6)
     fed.shutdown()
 
 
