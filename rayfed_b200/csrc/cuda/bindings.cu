@@ -444,6 +444,32 @@ PYBIND11_MODULE(_fedcuda, m) {
       py::arg("status"), py::arg("timeout_cycles"), py::arg("stream"));
 
   m.def(
+      "lora_merge",
+      [](const std::vector<uint64_t>& b, const std::vector<uint64_t>& at, uint64_t w_base, uint64_t w_base_scales,
+         uint64_t out, uint64_t out_scales, uint64_t m_rows, uint64_t n_cols, int r, float scale,
+         const std::vector<float>& weights, bool base_fp8, bool out_fp8, uint64_t stream) {
+        LoraMergeArgs a{};
+        fill_peers(a.b, b);
+        fill_peers(a.at, at);
+        a.w_base = P<const void>(w_base);
+        a.w_base_scales = P<const unsigned char>(w_base_scales);
+        a.out = P<void>(out);
+        a.out_scales = P<unsigned char>(out_scales);
+        a.m = m_rows;
+        a.n = n_cols;
+        a.r = r;
+        a.n_parties = (int)b.size();
+        a.scale = scale;
+        for (int i = 0; i < kMaxParties; ++i) a.w[i] = i < (int)weights.size() ? weights[i] : 1.f;
+        a.base_fp8 = base_fp8;
+        a.out_fp8 = out_fp8;
+        check(fedk_launch_lora_merge(&a, (cudaStream_t)(uintptr_t)stream), "fed_lora_merge launch");
+      },
+      py::arg("b"), py::arg("at"), py::arg("w_base"), py::arg("w_base_scales"), py::arg("out"),
+      py::arg("out_scales"), py::arg("m"), py::arg("n"), py::arg("r"), py::arg("scale"), py::arg("weights"),
+      py::arg("base_fp8"), py::arg("out_fp8"), py::arg("stream"));
+
+  m.def(
       "local_sgd",
       [](uint64_t w, uint64_t g, uint64_t mom, uint64_t n, float lr, float momentum, float weight_decay,
          float grad_scale, bool zero_grad, int blocks, uint64_t stream) {

@@ -74,7 +74,23 @@ struct LocalSgdArgs {
 };
 
 
+// K3 GEMM: W <- W_base + scale * sum_i w_i * B_i A_i with operands gathered from peers.
+struct LoraMergeArgs {
+  PeerPtrs b;    // B_i  [m, r] bf16, row-major, one per party (peer-mapped)
+  PeerPtrs at;   // A_i^T [n, r] bf16, row-major, one per party (peer-mapped)
+  const void* w_base;                  // [m, n] bf16, or e4m3 when base_fp8 (nullptr: dW only)
+  const unsigned char* w_base_scales;  // UE8M0 per 32 along n (base_fp8)
+  void* out;                           // [m, n] bf16, or e4m3 when out_fp8
+  unsigned char* out_scales;
+  unsigned long long m, n;
+  int r, n_parties;
+  float scale;
+  float w[kMaxParties];  // per-party weights applied to B_i while gathering (1.0 = none)
+  int base_fp8, out_fp8;
+};
+
 extern "C" {
+cudaError_t fedk_launch_lora_merge(const LoraMergeArgs* a, cudaStream_t stream);
 cudaError_t fedk_launch_push(const PushArgs* a, int mode, int blocks, int use_bulk, cudaStream_t stream);
 cudaError_t fedk_launch_unpack(const PushArgs* a, int mode, int blocks, cudaStream_t stream);
 cudaError_t fedk_launch_aggregate(const AggArgs* a, int blocks, cudaStream_t stream);

@@ -1,0 +1,283 @@
+// K3 (GEMM part): exact federated LoRA aggregation on the 5th-gen tensor cores.
+//
+// FedAvg of LoRA adapters is not "average A, average B": the quantity to
+// average is the product, dW = sum_i w_i * B_i A_i.  Written as one GEMM,
+//
+//     dW[M x N] = [B_1 ... B_P] (M x P*r)  *  [A_1 ; ... ; A_P] (P*r x N),
+//
+// the K dimension is *spread over the P parties* (SURVEY §2.D K3).  This kernel
+// fuses the all-gather with the GEMM: every CTA pulls its operand tiles straight
+// from the peers' adapter buffers over NVLink (P2P 16-byte loads from the
+// symmetric heap) into the canonical K-major SWIZZLE_128B shared-memory layout,
+// one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32, M=128,
+// N=128, K=16 per instruction) accumulating in TMEM, and the epilogue reads the
+// accumulator back with tcgen05.ld, applies  W <- W_base + scale * dW  and
+// writes bf16 — or re-quantises to block-scaled e4m3 (UE8M0 per 32 along the
+// row; one thread holds exactly one 32-element block of one row after
+// tcgen05.ld.32x32b.x32, so the block scale needs no shuffles).
+//
+// Storage convention (ours, chosen for the hardware): B_i is [M, r] row-major
+// and A_i is stored transposed, At_i = [N, r] row-major, so both operands are
+// K-major and a party's slice of K is r contiguous elements.
+#include "kernels.h"
+
+namespace fedk {
+
+constexpr int kLoraBM = 128;
+constexpr int kLoraBN = 128;
+constexpr int kLoraThreads = 128;
+
+__device__ __forceinline__ uint32_t lm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1").
+//   start address >> 4 | LBO(=1, unused for swizzled K-major) | SBO = 1024 B (8 rows x 128 B) | layout 2
+__device__ __forceinline__ uint64_t lm_make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128.
+__device__ __forceinline__ uint32_t lm_instr_desc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kLoraBN >> 3) << 17) | ((uint32_t)(kLoraBM >> 4) << 24);
+}
+
+__device__ __forceinline__ void lm_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+__device__ __forceinline__ void lm_tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Gather one operand tile (128 rows x K) from the P parties into swizzled smem.
+//   src_i(row, c) : 16-byte chunk c of row `row` of party i's [rows_total, r] matrix
+//   smem layout   : [K/64 atoms][128 rows][128 B], 16 B chunks XOR-swizzled by (row & 7)
+__device__ __forceinline__ void lm_gather_tile(unsigned char* smem, const PeerPtrs& src, int n_parties, int r,
+                                               size_t row0, size_t rows_total, const float* party_w) {
+  const int chunks_per_party = r >> 3;  // 16 B = 8 bf16
+  const int per_row = n_parties * chunks_per_party;
+  const int total = kLoraBM * per_row;
+  for (int idx = threadIdx.x; idx < total; idx += kLoraThreads) {
+    // consecutive threads -> consecutive 16 B chunks of one party's contiguous [128 x r] block
+    const int i = idx / (kLoraBM * chunks_per_party);
+    const int rem = idx - i * (kLoraBM * chunks_per_party);
+    const int row = rem / chunks_per_party;
+    const int c = rem - row * chunks_per_party;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row0 + row < rows_total) {
+      const char* p = reinterpret_cast<const char*>(src.p[i]) + ((row0 + row) * (size_t)r + (size_t)c * 8) * 2;
+      v = ld_v4(p);
+      if (party_w != nullptr && party_w[i] != 1.0f) {
+        const float w = party_w[i];
+        v.x = pack_bf16x2(bf16_lo(v.x) * w, bf16_hi(v.x) * w);
+        v.y = pack_bf16x2(bf16_lo(v.y) * w, bf16_hi(v.y) * w);
+        v.z = pack_bf16x2(bf16_lo(v.z) * w, bf16_hi(v.z) * w);
+        v.w = pack_bf16x2(bf16_lo(v.w) * w, bf16_hi(v.w) * w);
+      }
+    }
+    const int k0 = i * r + c * 8;
+    const int atom = k0 >> 6;
+    const int chunk = (k0 & 63) >> 3;
+    unsigned char* dst = smem + (size_t)atom * (kLoraBM * 128) + row * 128 + ((chunk ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(dst) = v;
+  }
+}
+
+__global__ void __launch_bounds__(kLoraThreads) fed_lora_merge_kernel(LoraMergeArgs a) {
+  extern __shared__ unsigned char lm_smem[];
+  __shared__ __align__(8) uint64_t mma_done;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int K = a.n_parties * a.r;
+  const int atoms = (K + 63) >> 6;
+  // SWIZZLE_128B atoms need a 1024 B aligned base; dynamic smem starts after the statics.
+  const uint32_t raw = lm_smem_u32(lm_smem);
+  unsigned char* tile0 = lm_smem + (((raw + 1023u) & ~1023u) - raw);
+  unsigned char* sA = tile0;                                      // B_cat tile: rows of W  (M operand)
+  unsigned char* sB = tile0 + (size_t)atoms * (kLoraBM * 128);    // At_cat tile: cols of W (N operand)
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const size_t m0 = (size_t)blockIdx.y * kLoraBM;
+  const size_t n0 = (size_t)blockIdx.x * kLoraBN;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     lm_smem_u32(&tmem_base_slot)),
+                 "n"(kLoraBN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lm_smem_u32(&mma_done)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  // ---- all-gather of the operand tiles, fused: peers' memory -> my smem ------------------
+  lm_gather_tile(sA, a.b, a.n_parties, a.r, m0, a.m, a.w);
+  lm_gather_tile(sB, a.at, a.n_parties, a.r, n0, a.n, nullptr);
+  // generic-proxy smem writes must be visible to the tensor core (async proxy)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_slot;
+
+  // ---- one thread drives the tensor core ---------------------------------------------------
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = lm_instr_desc();
+    const uint32_t a_base = lm_smem_u32(sA), b_base = lm_smem_u32(sB);
+    const int ksteps = K >> 4;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint32_t off = (uint32_t)(ks >> 2) * (kLoraBM * 128) + (uint32_t)(ks & 3) * 32;  // atom + 32 B per K=16
+      lm_mma(tmem_d, lm_make_desc(a_base + off), lm_make_desc(b_base + off), idesc, ks > 0 ? 1u : 0u);
+    }
+    // commit: mbarrier arrives when every MMA above has finished writing TMEM
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     lm_smem_u32(&mma_done))
+                 : "memory");
+  }
+
+  // ---- epilogue: TMEM -> registers -> W = W_base + scale * dW -> global ---------------------
+  {
+    uint32_t done;
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(lm_smem_u32(&mma_done)), "r"(0u)
+          : "memory");
+    } while (!done);
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  const size_t row = m0 + (size_t)warp * 32 + lane;  // warp w owns TMEM lanes 32w..32w+31
+  const float scale = a.scale;
+#pragma unroll 1
+  for (int c = 0; c < kLoraBN / 32; ++c) {
+    uint32_t v[32];
+    lm_tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+    const size_t col = n0 + (size_t)c * 32;
+    if (row < a.m && col < a.n) {
+      float acc[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc[k] = __uint_as_float(v[k]) * scale;
+      const size_t e = row * a.n + col;
+      if (a.w_base) {
+        if (!a.base_fp8) {
+          const uint4* wb = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.w_base) + e);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 x = wb[q];
+            acc[q * 8 + 0] += bf16_lo(x.x); acc[q * 8 + 1] += bf16_hi(x.x);
+            acc[q * 8 + 2] += bf16_lo(x.y); acc[q * 8 + 3] += bf16_hi(x.y);
+            acc[q * 8 + 4] += bf16_lo(x.z); acc[q * 8 + 5] += bf16_hi(x.z);
+            acc[q * 8 + 6] += bf16_lo(x.w); acc[q * 8 + 7] += bf16_hi(x.w);
+          }
+        } else {
+          const unsigned char* wq = reinterpret_cast<const unsigned char*>(a.w_base) + e;
+          const float s = __uint_as_float((uint32_t)a.w_base_scales[e >> 5] << 23);
+          const uint4* w4 = reinterpret_cast<const uint4*>(wq);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint4 x = w4[q];
+            uint32_t ws[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __half2_raw lo = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(ws[j] & 0xffffu), __NV_E4M3);
+              __half2_raw hi = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(ws[j] >> 16), __NV_E4M3);
+              float2 f0 = __half22float2(*reinterpret_cast<__half2*>(&lo));
+              float2 f1 = __half22float2(*reinterpret_cast<__half2*>(&hi));
+              acc[q * 16 + j * 4 + 0] += f0.x * s; acc[q * 16 + j * 4 + 1] += f0.y * s;
+              acc[q * 16 + j * 4 + 2] += f1.x * s; acc[q * 16 + j * 4 + 3] += f1.y * s;
+            }
+          }
+        }
+      }
+      if (!a.out_fp8) {
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + e);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 y;
+          y.x = pack_bf16x2(acc[q * 8 + 0], acc[q * 8 + 1]);
+          y.y = pack_bf16x2(acc[q * 8 + 2], acc[q * 8 + 3]);
+          y.z = pack_bf16x2(acc[q * 8 + 4], acc[q * 8 + 5]);
+          y.w = pack_bf16x2(acc[q * 8 + 6], acc[q * 8 + 7]);
+          o[q] = y;
+        }
+      } else {
+        float amax = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) amax = fmaxf(amax, fabsf(acc[k]));
+        float rr = amax * (1.0f / 448.0f);
+        uint32_t bits = __float_as_uint(rr);
+        uint32_t eb = (bits >> 23) & 0xffu;
+        if (bits & 0x7fffffu) eb += 1;
+        eb = eb < 1u ? 1u : (eb > 253u ? 253u : eb);
+        const float inv = __uint_as_float((254u - eb) << 23);
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(a.out) + e);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t lo = __nv_cvt_float2_to_fp8x2(
+                make_float2(acc[q * 16 + j * 4 + 0] * inv, acc[q * 16 + j * 4 + 1] * inv), __NV_SATFINITE, __NV_E4M3);
+            uint32_t hi = __nv_cvt_float2_to_fp8x2(
+                make_float2(acc[q * 16 + j * 4 + 2] * inv, acc[q * 16 + j * 4 + 3] * inv), __NV_SATFINITE, __NV_E4M3);
+            w[j] = lo | (hi << 16);
+          }
+          o[q] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        a.out_scales[e >> 5] = (unsigned char)eb;
+      }
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kLoraBN) : "memory");
+  }
+}
+
+extern "C" cudaError_t fedk_launch_lora_merge(const LoraMergeArgs* a, cudaStream_t stream) {
+  const int K = a->n_parties * a->r;
+  if (a->r % 16 != 0 || K > 256 || K < 16) return cudaErrorInvalidValue;
+  if (a->n % 32 != 0) return cudaErrorInvalidValue;
+  const int atoms = (K + 63) / 64;
+  const int smem = 2 * atoms * kLoraBM * 128 + 1024;  // + slack for the 1024 B alignment
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(fed_lora_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  dim3 grid((unsigned)((a->n + kLoraBN - 1) / kLoraBN), (unsigned)((a->m + kLoraBM - 1) / kLoraBM));
+  fed_lora_merge_kernel<<<grid, kLoraThreads, smem, stream>>>(*a);
+  return cudaGetLastError();
+}
+
+}  // namespace fedk

@@ -34,6 +34,7 @@ from .kernels import (  # noqa: F401
     cuda_ext,
     launch_counter,
     local_sgd,
+    lora_merge,
     push,
     sm_count,
     unpack,

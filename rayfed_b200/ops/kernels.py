@@ -182,6 +182,25 @@ def barrier(*, n_parties: int, my_rank: int, sig_ptr: int, sig_peers: Sequence[i
     launch_counter.add("fed_barrier")
 
 
+def lora_merge(*, b_ptrs: Sequence[int], at_ptrs: Sequence[int], out_ptr: int, m: int, n: int, r: int,
+               scale: Optional[float] = None, weights: Optional[Sequence[float]] = None, w_base_ptr: int = 0,
+               w_base_scales_ptr: int = 0, out_scales_ptr: int = 0, base_fp8: bool = False, out_fp8: bool = False,
+               stream=None) -> None:
+    """K3 GEMM (tcgen05/TMEM): ``out = W_base + scale * sum_i w_i * B_i @ A_i`` with the
+    operands gathered from every party's adapter buffers. ``B_i``: [m, r]; ``A_i^T``: [n, r]."""
+    p = len(b_ptrs)
+    if scale is None:
+        scale = 1.0 / p
+    if r % 16 or not (16 <= p * r <= 256):
+        raise ValueError(f"lora_merge needs r % 16 == 0 and 16 <= parties*r <= 256 (got r={r}, parties={p})")
+    if n % 32:
+        raise ValueError("lora_merge needs n % 32 == 0")
+    cuda_ext().lora_merge(list(b_ptrs), list(at_ptrs), w_base_ptr, w_base_scales_ptr, out_ptr, out_scales_ptr, m, n,
+                          r, float(scale), [float(w) for w in (weights or [1.0] * p)], bool(base_fp8),
+                          bool(out_fp8), _stream_handle(stream))
+    launch_counter.add("fed_lora_merge")
+
+
 def local_sgd(w_ptr: int, g_ptr: int, mom_ptr: int, n: int, *, lr: float, momentum: float = 0.0,
               weight_decay: float = 0.0, grad_scale: float = 1.0, zero_grad: bool = True, stream=None,
               device_index: int = 0, blocks: Optional[int] = None) -> None:

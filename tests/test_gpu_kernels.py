@@ -251,3 +251,53 @@ def test_two_virtual_parties_on_one_gpu_rendezvous_in_kernel():
     ref = ((xs[0].float() + xs[1].float()) * 0.5).to(torch.bfloat16)
     assert torch.equal(bufs[0], ref) and torch.equal(bufs[1], ref)
     assert pads[0][15000].item() == 0 and pads[1][15000].item() == 0
+
+
+# -- K3: tcgen05/TMEM LoRA merge -----------------------------------------------------------------
+@pytest.mark.parametrize("parties,r,m,n", [(2, 16, 256, 256), (8, 16, 512, 384), (4, 32, 128, 1024), (1, 64, 200, 96)])
+def test_lora_merge_tcgen05_matches_torch(parties, r, m, n):
+    torch.manual_seed(parties * 1000 + r)
+    Bs = [(torch.randn(m, r, device=DEV) * 0.5).to(torch.bfloat16) for _ in range(parties)]
+    Ats = [(torch.randn(n, r, device=DEV) * 0.5).to(torch.bfloat16) for _ in range(parties)]
+    base = torch.randn(m, n, device=DEV).to(torch.bfloat16)
+    out = torch.zeros(m, n, dtype=torch.bfloat16, device=DEV)
+    weights = [1.0] * parties
+    weights[0] = 0.5
+    K.lora_merge(b_ptrs=[b.data_ptr() for b in Bs], at_ptrs=[a.data_ptr() for a in Ats], out_ptr=out.data_ptr(),
+                 m=m, n=n, r=r, scale=1.0 / parties, weights=weights, w_base_ptr=base.data_ptr())
+    torch.cuda.synchronize()
+    dw = torch.zeros(m, n, device=DEV)
+    for i, (b, at) in enumerate(zip(Bs, Ats)):
+        bw = (b.float() * weights[i]).to(torch.bfloat16).float() if weights[i] != 1.0 else b.float()
+        dw += bw @ at.float().t()
+    ref = (base.float() + dw / parties).to(torch.bfloat16)
+    err = (out.float() - ref.float()).abs().max().item()
+    assert err <= 2 ** -6 * max(1.0, ref.float().abs().max().item()), err
+    assert torch.equal(out, ref) or (out.float() - ref.float()).abs().mean().item() < 1e-3
+
+
+def test_lora_merge_fp8_base_and_out():
+    parties, r, m, n = 4, 16, 256, 256
+    torch.manual_seed(7)
+    Bs = [(torch.randn(m, r, device=DEV) * 0.3).to(torch.bfloat16) for _ in range(parties)]
+    Ats = [(torch.randn(n, r, device=DEV) * 0.3).to(torch.bfloat16) for _ in range(parties)]
+    w = torch.randn(m, n, device=DEV)
+    e = torch.ceil(torch.log2(w.view(m, -1, 32).abs().amax(-1, keepdim=True) / 448.0))
+    wq = (w.view(m, -1, 32) / torch.exp2(e)).to(torch.float8_e4m3fn)
+    base_q = wq.view(m, n).view(torch.uint8).contiguous()
+    base_s = (e.view(m, n // 32) + 127).to(torch.uint8).contiguous()
+    out_q = torch.zeros(m, n, dtype=torch.uint8, device=DEV)
+    out_s = torch.zeros(m, n // 32, dtype=torch.uint8, device=DEV)
+    K.lora_merge(b_ptrs=[b.data_ptr() for b in Bs], at_ptrs=[a.data_ptr() for a in Ats], out_ptr=out_q.data_ptr(),
+                 m=m, n=n, r=r, w_base_ptr=base_q.data_ptr(), w_base_scales_ptr=base_s.data_ptr(),
+                 out_scales_ptr=out_s.data_ptr(), base_fp8=True, out_fp8=True)
+    torch.cuda.synchronize()
+    base_deq = (wq.float() * torch.exp2(e)).view(m, n)
+    dw = sum(b.float() @ at.float().t() for b, at in zip(Bs, Ats)) / parties
+    ref = base_deq + dw
+    got = (out_q.view(torch.float8_e4m3fn).float().view(m, -1, 32)
+           * torch.exp2(out_s.float().view(m, -1, 1) - 127)).view(m, n)
+    rel = ((got - ref).abs().mean() / ref.abs().mean()).item()
+    assert rel < 0.04, rel  # e4m3 has 3 mantissa bits
+    e_ref = torch.ceil(torch.log2(ref.view(m, -1, 32).abs().amax(-1) / 448.0))
+    assert (out_s.float() - 127 - e_ref).abs().max().item() <= 1
