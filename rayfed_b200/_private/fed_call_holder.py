@@ -15,7 +15,7 @@ import logging
 
 from ..fed_object import FedObject
 from ..proxy.barriers import send
-from ..tree_util import tree_flatten
+from ..tree_util import has_containers, tree_flatten
 from ..utils import resolve_dependencies
 from .global_context import get_global_context
 
@@ -54,7 +54,10 @@ class FedCallHolder:
             return FedObject(self._node_party, fed_task_id, refs)
 
         # Not ours to run: feed the owner whatever it needs from us.
-        leaves, _ = tree_flatten((args, kwargs))
+        if has_containers(args, kwargs):
+            leaves, _ = tree_flatten((args, kwargs))
+        else:
+            leaves = list(args) + (list(kwargs.values()) if kwargs else [])
         for arg in leaves:
             if type(arg) is FedObject and arg.get_party() == self._party:
                 if arg._was_sending_or_sent_to_party(self._node_party):

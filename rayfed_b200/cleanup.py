@@ -17,6 +17,7 @@ from __future__ import annotations
 import logging
 import os
 import signal
+import threading
 
 from ._private.message_queue import MessageQueueManager
 from .exceptions import FedRemoteError, FedTaskError
@@ -37,6 +38,11 @@ class CleanupManager:
         self._last_sending_error = None
         self._exit_on_sending_failure = False
         self._expose_error_trace = False
+        # sends whose outcome is not known yet; success is retired by a completion
+        # callback, only failures are handed to the queue threads
+        self._pending = 0
+        self._pending_err = 0
+        self._pending_cv = threading.Condition()
 
     def start(self, exit_on_sending_failure=False, expose_error_trace=False):
         self._exit_on_sending_failure = exit_on_sending_failure
@@ -45,17 +51,63 @@ class CleanupManager:
         self._sending_error_q.start()
         logger.debug("Started the send-checking threads.")
 
-    def stop(self, wait_for_sending=False):
+    def stop(self, wait_for_sending=False, drain_timeout_s: float = 600.0, error_drain_timeout_s: float = 10.0):
+        """Stop watching sends.
+
+        ``wait_for_sending`` waits for every *unresolved* send first.  Failures
+        that were already detected are always processed, and the replacement
+        errors they trigger are given a bounded time to reach the peer —
+        otherwise a party that shuts down right after a failure would leave its
+        peers waiting for data that will never come.
+        """
+        if wait_for_sending:
+            with self._pending_cv:
+                self._pending_cv.wait_for(lambda: self._pending <= 0 or not self._sending_data_q.is_started(),
+                                          timeout=drain_timeout_s)
         # Data queue first: draining it may enqueue replacement errors.
-        self._sending_data_q.stop(wait_for_sending=wait_for_sending)
+        self._sending_data_q.stop(wait_for_sending=True)
+        with self._pending_cv:
+            self._pending_cv.wait_for(lambda: self._pending_err <= 0, timeout=error_drain_timeout_s)
         self._sending_error_q.stop(wait_for_sending=wait_for_sending)
 
     def push_to_sending(self, obj_ref, dest_party: str = None, upstream_seq_id=-1, downstream_seq_id=-1,
                         is_error: bool = False):
-        """Queue the future of a send for checking. The seq ids are only needed
-        if a replacement error has to be shipped under the same key."""
+        """Watch the future of a send.  The seq ids are only needed if a
+        replacement error has to be shipped under the same key.
+
+        Unlike the reference (one ``ray.get`` per send on a polling thread,
+        fed/cleanup.py:150-152) a successful send is retired by its completion
+        callback; only failures go through the queue thread."""
         pack = (obj_ref, dest_party, upstream_seq_id, downstream_seq_id)
-        (self._sending_error_q if is_error else self._sending_data_q).append(pack)
+        with self._pending_cv:
+            self._pending += 1
+            if is_error:
+                self._pending_err += 1
+        q = self._sending_error_q if is_error else self._sending_data_q
+
+        def on_done(r):
+            ok = False
+            try:
+                ok = r.exception() is None and bool(r.result())
+            except BaseException:  # noqa: BLE001
+                ok = False
+            if ok or not q.is_started():
+                self._retire(is_error)
+            else:
+                q.append(pack)
+
+        obj_ref.add_done_callback(on_done)
+
+    def _retire(self, is_error: bool = False):
+        with self._pending_cv:
+            self._pending -= 1
+            if is_error:
+                self._pending_err -= 1
+            if self._pending <= 0 or self._pending_err <= 0:
+                self._pending_cv.notify_all()
+
+    def pending_sends(self) -> int:
+        return self._pending
 
     def get_last_sending_error(self):
         return self._last_sending_error
@@ -67,6 +119,12 @@ class CleanupManager:
             os.kill(os.getpid(), signal.SIGINT)
 
     def _process_data_sending_task_return(self, message):
+        try:
+            return self._handle_failed_data_send(message)
+        finally:
+            self._retire()
+
+    def _handle_failed_data_send(self, message):
         obj_ref, dest_party, upstream_seq_id, downstream_seq_id = message
         try:
             res = obj_ref.result()
@@ -99,6 +157,12 @@ class CleanupManager:
         return True
 
     def _process_error_sending_task_return(self, error_msg):
+        try:
+            return self._handle_failed_error_send(error_msg)
+        finally:
+            self._retire(True)
+
+    def _handle_failed_error_send(self, error_msg):
         error_ref, dest_party, upstream_seq_id, downstream_seq_id = error_msg
         try:
             res = error_ref.result()

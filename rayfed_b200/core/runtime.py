@@ -48,8 +48,14 @@ def native():
     return _native
 
 
+_REF_T = None
+
+
 def _ref_type():
-    return native().Ref
+    global _REF_T
+    if _REF_T is None:
+        _REF_T = native().Ref
+    return _REF_T
 
 
 class _RefMeta(type):
@@ -66,7 +72,7 @@ class Ref(metaclass=_RefMeta):
 
 
 def is_ref(obj) -> bool:
-    return isinstance(obj, _ref_type())
+    return type(obj) is (_REF_T or _ref_type())
 
 
 def is_refs(objs) -> bool:

@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import asyncio
 import inspect
+import itertools
 import logging
 import threading
 import time
@@ -141,12 +142,13 @@ class ProxyHost:
         self._job_name = job_name
         self._proxy_instance = proxy
         self._role = role
-        self._stats = {}
-        if role in ("sender", "sender_receiver"):
-            self._stats["send_op_count"] = 0
-        if role in ("receiver", "sender_receiver"):
-            self._stats["receive_op_count"] = 0
-        self._stats_lock = threading.Lock()
+        # itertools.count.__next__ is atomic under the GIL: lock-free op counters
+        self._send_ops = itertools.count(1) if role in ("sender", "sender_receiver") else None
+        self._recv_ops = itertools.count(1) if role in ("receiver", "sender_receiver") else None
+        self._send_seen = 0
+        self._recv_seen = 0
+        self._native_refs = bool(getattr(proxy, "REFS_RAISE_REMOTE_ERRORS", False))
+        self._device_aware = bool(getattr(proxy, "DEVICE_AWARE", False))
         self._loop: Optional[_LoopThread] = _LoopThread(f"{name}-loop") if _needs_loop(proxy) else None
         self._start_future = None
 
@@ -228,27 +230,29 @@ class ProxyHost:
             raise FedGetTimeoutError(f"proxy {self._name} was not ready within {timeout}s") from None
 
     def send(self, dest_party, data, upstream_seq_id, downstream_seq_id, is_error=False):
-        """Issue the push; returns a `Ref` → True/False (transport errors are
-        swallowed into False like fed/proxy/barriers.py:170-172)."""
-        with self._stats_lock:
-            self._stats["send_op_count"] += 1
-        result = native().Ref()
-        assert dest_party in self._proxy_instance._addresses, (
-            f"Failed to find {dest_party} in addresses {self._proxy_instance._addresses}."
-        )
+        """Issue the push; returns a `Ref` that resolves truthy on success.  A
+        transport failure resolves to False (generic proxies, like
+        fed/proxy/barriers.py:170-172) or raises from the ack future (native
+        proxies) — the CleanupManager treats both as a failed send."""
+        self._send_seen = next(self._send_ops)
         try:
-            if type(data) is _Produced and not getattr(self._proxy_instance, "DEVICE_AWARE", False):
+            if type(data) is _Produced and not self._device_aware:
                 # host-only transport: the value must be complete before pickling
                 if data.event is not None:
                     data.event.synchronize()
                 data = data.value
             out = self._proxy_instance.send(dest_party, data, upstream_seq_id, downstream_seq_id)
+        except KeyError:
+            raise AssertionError(
+                f"Failed to find {dest_party} in addresses {self._proxy_instance._addresses}.") from None
         except BaseException as e:  # noqa: BLE001
             logger.error(f"Failed to {'send error' if is_error else 'send'} to {dest_party}: {e!r}")
+            result = native().Ref()
             result.set_value(False)
             return result
-
-        # transport-level failures resolve to False; success to the response
+        if self._native_refs and is_ref(out):
+            return out  # the C++ ack future: True, or raises the transport error
+        result = native().Ref()
         inner = native().Ref()
         self._into_ref(out, inner)
 
@@ -271,10 +275,9 @@ class ProxyHost:
         """`Ref` of the message keyed (upstream, curr). A delivered
         ``FedRemoteError`` becomes the Ref's *error*, wrapped like a failed
         local task (parity: fed/proxy/barriers.py:227-233)."""
-        with self._stats_lock:
-            self._stats["receive_op_count"] += 1
+        self._recv_seen = next(self._recv_ops)
         out = self._proxy_instance.get_data(src_party, upstream_seq_id, curr_seq_id)
-        if is_ref(out) and getattr(self._proxy_instance, "REFS_RAISE_REMOTE_ERRORS", False):
+        if self._native_refs and is_ref(out):
             return out  # native transports already complete the Ref correctly
         result = native().Ref()
 
@@ -288,8 +291,11 @@ class ProxyHost:
         return result
 
     def _get_stats(self):
-        with self._stats_lock:
-            stats = dict(self._stats)
+        stats = {}
+        if self._send_ops is not None:
+            stats["send_op_count"] = self._send_seen
+        if self._recv_ops is not None:
+            stats["receive_op_count"] = self._recv_seen
         extra = getattr(self._proxy_instance, "get_stats", None)
         if callable(extra):
             try:
@@ -417,52 +423,50 @@ def _stop_proxies():
 
 
 # ---------------------------------------------------------------------------
+def _copy_outcome(src, dst):
+    e = src.exception()
+    if e is not None:
+        dst.set_error(e)
+    else:
+        dst.set_value(src.result())
+
+
 def send(dest_party, data, upstream_seq_id, downstream_seq_id, is_error=False, check_sending=True):
     """Push ``data`` (a value or the `Ref` of one) to ``dest_party``.
 
     Returns the `Ref` of the send outcome.  When ``data`` is an unresolved
-    `Ref` the push is released by the scheduler once the producer finishes; if
-    the producer *failed*, the outcome Ref carries that ``FedTaskError`` — which
-    is how the CleanupManager tells "producer failed" from "link failed".
+    `Ref` the push is issued by a completion callback on the thread that
+    finishes the producer (no polling, no extra thread hop); if the producer
+    *failed*, the outcome Ref carries that ``FedTaskError`` — which is how the
+    CleanupManager tells "producer failed" from "link failed".
     """
     host: ProxyHost = get_runtime().get_named(sender_proxy_actor_name())
-    result = native().Ref()
-
-    def issue(value):
-        try:
-            inner = host.send(dest_party, value, upstream_seq_id, downstream_seq_id, is_error)
-        except BaseException as e:  # noqa: BLE001
-            result.set_error(e)
-            return
-
-        def chain(r):
-            e = r.exception()
-            if e is not None:
-                result.set_error(e)
-            else:
-                result.set_value(r.result())
-
-        inner.add_done_callback(chain)
-
     if is_ref(data):
         if data.done():
-            _issue_from_ref(data, issue, result)
+            e = data.exception()
+            if e is not None:
+                result = native().Ref()
+                result.set_error(e)
+            else:
+                result = host.send(dest_party, data.result(), upstream_seq_id, downstream_seq_id, is_error)
         else:
-            # run the (possibly heavy) serialisation on a pool thread once ready
-            def on_ready(value):
-                issue(value)
-                return None
+            result = native().Ref()
 
-            gate = get_runtime()._executor.submit(0, on_ready, (data,), None, 1)[0]
-
-            def gate_done(r):
+            def on_ready(r):
                 e = r.exception()
-                if e is not None and not result.done():
+                if e is not None:
                     result.set_error(e)
+                    return
+                try:
+                    inner = host.send(dest_party, r.result(), upstream_seq_id, downstream_seq_id, is_error)
+                except BaseException as ex:  # noqa: BLE001
+                    result.set_error(ex)
+                    return
+                inner.add_done_callback(lambda a: _copy_outcome(a, result))
 
-            gate.add_done_callback(gate_done)
+            data.add_done_callback(on_ready)
     else:
-        issue(data)
+        result = host.send(dest_party, data, upstream_seq_id, downstream_seq_id, is_error)
 
     if check_sending:
         ctx = get_global_context()
@@ -471,14 +475,6 @@ def send(dest_party, data, upstream_seq_id, downstream_seq_id, is_error=False, c
                 result, dest_party, upstream_seq_id, downstream_seq_id, is_error
             )
     return result
-
-
-def _issue_from_ref(data_ref, issue, result):
-    e = data_ref.exception()
-    if e is not None:
-        result.set_error(e)
-    else:
-        issue(data_ref.result())
 
 
 def recv(party: str, src_party: str, upstream_seq_id, curr_seq_id):

@@ -81,7 +81,30 @@ class TreeSpec:
 LEAF_SPEC = TreeSpec(None, None, ())
 
 
+_SCALAR_LEAVES = frozenset({type(None), bool, int, float, str, bytes, complex})
+
+
+def has_containers(args, kwargs) -> bool:
+    """Cheap pre-check used on the per-call hot path: is there anything to flatten?"""
+    for a in args:
+        t = type(a)
+        if t in _SCALAR_LEAVES:
+            continue
+        if t in _REGISTRY or isinstance(a, tuple):
+            return True
+    if kwargs:
+        for a in kwargs.values():
+            t = type(a)
+            if t in _SCALAR_LEAVES:
+                continue
+            if t in _REGISTRY or isinstance(a, tuple):
+                return True
+    return False
+
+
 def _node_def(obj) -> Optional[_NodeDef]:
+    if type(obj) in _SCALAR_LEAVES:
+        return None
     nd = _REGISTRY.get(type(obj))
     if nd is not None:
         return nd

@@ -16,7 +16,7 @@ from typing import Dict, Optional
 
 from ..core import is_ref, is_refs
 from ..fed_object import FedObject
-from ..tree_util import tree_flatten, tree_unflatten
+from ..tree_util import has_containers, tree_flatten, tree_unflatten
 
 logger = logging.getLogger(__name__)
 
@@ -44,6 +44,21 @@ def resolve_dependencies(current_party, current_fed_task_id, *args, **kwargs):
     task body as futures and are read with ``fed.get`` (same as the reference).
     """
     from ..proxy.barriers import recv
+
+    if not has_containers(args, kwargs):
+        # hot path: flat argument list, no pytree walk
+        def resolve(arg):
+            if type(arg) is not FedObject:
+                return arg
+            if arg.get_party() == current_party:
+                return arg.get_ref()
+            ref = arg.get_ref()
+            if ref is None:
+                ref = recv(current_party, arg.get_party(), arg.get_fed_task_id(), current_fed_task_id)
+                arg._cache_ref(ref)
+            return ref
+
+        return tuple(resolve(a) for a in args), {k: resolve(v) for k, v in kwargs.items()} if kwargs else {}
 
     leaves, spec = tree_flatten((args, kwargs))
     for i, arg in enumerate(leaves):
