@@ -115,7 +115,10 @@ def test_grpc_metadata_and_job_name_reach_the_server():
         assert seen["key"] == ("0", "1")
     finally:
         _teardown()
-        asyncio.run_coroutine_threadsafe(holder["server"].stop(0), loop).result(5)
+        try:  # best-effort stop of the fake server (a daemon thread owns its loop)
+            asyncio.run_coroutine_threadsafe(holder["server"].stop(None), loop).result(2)
+        except Exception:  # noqa: BLE001
+            pass
 
 
 @pytest.mark.parametrize("transport", ["native", "grpc"])
