@@ -78,6 +78,38 @@ def main():
     t = timed(agg_sgd)
     byts = n * (2 + 2 + 16)
     out["aggregate_fedavgm_n1"] = {"us": t * 1e6, "GBps": byts / t / 1e9, "frac_hbm": byts / t / hbm}
+    # pre-baked plan (what FedAggregator uses): launch overhead = one pybind call
+    for kind, name in ((K.AGG_AVG, "avg"), (K.AGG_FEDAVGM, "fedavgm")):
+        plan = K.AggregatePlan(inputs=[buf.data_ptr()], outputs=[buf.data_ptr()], my_rank=0, shard_start=0,
+                               shard_len=n, kind=kind, master_ptr=master.data_ptr(), mom_ptr=mom.data_ptr(), lr=1.0,
+                               momentum=0.9, sig_ptr=base + 8192, sig_peers=[base + 8192], epoch_dev_ptr=base + 256,
+                               agg_done_ptr=base + 260, status_ptr=base + 264, timeout_cycles=int(5e9))
+        t = timed(lambda: plan.launch(0, 1))
+        byts = n * (4 if kind == K.AGG_AVG else 20)
+        out[f"aggregate_plan_{name}_n1"] = {"us": t * 1e6, "GBps": byts / t / 1e9, "frac_hbm": byts / t / hbm}
+    tiny = torch.zeros(4096, dtype=torch.bfloat16, device=dev)
+    plan = K.AggregatePlan(inputs=[tiny.data_ptr()], outputs=[tiny.data_ptr()], my_rank=0, shard_start=0,
+                           shard_len=4096, kind=K.AGG_AVG, sig_ptr=base + 8192, sig_peers=[base + 8192],
+                           epoch_dev_ptr=base + 256, agg_done_ptr=base + 260, status_ptr=base + 264,
+                           timeout_cycles=int(5e9))
+    t = timed(lambda: plan.launch(0, 1), iters=200)
+    out["aggregate_plan_launch_floor_us"] = t * 1e6
+    # K3 tcgen05 LoRA merge, Llama-3-8B q_proj shape, 8 parties x r=16 (loopback operands)
+    P, r, M, N = 8, 16, 4096, 4096
+    Bs = [(torch.randn(M, r, device=dev) * 0.1).to(torch.bfloat16) for _ in range(P)]
+    Ats = [(torch.randn(N, r, device=dev) * 0.1).to(torch.bfloat16) for _ in range(P)]
+    W = torch.randn(M, N, device=dev).to(torch.bfloat16)
+    Wout = torch.empty_like(W)
+    t = timed(lambda: K.lora_merge(b_ptrs=[b.data_ptr() for b in Bs], at_ptrs=[a.data_ptr() for a in Ats],
+                                   out_ptr=Wout.data_ptr(), m=M, n=N, r=r, w_base_ptr=W.data_ptr()))
+    byts = 2 * M * N * 2
+    flops = 2.0 * M * N * P * r
+    out["lora_merge_4096x4096_k128"] = {"us": t * 1e6, "GBps": byts / t / 1e9, "frac_hbm": byts / t / hbm,
+                                        "TFLOPs": flops / t / 1e12}
+    Bc = torch.cat(Bs, 1)
+    Ac = torch.cat(Ats, 1)
+    t = timed(lambda: torch.addmm(W, Bc, Ac.t(), alpha=1.0 / P, out=Wout))
+    out["torch_addmm_same_shape"] = {"us": t * 1e6, "GBps": byts / t / 1e9}
     g = torch.randn(n, device=dev).to(torch.bfloat16)
     mo = torch.zeros(n, device=dev)
     for blocks in (296, 592, 1184):
