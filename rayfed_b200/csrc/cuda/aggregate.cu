@@ -83,18 +83,33 @@ __device__ __forceinline__ uint32_t agg_quant4(float a, float b, float c, float 
 
 // Optimizer/server update for 8 consecutive elements held in registers, then the
 // all-gather store of the result to every party (or one multicast store).
+// Optimizer state of one 8-element vector, fetched together with the contributions
+// so that its HBM latency overlaps theirs.
+struct StateRegs {
+  float4 m0, m1, q0, q1, r0, r1;
+};
+
+__device__ __forceinline__ void load_state(const AggArgs& a, size_t v, StateRegs& st) {
+  const size_t s0 = v << 3;
+  st.m0 = *reinterpret_cast<const float4*>(a.master + s0);
+  st.m1 = *reinterpret_cast<const float4*>(a.master + s0 + 4);
+  st.q0 = *reinterpret_cast<const float4*>(a.mom + s0);
+  st.q1 = *reinterpret_cast<const float4*>(a.mom + s0 + 4);
+  if (a.kind == kAdamGrad || a.kind == kFedAdam) {
+    st.r0 = *reinterpret_cast<const float4*>(a.var + s0);
+    st.r1 = *reinterpret_cast<const float4*>(a.var + s0 + 4);
+  }
+}
+
 template <bool kUseMc>
 __device__ __forceinline__ void finish_vector(const AggArgs& a, size_t v, size_t nvec, bool live, float* acc,
-                                              int lane) {
+                                              int lane, const StateRegs& st) {
   const int N = a.n_parties;
   const size_t e0 = a.shard_start + (v << 3);
   if (live && a.kind != kAvg) {
     const size_t s0 = v << 3;  // index into the local shard state
-    float4 m0 = *reinterpret_cast<const float4*>(a.master + s0);
-    float4 m1 = *reinterpret_cast<const float4*>(a.master + s0 + 4);
+    const float4 m0 = st.m0, m1 = st.m1, q0 = st.q0, q1 = st.q1;
     float ms[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-    float4 q0 = *reinterpret_cast<const float4*>(a.mom + s0);
-    float4 q1 = *reinterpret_cast<const float4*>(a.mom + s0 + 4);
     float mo[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
     if (a.kind == kFedAvgM || a.kind == kSgdGrad) {
 #pragma unroll
@@ -105,8 +120,7 @@ __device__ __forceinline__ void finish_vector(const AggArgs& a, size_t v, size_t
         acc[k] = ms[k];
       }
     } else {
-      float4 r0 = *reinterpret_cast<const float4*>(a.var + s0);
-      float4 r1 = *reinterpret_cast<const float4*>(a.var + s0 + 4);
+      const float4 r0 = st.r0, r1 = st.r1;
       float va[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -179,10 +193,12 @@ __device__ __forceinline__ void finish_vector(const AggArgs& a, size_t v, size_t
 // kNP = parties whose 16-byte requests are preloaded per vector, kU = vectors per
 // thread per trip; kNP * kU outstanding 16 B loads per thread (8 => 32 registers),
 // all issued before the first use, so ~1 MB/SM is in flight against NVLink latency.
-template <bool kUseMc, int kNP, int kU>
-__global__ void __launch_bounds__(512) fed_aggregate_kernel(AggArgs a) {
-  if (a.epoch_dev) a.epoch = ld_relaxed_sys_u32(a.epoch_dev);  // graph-replayable epoch
-  cta_party_barrier(a, a.epoch + 1);
+template <bool kUseMc, int kNP, int kU, bool kState>
+__global__ void __launch_bounds__(512) fed_aggregate_kernel(const __grid_constant__ AggArgs a) {
+  // graph-replayable epoch (kept in a register: writing to the parameter struct would
+  // force a local-memory copy of all 700+ bytes of it)
+  const uint32_t epoch = a.epoch_dev ? ld_relaxed_sys_u32(a.epoch_dev) : a.epoch;
+  cta_party_barrier(a, epoch + 1);
 
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -199,6 +215,8 @@ __global__ void __launch_bounds__(512) fed_aggregate_kernel(AggArgs a) {
       float acc[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+      StateRegs st;
+      if (kState && live) load_state(a, v, st);
       if (live) {
         if (kUseMc) {
           const char* p = reinterpret_cast<const char*>(a.mc_in) + e0 * 4;
@@ -232,18 +250,20 @@ __global__ void __launch_bounds__(512) fed_aggregate_kernel(AggArgs a) {
           }
         }
       }
-      finish_vector<kUseMc>(a, v, nvec, live, acc, lane);
+      finish_vector<kUseMc>(a, v, nvec, live, acc, lane, st);
     }
   } else {
     for (size_t v0 = tid; v0 < nvec_rounded; v0 += stride * kU) {
       uint4 x[kU][kNP];
       bool live[kU];
+      StateRegs st[kState ? kU : 1];
       // ---- phase 1: issue every request of this trip ------------------------------
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const size_t v = v0 + (size_t)u * stride;
         live[u] = v < nvec;
         if (live[u]) {
+          if (kState) load_state(a, v, st[u]);
           const size_t e0 = a.shard_start + (v << 3);
           if (kUseMc) {
             x[u][0] = multimem_ld_reduce_bf16x8(reinterpret_cast<const char*>(a.mc_in) + e0 * 2);
@@ -258,7 +278,7 @@ __global__ void __launch_bounds__(512) fed_aggregate_kernel(AggArgs a) {
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const size_t v = v0 + (size_t)u * stride;
-        if (v >= nvec_rounded) break;
+        if (v >= nvec_rounded) continue;  // (not `break`: keeps the unrolled arrays in registers)
         float acc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = 0.f;
@@ -291,24 +311,24 @@ __global__ void __launch_bounds__(512) fed_aggregate_kernel(AggArgs a) {
             }
           }
         }
-        finish_vector<kUseMc>(a, v, nvec, live[u], acc, lane);
+        finish_vector<kUseMc>(a, v, nvec, live[u], acc, lane, st[kState ? u : 0]);
       }
     }
   }
 
-  cta_party_barrier(a, a.epoch + 2);
+  cta_party_barrier(a, epoch + 2);
   if (a.epoch_dev && threadIdx.x == 0) {
     unsigned prev = atomicAdd(a.agg_done, 1u);
     if (prev == gridDim.x - 1) {  // every CTA has read the epoch and passed both barriers
       *a.agg_done = 0;
-      *a.epoch_dev = a.epoch + 2;
+      *a.epoch_dev = epoch + 2;
     }
   }
 }
 
 // K5: N-party device barrier (replaces the reference's ping loop,
 // fed/proxy/barriers.py:497-523, once the symmetric heap is up).
-__global__ void fed_barrier_kernel(AggArgs a) { cta_party_barrier(a, a.epoch + 1); }
+__global__ void fed_barrier_kernel(const __grid_constant__ AggArgs a) { cta_party_barrier(a, a.epoch + 1); }
 
 // Fused local optimizer step on flat buffers: SGD + momentum + weight decay,
 // optional gradient clear in the same pass (saves a memset of the grad bucket).
@@ -348,14 +368,25 @@ extern "C" {
 cudaError_t fedk_launch_aggregate(const AggArgs* a, int blocks, cudaStream_t stream) {
   const bool mc = a->mc_in != nullptr && a->mc_out != nullptr && !a->out_fp8;
   const int n = a->n_parties;
-  if (mc)
-    fed_aggregate_kernel<true, 1, 8><<<blocks, 512, 0, stream>>>(*a);
-  else if (n <= 2)
-    fed_aggregate_kernel<false, 2, 4><<<blocks, 512, 0, stream>>>(*a);
-  else if (n <= 4)
-    fed_aggregate_kernel<false, 4, 2><<<blocks, 512, 0, stream>>>(*a);
-  else
-    fed_aggregate_kernel<false, 8, 1><<<blocks, 512, 0, stream>>>(*a);
+  const bool state = a->kind != kAvg;
+  // <multicast, preloaded parties per vector, vectors per trip>: kNP*kU 16-byte
+  // requests (+ the optimizer state of kU vectors) are in flight per thread.
+  if (mc) {
+    if (state) fed_aggregate_kernel<true, 1, 2, true><<<blocks, 512, 0, stream>>>(*a);
+    else       fed_aggregate_kernel<true, 1, 8, false><<<blocks, 512, 0, stream>>>(*a);
+  } else if (n == 1) {
+    if (state) fed_aggregate_kernel<false, 1, 2, true><<<blocks, 512, 0, stream>>>(*a);
+    else       fed_aggregate_kernel<false, 1, 8, false><<<blocks, 512, 0, stream>>>(*a);
+  } else if (n <= 2) {
+    if (state) fed_aggregate_kernel<false, 2, 1, true><<<blocks, 512, 0, stream>>>(*a);
+    else       fed_aggregate_kernel<false, 2, 4, false><<<blocks, 512, 0, stream>>>(*a);
+  } else if (n <= 4) {
+    if (state) fed_aggregate_kernel<false, 4, 1, true><<<blocks, 512, 0, stream>>>(*a);
+    else       fed_aggregate_kernel<false, 4, 2, false><<<blocks, 512, 0, stream>>>(*a);
+  } else {
+    if (state) fed_aggregate_kernel<false, 8, 1, true><<<blocks, 512, 0, stream>>>(*a);
+    else       fed_aggregate_kernel<false, 8, 1, false><<<blocks, 512, 0, stream>>>(*a);
+  }
   return cudaGetLastError();
 }
 

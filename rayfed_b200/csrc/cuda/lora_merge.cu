@@ -75,35 +75,43 @@ __device__ __forceinline__ void lm_tmem_ld32(uint32_t taddr, uint32_t* v) {
 __device__ __forceinline__ void lm_gather_tile(unsigned char* smem, const PeerPtrs& src, int n_parties, int r,
                                                size_t row0, size_t rows_total, const float* party_w) {
   const int chunks_per_party = r >> 3;  // 16 B = 8 bf16
-  const int per_row = n_parties * chunks_per_party;
-  const int total = kLoraBM * per_row;
-  for (int idx = threadIdx.x; idx < total; idx += kLoraThreads) {
-    // consecutive threads -> consecutive 16 B chunks of one party's contiguous [128 x r] block
-    const int i = idx / (kLoraBM * chunks_per_party);
-    const int rem = idx - i * (kLoraBM * chunks_per_party);
-    const int row = rem / chunks_per_party;
-    const int c = rem - row * chunks_per_party;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row0 + row < rows_total) {
-      const char* p = reinterpret_cast<const char*>(src.p[i]) + ((row0 + row) * (size_t)r + (size_t)c * 8) * 2;
-      v = ld_v4(p);
-      if (party_w != nullptr && party_w[i] != 1.0f) {
-        const float w = party_w[i];
-        v.x = pack_bf16x2(bf16_lo(v.x) * w, bf16_hi(v.x) * w);
-        v.y = pack_bf16x2(bf16_lo(v.y) * w, bf16_hi(v.y) * w);
-        v.z = pack_bf16x2(bf16_lo(v.z) * w, bf16_hi(v.z) * w);
-        v.w = pack_bf16x2(bf16_lo(v.w) * w, bf16_hi(v.w) * w);
+  const int per_party = kLoraBM * chunks_per_party;
+  const int total = n_parties * per_party;
+  constexpr int kBatch = 8;  // 8 independent 16 B requests in flight per thread before the first smem store
+  for (int base = threadIdx.x; base < total; base += kLoraThreads * kBatch) {
+    uint4 v[kBatch];
+    int dst_off[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int idx = base + u * kLoraThreads;
+      v[u] = make_uint4(0, 0, 0, 0);
+      dst_off[u] = -1;
+      if (idx < total) {
+        // consecutive threads -> consecutive 16 B chunks of one party's contiguous [128 x r] block
+        const int i = idx / per_party;
+        const int rem = idx - i * per_party;
+        const int row = rem / chunks_per_party;
+        const int c = rem - row * chunks_per_party;
+        if (row0 + row < rows_total)
+          v[u] = ld_v4(reinterpret_cast<const char*>(src.p[i]) + ((row0 + row) * (size_t)r + (size_t)c * 8) * 2);
+        const int k0 = i * r + c * 8;
+        dst_off[u] = (k0 >> 6) * (kLoraBM * 128) + row * 128 + ((((k0 & 63) >> 3) ^ (row & 7)) << 4);
+        if (party_w != nullptr && party_w[i] != 1.0f) {
+          const float w = party_w[i];
+          v[u].x = pack_bf16x2(bf16_lo(v[u].x) * w, bf16_hi(v[u].x) * w);
+          v[u].y = pack_bf16x2(bf16_lo(v[u].y) * w, bf16_hi(v[u].y) * w);
+          v[u].z = pack_bf16x2(bf16_lo(v[u].z) * w, bf16_hi(v[u].z) * w);
+          v[u].w = pack_bf16x2(bf16_lo(v[u].w) * w, bf16_hi(v[u].w) * w);
+        }
       }
     }
-    const int k0 = i * r + c * 8;
-    const int atom = k0 >> 6;
-    const int chunk = (k0 & 63) >> 3;
-    unsigned char* dst = smem + (size_t)atom * (kLoraBM * 128) + row * 128 + ((chunk ^ (row & 7)) << 4);
-    *reinterpret_cast<uint4*>(dst) = v;
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+      if (dst_off[u] >= 0) *reinterpret_cast<uint4*>(smem + dst_off[u]) = v[u];
   }
 }
 
-__global__ void __launch_bounds__(kLoraThreads) fed_lora_merge_kernel(LoraMergeArgs a) {
+__global__ void __launch_bounds__(kLoraThreads) fed_lora_merge_kernel(const __grid_constant__ LoraMergeArgs a) {
   extern __shared__ unsigned char lm_smem[];
   __shared__ __align__(8) uint64_t mma_done;
   __shared__ uint32_t tmem_base_slot;
@@ -176,20 +184,27 @@ __global__ void __launch_bounds__(kLoraThreads) fed_lora_merge_kernel(LoraMergeA
   const float scale = a.scale;
 #pragma unroll 1
   for (int c = 0; c < kLoraBN / 32; ++c) {
+    const size_t col = n0 + (size_t)c * 32;
+    const bool in_range = row < a.m && col < a.n;
+    const size_t e = row * a.n + col;
+    uint4 wpre[4];
+    const bool bf16_base = in_range && a.w_base && !a.base_fp8;
+    if (bf16_base) {
+      const uint4* wb = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.w_base) + e);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) wpre[q] = ld_stream_v4(wb + q);
+    }
     uint32_t v[32];
     lm_tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-    const size_t col = n0 + (size_t)c * 32;
-    if (row < a.m && col < a.n) {
+    if (in_range) {
       float acc[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) acc[k] = __uint_as_float(v[k]) * scale;
-      const size_t e = row * a.n + col;
       if (a.w_base) {
         if (!a.base_fp8) {
-          const uint4* wb = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.w_base) + e);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint4 x = wb[q];
+            uint4 x = wpre[q];
             acc[q * 8 + 0] += bf16_lo(x.x); acc[q * 8 + 1] += bf16_hi(x.x);
             acc[q * 8 + 2] += bf16_lo(x.y); acc[q * 8 + 3] += bf16_hi(x.y);
             acc[q * 8 + 4] += bf16_lo(x.z); acc[q * 8 + 5] += bf16_hi(x.z);
