@@ -15,4 +15,5 @@ one party, averages and redistributes them through the gRPC proxy
   to one party, mean, broadcast) used as the measured baseline.
 """
 from .bucket import FlatBucket  # noqa: F401
+from .lora import FedLoRAAdam, FedLoRAExactMerge  # noqa: F401
 from .fedavg import FedAggregator, FedAvgWorker, LocalSGD, aggregate_reference, device_context  # noqa: F401

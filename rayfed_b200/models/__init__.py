@@ -5,5 +5,6 @@
   configs for tests) for federated LoRA fine-tuning.
 * :mod:`.mlp` — small MLP / split-learning halves for CPU tests.
 """
+from .llama import LlamaConfig, LlamaLoRA, LoRALinear, llama_lora  # noqa: F401
 from .mlp import MLP, SplitBottom, SplitTop  # noqa: F401
 from .resnet import resnet18, resnet50  # noqa: F401
