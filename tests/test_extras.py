@@ -1,0 +1,161 @@
+"""CPU tests for the pieces around the core: `import fed` shim, models, split
+learning over the fed API, tracing, checkpointing, CUDA extension build."""
+import json
+import os
+
+import pytest
+import torch
+
+from party_utils import comm_config, make_addresses, run_parties
+
+
+def test_import_fed_shim_exposes_reference_module_paths():
+    import fed
+    import fed.api
+    import fed.config
+    from fed._private.global_context import get_global_context  # noqa: F401
+    from fed.exceptions import FedRemoteError
+    from fed.fed_object import FedObject
+    from fed.proxy.barriers import recv, send  # noqa: F401
+    from fed.proxy.base_proxy import ReceiverProxy, SenderProxy, SenderReceiverProxy  # noqa: F401
+    from fed.proxy.grpc.grpc_proxy import GrpcReceiverProxy, GrpcSenderProxy  # noqa: F401
+
+    import rayfed_b200
+
+    assert fed.init is rayfed_b200.init and fed.FedObject is FedObject
+    assert fed.FedRemoteError is FedRemoteError
+    fed.utils.validate_address("127.0.0.1:1")
+
+
+def test_cuda_extension_builds_and_imports_without_gpu():
+    from rayfed_b200 import _build
+
+    so = _build.ensure_cuda()
+    assert os.path.exists(so)
+    import rayfed_b200._fedcuda as ext
+
+    for name in ("push", "unpack", "aggregate", "AggPlan", "barrier", "local_sgd", "lora_merge", "ipc_alloc",
+                 "vmm_alloc", "mc_create"):
+        assert hasattr(ext, name), name
+
+
+def test_resnet50_shape_and_param_count():
+    from rayfed_b200.models import resnet18, resnet50
+
+    m = resnet50()
+    assert sum(p.numel() for p in m.parameters()) == 25_557_032
+    y = resnet18(10, width=8)(torch.randn(2, 3, 32, 32))
+    assert y.shape == (2, 10)
+
+
+def test_llama_lora_only_adapters_train_and_fp8_base_roundtrip():
+    from rayfed_b200.models import LlamaConfig, llama_lora
+    from rayfed_b200.models.llama import dequantize_block_fp8, quantize_block_fp8
+
+    cfg8 = LlamaConfig.llama3_8b()
+    assert (cfg8.hidden_size, cfg8.num_layers, cfg8.num_kv_heads, cfg8.intermediate_size) == (4096, 32, 8, 14336)
+    m = llama_lora()
+    trainable = [n for n, p in m.named_parameters() if p.requires_grad]
+    assert trainable and all("lora_" in n for n in trainable)
+    tok = torch.randint(0, 512, (2, 8))
+    out = m(tok)
+    assert out.shape == (2, 8, 512)
+    torch.nn.functional.cross_entropy(out.float().view(-1, 512), tok.view(-1)).backward()
+    assert all(p.grad is not None for p in m.parameters() if p.requires_grad)
+    mod = m.lora_modules()[0][1]
+    assert mod.lora_B.shape == (mod.d_out, mod.r) and mod.lora_At.shape == (mod.d_in, mod.r)
+    w = torch.randn(64, 128)
+    q, s = quantize_block_fp8(w)
+    rel = ((dequantize_block_fp8(q, s).float() - w).abs().mean() / w.abs().mean()).item()
+    assert rel < 0.04
+    assert llama_lora(base_dtype="fp8")(tok).shape == (2, 8, 512)
+
+
+def _split_learning(party, addresses):
+    import rayfed_b200 as fed
+    from rayfed_b200.models import SplitBottom, SplitTop
+    from rayfed_b200.parallel.split import SplitBottomWorker, SplitTopWorker
+
+    fed.init(addresses=addresses, party=party, logging_level="warning",
+             config={"cross_silo_comm": comm_config()})
+
+    @fed.remote
+    def feats(step):
+        return torch.randn(64, 32, generator=torch.Generator().manual_seed(step))
+
+    @fed.remote
+    def labels(step):
+        x = torch.randn(64, 32, generator=torch.Generator().manual_seed(step))
+        return x[:, :10].argmax(1)
+
+    bottom = fed.remote(SplitBottomWorker).party("alice").remote(lambda: SplitBottom(32, 16), lr=0.3)
+    top = fed.remote(SplitTopWorker).party("bob").remote(lambda: SplitTop(16, 10), lr=0.3)
+    losses = []
+    for step in range(80):
+        h = bottom.forward.remote(feats.party("alice").remote(step % 4))
+        loss, grad_h = top.step.options(num_returns=2).remote(h, labels.party("bob").remote(step % 4))
+        bottom.backward.remote(grad_h)
+        losses.append(loss)
+    vals = fed.get(losses)
+    assert vals[-1] < vals[0] * 0.9, (vals[0], vals[-1])  # the two halves learn jointly
+    fed.shutdown()
+
+
+def test_split_learning_across_two_parties():
+    run_parties(_split_learning, ["alice", "bob"], args=(make_addresses(["alice", "bob"]),), timeout=120)
+
+
+def test_timeline_dumps_chrome_trace(tmp_path):
+    from rayfed_b200.utils.tracing import Timeline
+
+    tl = Timeline("alice")
+    with tl.span("send", seq_id=3, dest="bob"):
+        pass
+    path = tmp_path / "trace.json"
+    tl.dump(str(path))
+    ev = json.load(open(path))["traceEvents"]
+    assert ev[0]["name"] == "send" and ev[0]["args"]["seq_id"] == 3 and ev[0]["pid"] == "alice"
+
+
+def test_checkpoint_roundtrip_cpu(tmp_path):
+    from rayfed_b200.fl.bucket import FlatBucket
+    from rayfed_b200.models import MLP
+    from rayfed_b200.utils import checkpoint
+
+    torch.manual_seed(0)
+    model = MLP(8, 16, 4)
+    bucket = FlatBucket(model, None, dtype=torch.float32, n_parties=2)
+    w0 = bucket.flat_w.clone()
+    path = checkpoint.save_round_state(str(tmp_path), "alice", 7, bucket=bucket, extra={"lr": 0.1})
+    bucket.flat_w.zero_()
+    assert model(torch.ones(1, 8)).abs().sum() == 0  # params are views of the bucket
+    state = checkpoint.load_round_state(checkpoint.latest(str(tmp_path), "alice"), bucket=bucket)
+    assert state["round"] == 7 and state["extra"]["lr"] == 0.1 and path.endswith("round00000007.pt")
+    assert torch.equal(bucket.flat_w, w0)
+    assert bucket.numel % 64 == 0 and bucket.shard_len * 2 == bucket.numel
+
+
+def test_flat_bucket_grads_accumulate_in_place_cpu():
+    from rayfed_b200.fl.bucket import FlatBucket
+    from rayfed_b200.models import MLP
+
+    model = MLP(8, 16, 4)
+    bucket = FlatBucket(model, None, dtype=torch.float32)
+    model(torch.randn(3, 8)).sum().backward()
+    assert bucket.flat_g.abs().sum() > 0
+    for p in model.parameters():
+        assert p.grad.data_ptr() >= bucket.flat_g.data_ptr()
+    bucket.zero_grad()
+    assert all(p.grad.abs().sum() == 0 for p in model.parameters())
+
+
+def test_reference_arm_reports_unavailable_without_ray():
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and ("unavailable" in line or "value" in line)
