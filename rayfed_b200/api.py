@@ -455,6 +455,7 @@ def get(fed_objects: Union[FedObject, List[FedObject], Any]) -> Any:
 
     try:
         values = _local_get(refs)
+        _raise_on_device_failure()
         return values[0] if is_individual_id else values
     except FedTaskError as e:
         if isinstance(e.cause, FedRemoteError):
@@ -462,6 +463,16 @@ def get(fed_objects: Union[FedObject, List[FedObject], Any]) -> Any:
             if get_global_context() is not None:
                 get_global_context().set_last_recevied_error(e.cause)
         raise
+
+
+def _raise_on_device_failure():
+    """A device-side wait that timed out leaves its destination untouched and sets a
+    status word; surface that as an error instead of handing out garbage."""
+    mod = sys.modules.get("rayfed_b200.proxy.nvlink.nvlink_proxy")
+    if mod is not None:
+        ch = mod.current_channel()
+        if ch is not None:
+            ch.raise_if_failed()
 
 
 def kill(actor: FedActorHandle, *, no_restart=True):

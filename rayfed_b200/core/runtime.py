@@ -88,11 +88,12 @@ def is_refs(objs) -> bool:
 class _Produced:
     """A value plus the CUDA event that orders it after its producer stream."""
 
-    __slots__ = ("value", "event")
+    __slots__ = ("value", "event", "stream")
 
-    def __init__(self, value, event):
+    def __init__(self, value, event, stream=None):
         self.value = value
         self.event = event
+        self.stream = stream  # the stream the producer ran on
 
 
 def _wrap_task_error(exc: BaseException):
@@ -284,7 +285,7 @@ def _device_trampoline(fn, stream_ctx: _StreamContext, pool_tls):
             out = fn(*args, **kwargs)
             ev = torch.cuda.Event()
             ev.record(stream)
-        return _Produced(out, ev)
+        return _Produced(out, ev, stream)
 
     run.__name__ = getattr(fn, "__name__", "task")
     return run

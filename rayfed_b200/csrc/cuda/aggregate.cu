@@ -33,7 +33,8 @@ __device__ __forceinline__ void cta_party_barrier(const AggArgs& a, uint32_t val
     uint32_t* remote = reinterpret_cast<uint32_t*>(a.sig_peers.p[t]) + (size_t)blockIdx.x * kMaxParties + a.my_rank;
     st_release_sys_u32(remote, value);
     const uint32_t* mine = a.sig + (size_t)blockIdx.x * kMaxParties + t;
-    if (!spin_wait_ge(mine, value, a.timeout_cycles) && a.status) atomicExch(a.status, 2u);
+    if (!spin_wait_ge(mine, value, a.timeout_ns) && a.status)
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.status), "r"(2u) : "memory");
   }
   __syncthreads();
 }

@@ -294,7 +294,7 @@ PYBIND11_MODULE(_fedcuda, m) {
   m.def(
       "unpack",
       [](uint64_t src, uint64_t dst, uint64_t scales, uint64_t n, float scale, uint64_t flag, uint32_t flag_value,
-         uint64_t done_counter, uint64_t credit, uint64_t credit_value, uint64_t status, long long timeout_cycles,
+         uint64_t done_counter, uint64_t credit, uint64_t credit_value, uint64_t status, long long timeout_ns,
          int mode, int blocks, uint64_t stream) {
         PushArgs a{};
         a.src = P<const void>(src);
@@ -308,12 +308,12 @@ PYBIND11_MODULE(_fedcuda, m) {
         a.credit = P<unsigned long long>(credit);
         a.credit_value = credit_value;
         a.status = P<uint32_t>(status);
-        a.timeout_cycles = timeout_cycles;
+        a.timeout_ns = timeout_ns;
         check(fedk_launch_unpack(&a, mode, blocks, (cudaStream_t)(uintptr_t)stream), "fed_unpack launch");
       },
       py::arg("src"), py::arg("dst"), py::arg("scales"), py::arg("n"), py::arg("scale"), py::arg("flag"),
       py::arg("flag_value"), py::arg("done_counter"), py::arg("credit"), py::arg("credit_value"), py::arg("status"),
-      py::arg("timeout_cycles"), py::arg("mode"), py::arg("blocks"), py::arg("stream"));
+      py::arg("timeout_ns"), py::arg("mode"), py::arg("blocks"), py::arg("stream"));
 
   m.def(
       "aggregate",
@@ -322,7 +322,7 @@ PYBIND11_MODULE(_fedcuda, m) {
          uint64_t shard_len, int my_rank, int kind, bool in_fp32, bool out_fp8, const std::vector<float>& weights,
          float lr, float momentum, float weight_decay, float beta1, float beta2, float eps, float bias_c1,
          float bias_c2, uint64_t sig, const std::vector<uint64_t>& sig_peers, uint32_t epoch, uint64_t status,
-         long long timeout_cycles, int blocks, uint64_t stream) {
+         long long timeout_ns, int blocks, uint64_t stream) {
         AggArgs a{};
         fill_peers(a.in, in);
         fill_peers(a.out, out);
@@ -352,7 +352,7 @@ PYBIND11_MODULE(_fedcuda, m) {
         fill_peers(a.sig_peers, sig_peers);
         a.epoch = epoch;
         a.status = P<uint32_t>(status);
-        a.timeout_cycles = timeout_cycles;
+        a.timeout_ns = timeout_ns;
         check(fedk_launch_aggregate(&a, blocks, (cudaStream_t)(uintptr_t)stream), "fed_aggregate launch");
       },
       py::arg("inputs"), py::arg("outputs"), py::arg("out_scales"), py::arg("mc_in"), py::arg("mc_out"),
@@ -360,7 +360,7 @@ PYBIND11_MODULE(_fedcuda, m) {
       py::arg("my_rank"), py::arg("kind"), py::arg("in_fp32"), py::arg("out_fp8"), py::arg("weights"), py::arg("lr"),
       py::arg("momentum"), py::arg("weight_decay"), py::arg("beta1"), py::arg("beta2"), py::arg("eps"),
       py::arg("bias_c1"), py::arg("bias_c2"), py::arg("sig"), py::arg("sig_peers"), py::arg("epoch"),
-      py::arg("status"), py::arg("timeout_cycles"), py::arg("blocks"), py::arg("stream"));
+      py::arg("status"), py::arg("timeout_ns"), py::arg("blocks"), py::arg("stream"));
 
   // Pre-baked argument block: per-round launches only patch the scalars that change.
   struct AggPlan {
@@ -374,7 +374,7 @@ PYBIND11_MODULE(_fedcuda, m) {
                        bool in_fp32, bool out_fp8, const std::vector<float>& weights, float lr, float momentum,
                        float weight_decay, float beta1, float beta2, float eps, uint64_t sig,
                        const std::vector<uint64_t>& sig_peers, uint64_t epoch_dev, uint64_t agg_done,
-                       uint64_t status, long long timeout_cycles, int blocks) {
+                       uint64_t status, long long timeout_ns, int blocks) {
              AggPlan p{};
              AggArgs& a = p.a;
              fill_peers(a.in, in);
@@ -406,7 +406,7 @@ PYBIND11_MODULE(_fedcuda, m) {
              a.epoch_dev = P<uint32_t>(epoch_dev);
              a.agg_done = P<uint32_t>(agg_done);
              a.status = P<uint32_t>(status);
-             a.timeout_cycles = timeout_cycles;
+             a.timeout_ns = timeout_ns;
              p.blocks = blocks;
              return p;
            }),
@@ -415,7 +415,7 @@ PYBIND11_MODULE(_fedcuda, m) {
            py::arg("my_rank"), py::arg("kind"), py::arg("in_fp32"), py::arg("out_fp8"), py::arg("weights"),
            py::arg("lr"), py::arg("momentum"), py::arg("weight_decay"), py::arg("beta1"), py::arg("beta2"),
            py::arg("eps"), py::arg("sig"), py::arg("sig_peers"), py::arg("epoch_dev"), py::arg("agg_done"),
-           py::arg("status"), py::arg("timeout_cycles"), py::arg("blocks"))
+           py::arg("status"), py::arg("timeout_ns"), py::arg("blocks"))
       .def("launch",
            [](AggPlan& p, uint32_t epoch, float lr, float bias_c1, float bias_c2, uint64_t stream) {
              p.a.epoch = epoch;
@@ -429,7 +429,7 @@ PYBIND11_MODULE(_fedcuda, m) {
   m.def(
       "barrier",
       [](int n_parties, int my_rank, uint64_t sig, const std::vector<uint64_t>& sig_peers, uint32_t epoch,
-         uint64_t status, long long timeout_cycles, uint64_t stream) {
+         uint64_t status, long long timeout_ns, uint64_t stream) {
         AggArgs a{};
         a.n_parties = n_parties;
         a.my_rank = my_rank;
@@ -437,11 +437,11 @@ PYBIND11_MODULE(_fedcuda, m) {
         fill_peers(a.sig_peers, sig_peers);
         a.epoch = epoch;
         a.status = P<uint32_t>(status);
-        a.timeout_cycles = timeout_cycles;
+        a.timeout_ns = timeout_ns;
         check(fedk_launch_barrier(&a, (cudaStream_t)(uintptr_t)stream), "fed_barrier launch");
       },
       py::arg("n_parties"), py::arg("my_rank"), py::arg("sig"), py::arg("sig_peers"), py::arg("epoch"),
-      py::arg("status"), py::arg("timeout_cycles"), py::arg("stream"));
+      py::arg("status"), py::arg("timeout_ns"), py::arg("stream"));
 
   m.def(
       "lora_merge",

@@ -78,15 +78,30 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
+// Nanosecond wall clock shared by every SM.  (clock64() is a *per-SM* cycle counter:
+// a long-parked CTA that is context-switched and resumed elsewhere sees it jump by
+// an arbitrary amount, which fired spurious timeouts on B200 — measured, see
+// profiles/README.md "device-side wait".)
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // Spin until *flag >= target (wrap-safe signed compare). One thread per CTA
-// should call this, then __syncthreads(). Returns false on timeout.
-__device__ __forceinline__ bool spin_wait_ge(const uint32_t* flag, uint32_t target, long long timeout_cycles) {
-  long long t0 = clock64();
+// should call this, then __syncthreads(). `timeout_ns` <= 0 waits for ever.
+// Returns false on timeout.
+__device__ __forceinline__ bool spin_wait_ge(const uint32_t* flag, uint32_t target, long long timeout_ns) {
+  if ((int32_t)(ld_acquire_sys_u32(flag) - target) >= 0) return true;
+  const unsigned long long t0 = global_ns();
   uint32_t ns = 20;
   while ((int32_t)(ld_acquire_sys_u32(flag) - target) < 0) {
     __nanosleep(ns);
-    if (ns < 256) ns <<= 1;
-    if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) return false;
+    if (ns < 512) ns <<= 1;
+    if (timeout_ns > 0 && (long long)(global_ns() - t0) > timeout_ns) {
+      // one last look: the flag may have landed while we were asleep
+      return (int32_t)(ld_acquire_sys_u32(flag) - target) >= 0;
+    }
   }
   return true;
 }

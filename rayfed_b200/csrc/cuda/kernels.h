@@ -25,7 +25,7 @@ struct PushArgs {
   unsigned long long* credit;  // unpack: producer's credit word in peer memory (may be null)
   unsigned long long credit_value;
   uint32_t* status;         // local error word (timeout)
-  long long timeout_cycles;
+  long long timeout_ns;
 };
 
 enum AggKind : int {
@@ -61,7 +61,7 @@ struct AggArgs {
                            // last CTA, so an identical launch can be replayed from a CUDA graph
   uint32_t* agg_done;      // device counter for "last CTA" detection (zero between launches)
   uint32_t* status;
-  long long timeout_cycles;
+  long long timeout_ns;
 };
 
 struct LocalSgdArgs {

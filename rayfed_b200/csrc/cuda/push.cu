@@ -70,10 +70,16 @@ __global__ void __launch_bounds__(512) fed_push_kernel(PushArgs a, int mode) {
     // K4: device-side receive barrier. Only one lane polls; the CTA parks on bar.sync.
     __shared__ int ok;
     if (threadIdx.x == 0) {
-      ok = spin_wait_ge(a.flag, a.flag_value, a.timeout_cycles) ? 1 : 0;
-      if (!ok && a.status) atomicExch(a.status, 1u);
+      ok = spin_wait_ge(a.flag, a.flag_value, a.timeout_ns) ? 1 : 0;
+      // status may live in pinned host memory (the host polls it without a CUDA call)
+      if (!ok && a.status) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.status), "r"(1u) : "memory");
     }
     __syncthreads();
+    if (!ok) {
+      // the payload never arrived: leave the destination untouched, still return credit
+      publish_when_grid_done(a, true);
+      return;
+    }
   }
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;

@@ -95,11 +95,12 @@ class FedAggregator:
             if self.kind in (K.AGG_ADAM, K.AGG_FEDADAM):
                 self.var = torch.zeros_like(self.master)
         self.out_fp8 = out_fp8
-        self._timeout_cycles = int(timeout_s * 1.9e9)
+        self._timeout_ns = int(timeout_s * 1e9)  # device waits use %globaltimer (ns)
         # A private signal pad per aggregator (symmetric when there are peers) and a
         # device-resident epoch: the launch is identical every round => graph-replayable.
         heap = heap or (channel.heap if channel is not None else None)
-        self._ctl = torch.zeros(64, dtype=torch.int32, device=self.dev)  # [0]=epoch [1]=done [2]=status
+        self._ctl = torch.zeros(64, dtype=torch.int32, device=self.dev)  # [0]=epoch [1]=done
+        self._status_host = torch.zeros(16, dtype=torch.int32).pin_memory()  # written by the kernel on timeout
         if n > 1:
             assert heap is not None, "multi-party aggregation needs the symmetric heap"
             self._pad = heap.alloc(f"aggpad/{bucket.name}/{kind}", 64 * 1024)
@@ -142,8 +143,8 @@ class FedAggregator:
             mom_ptr=self.mom.data_ptr() if self.mom is not None else 0,
             var_ptr=self.var.data_ptr() if self.var is not None else 0,
             lr=lr, momentum=momentum, weight_decay=weight_decay, beta1=betas[0], beta2=betas[1], eps=eps,
-            sig_ptr=sig_ptr, sig_peers=sig_peers, epoch_dev_ptr=base, agg_done_ptr=base + 4, status_ptr=base + 8,
-            timeout_cycles=self._timeout_cycles, device_index=self.dev.index or 0,
+            sig_ptr=sig_ptr, sig_peers=sig_peers, epoch_dev_ptr=base, agg_done_ptr=base + 4, status_ptr=self._status_host.data_ptr(),
+            timeout_ns=self._timeout_ns, device_index=self.dev.index or 0,
         )
 
     def aggregate(self, stream=None, lr: Optional[float] = None):
@@ -153,7 +154,7 @@ class FedAggregator:
 
     def status(self) -> int:
         """0 = healthy; 2 = an in-kernel party barrier timed out."""
-        return int(self._ctl[2].item())
+        return int(self._status_host[0])
 
     @property
     def uses_multicast(self) -> bool:

@@ -38,7 +38,7 @@ def run(device: str = "cuda:0"):
            done_counter_ptr=ctrl.data_ptr() + 8, device_index=dev.index or 0)
     dst = torch.empty_like(src)
     K.unpack(buf.local_ptr, dst.data_ptr(), src.numel() * 4, flag_ptr=ctrl.data_ptr(), flag_value=1,
-             done_counter_ptr=ctrl.data_ptr() + 12, status_ptr=ctrl.data_ptr() + 16, timeout_cycles=int(5e9),
+             done_counter_ptr=ctrl.data_ptr() + 12, status_ptr=ctrl.data_ptr() + 16, timeout_ns=int(5e9),
              device_index=dev.index or 0)
     torch.cuda.synchronize()
     assert torch.equal(src, dst), "push/unpack loopback mismatch"

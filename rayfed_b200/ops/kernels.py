@@ -110,14 +110,14 @@ def _bulk_default() -> bool:
 
 def unpack(src_ptr: int, dst_ptr: int, n: int, *, mode: int = MODE_COPY, scale: float = 1.0, scales_ptr: int = 0,
            flag_ptr: int, flag_value: int, done_counter_ptr: int, credit_ptr: int = 0, credit_value: int = 0,
-           status_ptr: int = 0, timeout_cycles: int = 0, stream=None, device_index: int = 0,
+           status_ptr: int = 0, timeout_ns: int = 0, stream=None, device_index: int = 0,
            blocks: Optional[int] = None) -> None:
     """K4 + unpack: wait for the flag on the device, undo the wire format, return credit."""
     nbytes = n if mode == MODE_COPY else n * 2
     if blocks is None:
         blocks = _blocks_for(nbytes, device_index)
     cuda_ext().unpack(src_ptr, dst_ptr, scales_ptr, n, float(scale), flag_ptr, flag_value, done_counter_ptr,
-                      credit_ptr, credit_value, status_ptr, timeout_cycles, mode, blocks, _stream_handle(stream))
+                      credit_ptr, credit_value, status_ptr, timeout_ns, mode, blocks, _stream_handle(stream))
     launch_counter.add("fed_unpack")
 
 
@@ -126,7 +126,7 @@ def aggregate(*, inputs: Sequence[int], outputs: Sequence[int], my_rank: int, sh
               out_fp8: bool = False, out_scales: Sequence[int] = (), mc_in: int = 0, mc_out: int = 0,
               master_ptr: int = 0, mom_ptr: int = 0, var_ptr: int = 0, lr: float = 1.0, momentum: float = 0.0,
               weight_decay: float = 0.0, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, step: int = 1,
-              sig_ptr: int, sig_peers: Sequence[int], epoch: int, status_ptr: int = 0, timeout_cycles: int = 0,
+              sig_ptr: int, sig_peers: Sequence[int], epoch: int, status_ptr: int = 0, timeout_ns: int = 0,
               stream=None, device_index: int = 0, blocks: Optional[int] = None) -> None:
     """K2/K3. Every party launches this with the same arguments (SPMD)."""
     n = len(inputs)
@@ -139,7 +139,7 @@ def aggregate(*, inputs: Sequence[int], outputs: Sequence[int], my_rank: int, sh
     cuda_ext().aggregate(list(inputs), list(outputs), list(out_scales), mc_in, mc_out, master_ptr, mom_ptr, var_ptr,
                          shard_start, shard_len, my_rank, kind, in_fp32, out_fp8, [float(w) for w in weights],
                          float(lr), float(momentum), float(weight_decay), float(beta1), float(beta2), float(eps),
-                         float(bias_c1), float(bias_c2), sig_ptr, list(sig_peers), epoch, status_ptr, timeout_cycles,
+                         float(bias_c1), float(bias_c2), sig_ptr, list(sig_peers), epoch, status_ptr, timeout_ns,
                          blocks, _stream_handle(stream))
     launch_counter.add("fed_aggregate")
 
@@ -152,7 +152,7 @@ class AggregatePlan:
     def __init__(self, *, inputs, outputs, my_rank, shard_start, shard_len, kind=AGG_AVG, weights=None,
                  in_fp32=False, out_fp8=False, out_scales=(), mc_in=0, mc_out=0, master_ptr=0, mom_ptr=0, var_ptr=0,
                  lr=1.0, momentum=0.0, weight_decay=0.0, beta1=0.9, beta2=0.999, eps=1e-8, sig_ptr, sig_peers,
-                 epoch_dev_ptr=0, agg_done_ptr=0, status_ptr=0, timeout_cycles=0, device_index=0, blocks=None):
+                 epoch_dev_ptr=0, agg_done_ptr=0, status_ptr=0, timeout_ns=0, device_index=0, blocks=None):
         n = len(inputs)
         if weights is None:
             weights = [1.0 / n] * n
@@ -163,7 +163,7 @@ class AggregatePlan:
                                         mom_ptr, var_ptr, shard_start, shard_len, my_rank, kind, bool(in_fp32),
                                         bool(out_fp8), [float(w) for w in weights], float(lr), float(momentum),
                                         float(weight_decay), float(beta1), float(beta2), float(eps), sig_ptr,
-                                        list(sig_peers), epoch_dev_ptr, agg_done_ptr, status_ptr, timeout_cycles,
+                                        list(sig_peers), epoch_dev_ptr, agg_done_ptr, status_ptr, timeout_ns,
                                         blocks)
 
     def launch(self, epoch: int = 0, step: int = 1, lr: Optional[float] = None, stream=None):
@@ -175,9 +175,9 @@ class AggregatePlan:
 
 
 def barrier(*, n_parties: int, my_rank: int, sig_ptr: int, sig_peers: Sequence[int], epoch: int, status_ptr: int = 0,
-            timeout_cycles: int = 0, stream=None) -> None:
+            timeout_ns: int = 0, stream=None) -> None:
     """K5."""
-    cuda_ext().barrier(n_parties, my_rank, sig_ptr, list(sig_peers), epoch, status_ptr, timeout_cycles,
+    cuda_ext().barrier(n_parties, my_rank, sig_ptr, list(sig_peers), epoch, status_ptr, timeout_ns,
                        _stream_handle(stream))
     launch_counter.add("fed_barrier")
 

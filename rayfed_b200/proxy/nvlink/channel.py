@@ -40,6 +40,12 @@ OFF_ARENA = 128 * 1024
 SIGNAL_BYTES = 64 * 1024
 ALIGN = 256
 
+import os as _os
+
+_DEBUG_SYNC_SEND = _os.environ.get("RAYFED_DEBUG_SYNC_SEND") == "1"
+_DEBUG_MODE = _os.environ.get("RAYFED_DEBUG_PUSH_MODE", "")
+_DEBUG_SYNC_RECV = _os.environ.get("RAYFED_DEBUG_SYNC_RECV") == "1"
+
 _WIRE = {None: None, "none": None, "bf16": "bf16", "fp8_e4m3": "fp8_e4m3", "fp8": "fp8_e4m3"}
 
 
@@ -65,8 +71,11 @@ class DeviceChannel:
         self._push_stream = torch.cuda.Stream(device=self._dev)
         self._recv_stream = torch.cuda.Stream(device=self._dev)
         self._epoch = 0
+        # error word in pinned host memory (UVA: same pointer on the device): kernels
+        # store to it on a wait timeout, the host reads it with a plain load
+        self._status_host = torch.zeros(16, dtype=torch.int32).pin_memory()
         # ~1.9 GHz SM clock: cycles until a device-side wait declares a timeout
-        self._timeout_cycles = int(timeout_s * 1.9e9)
+        self._timeout_ns = int(timeout_s * 1e9)  # device waits use %globaltimer (ns)
         self.stats = {"tensors_sent": 0, "bytes_sent": 0, "tensors_received": 0, "bytes_received": 0,
                       "credit_stalls": 0}
 
@@ -118,14 +127,16 @@ class DeviceChannel:
         self._head[dest] = end
         return off, end
 
-    def push_tensor(self, dest_rank: int, tensor, ready_event=None, scale: float = 1.0) -> dict:
+    def push_tensor(self, dest_rank: int, tensor, ready_event=None, scale: float = 1.0,
+                    producer_stream=None) -> dict:
         """Launch K1 for one CUDA tensor; returns the descriptor the host frame carries."""
         import torch
 
         with torch.cuda.device(self.device_index):  # callers are arbitrary runtime threads
-            return self._push_tensor(dest_rank, tensor, ready_event, scale)
+            return self._push_tensor(dest_rank, tensor, ready_event, scale, producer_stream)
 
-    def _push_tensor(self, dest_rank: int, tensor, ready_event=None, scale: float = 1.0) -> dict:
+    def _push_tensor(self, dest_rank: int, tensor, ready_event=None, scale: float = 1.0,
+                     producer_stream=None) -> dict:
         import torch
 
         t = tensor if tensor.is_contiguous() else tensor.contiguous()
@@ -153,7 +164,13 @@ class DeviceChannel:
             dst = self._peer(dest_rank, region + off)
             dst_scales = dst + pay_pad if scales_bytes else 0
             stream = self._push_stream
-            if ready_event is not None:
+            if _DEBUG_MODE == "same_stream" and producer_stream is not None:
+                stream = producer_stream
+            elif _DEBUG_MODE == "wait_stream" and producer_stream is not None:
+                stream.wait_stream(producer_stream)
+            elif ready_event is not None:
+                if _DEBUG_SYNC_SEND:
+                    ready_event.synchronize()
                 stream.wait_event(ready_event)
             else:
                 stream.wait_stream(torch.cuda.current_stream(self._dev))
@@ -198,11 +215,13 @@ class DeviceChannel:
                      flag_ptr=self._local(OFF_FLAGS + 4 * src_rank), flag_value=desc["seq"],
                      done_counter_ptr=self._local(OFF_UNPACK_DONE),
                      credit_ptr=self._peer(src_rank, OFF_CREDITS + 8 * self.group.rank), credit_value=desc["end"],
-                     status_ptr=self._local(OFF_STATUS), timeout_cycles=self._timeout_cycles, stream=stream,
+                     status_ptr=self._status_host.data_ptr(), timeout_ns=self._timeout_ns, stream=stream,
                      device_index=self.device_index)
             ev = torch.cuda.Event()
             ev.record(stream)
             out.record_stream(stream)
+            if _DEBUG_SYNC_RECV:
+                ev.synchronize()
         self.stats["tensors_received"] += 1
         self.stats["bytes_received"] += desc["pay"] + desc["scales"]
         return out, ev
@@ -212,11 +231,22 @@ class DeviceChannel:
         """K5 on the given (default: current) stream."""
         K.cuda_ext().set_device(self.device_index)
         K.barrier(n_parties=self.group.size, my_rank=self.group.rank, sig_ptr=self.signal_ptr,
-                  sig_peers=self.signal_peers, epoch=self.next_epoch(1), status_ptr=self._local(OFF_STATUS),
-                  timeout_cycles=self._timeout_cycles, stream=stream)
+                  sig_peers=self.signal_peers, epoch=self.next_epoch(1), status_ptr=self._status_host.data_ptr(),
+                  timeout_ns=self._timeout_ns, stream=stream)
 
     def check_status(self) -> int:
-        return K.cuda_ext().read_u32(self._local(OFF_STATUS))
+        """0 = healthy; 1 = a device-side receive wait timed out; 2 = a party barrier did."""
+        return int(self._status_host[0])
+
+    def raise_if_failed(self):
+        st = self.check_status()
+        if st:
+            from ...exceptions import FedError
+
+            raise FedError(
+                f"NVLink device channel failure (status {st}): a device-side wait for a peer timed out after "
+                f"{self._timeout_ns / 1e9:.0f}s — the peer party is gone or its producer never launched."
+            )
 
     def synchronize(self):
         self._push_stream.synchronize()

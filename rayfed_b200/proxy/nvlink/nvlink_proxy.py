@@ -32,6 +32,9 @@ from ..native.socket_proxy import NativeReceiverProxy, NativeSenderProxy, _ack_d
 
 logger = logging.getLogger(__name__)
 
+import os as _os
+
+_DEBUG_CONSUMER_SYNC = _os.environ.get("RAYFED_DEBUG_CONSUMER_SYNC") == "1"
 _DEVQ = "__devq__"
 _TAG = "fedcuda"
 _DEFAULT_MIN_BYTES = 4096
@@ -96,8 +99,9 @@ class NvlinkSenderProxy(NativeSenderProxy):
 
     def send(self, dest_party, data, upstream_seq_id, downstream_seq_id):
         ready_event = None
+        producer_stream = None
         if type(data) is _Produced:
-            ready_event, data = data.event, data.value
+            ready_event, producer_stream, data = data.event, data.stream, data.value
         channel = current_channel()
         if channel is None or isinstance(data, FedRemoteError):
             if ready_event is not None:
@@ -121,7 +125,7 @@ class NvlinkSenderProxy(NativeSenderProxy):
         with self._order_lock:
             k = self._k.get(dest_party, 0) + 1
             self._k[dest_party] = k
-            descs = [channel.push_tensor(dest_rank, t, ready_event) for t in tensors]
+            descs = [channel.push_tensor(dest_rank, t, ready_event, producer_stream=producer_stream) for t in tensors]
             self._transport.send(dest_party, f"{_DEVQ}/{self._party}", str(k), pickle.dumps(descs), False,
                                  _ack_decoder)
         frame = pickle.dumps((_TAG, k, buf.getvalue()), protocol=5)
@@ -196,6 +200,10 @@ class NvlinkReceiverProxy(NativeReceiverProxy):
                 _, k, skeleton = obj
                 parts = self._take(src_party, k)
                 value = _DeviceUnpickler(io.BytesIO(skeleton), lambda idx: parts[idx][0]).load()
+                if _DEBUG_CONSUMER_SYNC:
+                    import torch
+
+                    torch.cuda.synchronize()
                 # the receive stream is in-order: the last unpack's event covers them all
                 return _Produced(value, parts[-1][1])
             if isinstance(obj, FedRemoteError):

@@ -86,16 +86,22 @@ def _fedavg(party, addresses, kind):
         g = torch.Generator().manual_seed(100 * _rank + 10 * r + i)
         return torch.randn(8, 3, 32, 32, generator=g), torch.randint(0, 10, (8,), generator=g)
 
-    Worker = fed.remote(FedAvgWorker)
+    class DiagWorker(FedAvgWorker):
+        def snap(self):
+            c = self.bucket.flat_w.clone()
+            return c, float(c.float().sum())
+
+    Worker = fed.remote(DiagWorker)
     workers = {p: Worker.party(p).remote(lambda: resnet18(10, width=16), parties=parties, party=p,
                                          batch_fn=batch_fn, lr=0.05, kind=kind, server_lr=1.0,
                                          server_momentum=0.0)
                for p in parties}
     losses = [workers[p].local_round.remote(2) for p in parties]
-    before = fed.get([workers[p].get_flat_weights.remote() for p in parties])
+    before_s = fed.get([workers[p].snap.remote() for p in parties])
     for p in parties:
         workers[p].aggregate.remote()
-    after = fed.get([workers[p].get_flat_weights.remote() for p in parties])
+    after_s = fed.get([workers[p].snap.remote() for p in parties])
+    before, after = [x[0] for x in before_s], [x[0] for x in after_s]
     ls = fed.get(losses)
     assert all(torch.isfinite(torch.as_tensor(float(x))) for x in ls)
     b = [t.float().cpu() for t in before]
@@ -107,6 +113,8 @@ def _fedavg(party, addresses, kind):
         "max_abs_err": (a[0] - exp).abs().max().item(),
         "n_bad": int(((a[0] - exp).abs() > (2.0 ** -7) * exp.abs() + 1e-6).sum().item()),
         "max_after_diff": (a[0] - a[1]).abs().max().item(),
+        "before_recv_vs_sender": [(float(t.sum()), x[1]) for t, x in zip(b, before_s)],
+        "after_recv_vs_sender": [(float(t.sum()), x[1]) for t, x in zip(a, after_s)],
     }
     import json
     import os

@@ -51,7 +51,7 @@ def test_push_unpack_bit_exact(ctrl, nbytes, bulk):
     K.push(src.data_ptr(), arena.data_ptr(), nbytes, flag_ptr=f["flag"], flag_value=7, done_counter_ptr=f["done"],
            use_bulk=bulk)
     K.unpack(arena.data_ptr(), dst.data_ptr(), nbytes, flag_ptr=f["flag"], flag_value=7,
-             done_counter_ptr=f["undone"], status_ptr=f["status"], timeout_cycles=int(5e9))
+             done_counter_ptr=f["undone"], status_ptr=f["status"], timeout_ns=int(5e9))
     torch.cuda.synchronize()
     assert torch.equal(src, dst)
     assert ctrl[0].item() == 7  # flag published
@@ -71,7 +71,7 @@ def test_unpack_waits_for_flag_on_device(ctrl):
     torch.cuda.synchronize()
     with torch.cuda.stream(s_recv):
         K.unpack(arena.data_ptr(), dst.data_ptr(), n * 4, flag_ptr=f["flag"], flag_value=1,
-                 done_counter_ptr=f["undone"], status_ptr=f["status"], timeout_cycles=int(10e9), stream=s_recv)
+                 done_counter_ptr=f["undone"], status_ptr=f["status"], timeout_ns=int(10e9), stream=s_recv)
     assert not s_recv.query()  # still waiting
     with torch.cuda.stream(s_send):
         K.push(src.data_ptr(), arena.data_ptr(), n * 4, flag_ptr=f["flag"], flag_value=1,
@@ -85,7 +85,7 @@ def test_unpack_timeout_sets_status(ctrl):
     ctrl.zero_()
     a = torch.zeros(64, dtype=torch.uint8, device=DEV)
     K.unpack(a.data_ptr(), a.data_ptr(), 16, flag_ptr=f["flag"], flag_value=5, done_counter_ptr=f["undone"],
-             status_ptr=f["status"], timeout_cycles=int(2e6))
+             status_ptr=f["status"], timeout_ns=int(2e6))
     torch.cuda.synchronize()
     assert ctrl[18].item() == 1
 
@@ -100,7 +100,7 @@ def test_push_cast_f32_to_bf16_and_back(ctrl):
            done_counter_ptr=f["done"])
     y = torch.zeros(n, device=DEV)
     K.unpack(wire.data_ptr(), y.data_ptr(), n, mode=K.MODE_BF16_TO_F32, flag_ptr=f["flag"], flag_value=1,
-             done_counter_ptr=f["undone"], status_ptr=f["status"], timeout_cycles=int(5e9))
+             done_counter_ptr=f["undone"], status_ptr=f["status"], timeout_ns=int(5e9))
     torch.cuda.synchronize()
     ref = (x * 0.5).to(torch.bfloat16)
     assert torch.equal(wire, ref)
@@ -131,7 +131,7 @@ def test_fp8_block_scaled_wire_format_matches_torch(ctrl, n):
     y = torch.zeros(n, dtype=torch.bfloat16, device=DEV)
     K.unpack(payload.data_ptr(), y.data_ptr(), n, mode=K.MODE_FP8_TO_BF16, scales_ptr=scales.data_ptr(),
              flag_ptr=f["flag"], flag_value=1, done_counter_ptr=f["undone"], status_ptr=f["status"],
-             timeout_cycles=int(5e9))
+             timeout_ns=int(5e9))
     torch.cuda.synchronize()
     xf = x.float().view(-1, 32)
     amax = xf.abs().amax(dim=1, keepdim=True)
@@ -167,7 +167,7 @@ def _agg_single(kind, n=32 * 1000, **kw):
     buf = x.clone()
     K.aggregate(inputs=[buf.data_ptr()], outputs=[buf.data_ptr()], my_rank=0, shard_start=0, shard_len=n, kind=kind,
                 sig_ptr=pad.data_ptr(), sig_peers=[pad.data_ptr()], epoch=0, status_ptr=pad.data_ptr() + 60000,
-                timeout_cycles=int(5e9), **kw)
+                timeout_ns=int(5e9), **kw)
     torch.cuda.synchronize()
     return x, buf
 
@@ -209,7 +209,7 @@ def test_aggregate_adam_n1_matches_torch_adamw():
                     kind=K.AGG_ADAM, master_ptr=master.data_ptr(), mom_ptr=mom.data_ptr(), var_ptr=var.data_ptr(),
                     lr=1e-2, beta1=0.9, beta2=0.99, eps=1e-8, weight_decay=0.1, step=step, sig_ptr=pad.data_ptr(),
                     sig_peers=[pad.data_ptr()], epoch=2 * step, status_ptr=pad.data_ptr() + 60000,
-                    timeout_cycles=int(5e9))
+                    timeout_ns=int(5e9))
         torch.cuda.synchronize()
         assert torch.allclose(master, p.detach(), rtol=2e-5, atol=2e-6), step
     assert torch.equal(out, master.to(torch.bfloat16))
@@ -223,7 +223,7 @@ def test_aggregate_fp8_out_n1():
     scales = torch.zeros(n // 32, dtype=torch.uint8, device=DEV)
     K.aggregate(inputs=[x.data_ptr()], outputs=[out.data_ptr()], out_scales=[scales.data_ptr()], out_fp8=True,
                 my_rank=0, shard_start=0, shard_len=n, kind=K.AGG_AVG, sig_ptr=pad.data_ptr(),
-                sig_peers=[pad.data_ptr()], epoch=0, status_ptr=pad.data_ptr() + 60000, timeout_cycles=int(5e9))
+                sig_peers=[pad.data_ptr()], epoch=0, status_ptr=pad.data_ptr() + 60000, timeout_ns=int(5e9))
     torch.cuda.synchronize()
     xf = x.float().view(-1, 32)
     e = torch.ceil(torch.log2(xf.abs().amax(1, keepdim=True).clamp_min(2.0 ** -120) / 448.0))
@@ -246,7 +246,7 @@ def test_two_virtual_parties_on_one_gpu_rendezvous_in_kernel():
         K.aggregate(inputs=[b.data_ptr() for b in bufs], outputs=[b.data_ptr() for b in bufs], my_rank=r,
                     shard_start=r * shard, shard_len=shard, kind=K.AGG_AVG, sig_ptr=pads[r].data_ptr(),
                     sig_peers=[p.data_ptr() for p in pads], epoch=0, status_ptr=pads[r].data_ptr() + 60000,
-                    timeout_cycles=int(10e9), stream=streams[r], blocks=32)
+                    timeout_ns=int(10e9), stream=streams[r], blocks=32)
     torch.cuda.synchronize()
     ref = ((xs[0].float() + xs[1].float()) * 0.5).to(torch.bfloat16)
     assert torch.equal(bufs[0], ref) and torch.equal(bufs[1], ref)

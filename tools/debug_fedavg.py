@@ -90,6 +90,48 @@ def run(rank, world, base_port):
             "after_err": [float((a - exp).abs().max()) for a in after],
             "after_sums": [float(a.sum()) for a in after], "exp_sum": float(exp.sum()),
         }
+    # ---- 3. the FedAvgWorker flow of tests/test_gpu_fed_nvlink.py with sender-side checksums ------
+    from rayfed_b200.fl import FedAvgWorker
+    from rayfed_b200.models import resnet18
+
+    class W(FedAvgWorker):
+        def snap(self, mode):
+            if mode == "device_sync":
+                torch.cuda.synchronize()
+            elif mode == "lane_sync":
+                torch.cuda.current_stream().synchronize()
+            c = self.bucket.flat_w.clone()
+            return c
+
+        def live_sum(self):
+            torch.cuda.synchronize()
+            return float(self.bucket.flat_w.float().sum())
+
+    def batch_fn(r, i, _rank=rank):
+        g = torch.Generator().manual_seed(100 * _rank + 10 * r + i)
+        return torch.randn(8, 3, 32, 32, generator=g), torch.randint(0, 10, (8,), generator=g)
+
+    for mode in ("none", "lane_sync", "device_sync", "none"):
+        Wk = fed.remote(W)
+        ws = {p: Wk.party(p).remote(lambda: resnet18(10, width=16), parties=parties, party=p, batch_fn=batch_fn,
+                                    lr=0.05, kind="fedavg") for p in parties}
+        losses = [ws[p].local_round.remote(2) for p in parties]
+        b = fed.get([ws[p].snap.remote(mode) for p in parties])
+        for p in parties:
+            ws[p].aggregate.remote()
+        a = fed.get([ws[p].snap.remote(mode) for p in parties])
+        live = fed.get([ws[p].live_sum.remote() for p in parties])
+        bt = [x.float().cpu() for x in b]
+        at = [x.float().cpu() for x in a]
+        exp = ((bt[0] + bt[1]) * 0.5).to(torch.bfloat16).float()
+        out.setdefault("worker", []).append({
+            "mode": mode,
+            "before_sums": [float(t.sum()) for t in bt],
+            "after_sums": [float(t.sum()) for t in at],
+            "live_sums_after": live, "exp_sum": float(exp.sum()),
+            "after_err_vs_exp": [float((t - exp).abs().max()) for t in at],
+            "after_diff": float((at[0] - at[1]).abs().max()),
+        })
     fed.shutdown()
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open(f"gpurun_out/debug_fedavg_{rank}.json", "w"), indent=1)

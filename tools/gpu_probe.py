@@ -75,7 +75,7 @@ def run(rank, nproc, xdir, args):
                    done_counter_ptr=done, device_index=dev, use_bulk=bulk)
             dst = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{dev}")
             K.unpack(buf.local_ptr + 4096, dst.data_ptr(), nbytes, flag_ptr=flag_local, flag_value=seq,
-                     done_counter_ptr=undone, status_ptr=status, timeout_cycles=int(20e9), device_index=dev)
+                     done_counter_ptr=undone, status_ptr=status, timeout_ns=int(20e9), device_index=dev)
             torch.cuda.synchronize()
             # expected: what the *previous* rank generated
             g = torch.Generator(device=f"cuda:{dev}")
@@ -125,7 +125,7 @@ def run(rank, nproc, xdir, args):
     y = torch.empty(n, dtype=torch.bfloat16, device=f"cuda:{dev}")
     K.unpack(buf.local_ptr + 4096, y.data_ptr(), n, mode=K.MODE_FP8_TO_BF16, scales_ptr=buf.local_ptr + 4096 + pay_pad,
              flag_ptr=flag_local, flag_value=1, done_counter_ptr=undone, status_ptr=status,
-             timeout_cycles=int(20e9), device_index=dev)
+             timeout_ns=int(20e9), device_index=dev)
     torch.cuda.synchronize()
     xf = x.float().view(-1, 32)
     amax = xf.abs().amax(dim=1, keepdim=True).clamp_min(1e-30)
@@ -156,7 +156,7 @@ def run(rank, nproc, xdir, args):
     epoch = 0
     K.aggregate(inputs=wbuf.peer_ptrs, outputs=wbuf.peer_ptrs, my_rank=rank, shard_start=rank * shard,
                 shard_len=shard, kind=K.AGG_AVG, sig_ptr=sig_ptr, sig_peers=sig_peers, epoch=epoch,
-                status_ptr=status, timeout_cycles=int(20e9), device_index=dev)
+                status_ptr=status, timeout_ns=int(20e9), device_index=dev)
     epoch += 2
     torch.cuda.synchronize()
     group.barrier()
@@ -172,7 +172,7 @@ def run(rank, nproc, xdir, args):
     K.aggregate(inputs=wbuf.peer_ptrs, outputs=wbuf.peer_ptrs, my_rank=rank, shard_start=rank * shard,
                 shard_len=shard, kind=K.AGG_SGD, master_ptr=master.data_ptr(), mom_ptr=mom.data_ptr(), lr=0.1,
                 momentum=0.9, weight_decay=0.01, sig_ptr=sig_ptr, sig_peers=sig_peers, epoch=epoch,
-                status_ptr=status, timeout_cycles=int(20e9), device_index=dev)
+                status_ptr=status, timeout_ns=int(20e9), device_index=dev)
     epoch += 2
     torch.cuda.synchronize()
     group.barrier()
@@ -188,7 +188,7 @@ def run(rank, nproc, xdir, args):
         nonlocal epoch
         K.aggregate(inputs=wbuf.peer_ptrs, outputs=wbuf.peer_ptrs, my_rank=rank, shard_start=rank * shard,
                     shard_len=shard, kind=K.AGG_AVG, sig_ptr=sig_ptr, sig_peers=sig_peers, epoch=epoch,
-                    status_ptr=status, timeout_cycles=int(20e9), device_index=dev)
+                    status_ptr=status, timeout_ns=int(20e9), device_index=dev)
         epoch += 2
 
     t = timed(agg_once, stream, iters=20)
@@ -219,7 +219,7 @@ def run(rank, nproc, xdir, args):
                 K.aggregate(inputs=mcbuf.peer_ptrs, outputs=mcbuf.peer_ptrs, my_rank=rank,
                             shard_start=rank * shard, shard_len=shard, kind=K.AGG_AVG, mc_in=mcbuf.mc_ptr,
                             mc_out=mcbuf.mc_ptr, sig_ptr=sig_ptr, sig_peers=sig_peers, epoch=epoch,
-                            status_ptr=status, timeout_cycles=int(20e9), device_index=dev)
+                            status_ptr=status, timeout_ns=int(20e9), device_index=dev)
                 epoch += 2
                 torch.cuda.synchronize()
                 group.barrier()
@@ -230,7 +230,7 @@ def run(rank, nproc, xdir, args):
                     K.aggregate(inputs=mcbuf.peer_ptrs, outputs=mcbuf.peer_ptrs, my_rank=rank,
                                 shard_start=rank * shard, shard_len=shard, kind=K.AGG_AVG, mc_in=mcbuf.mc_ptr,
                                 mc_out=mcbuf.mc_ptr, sig_ptr=sig_ptr, sig_peers=sig_peers, epoch=epoch,
-                                status_ptr=status, timeout_cycles=int(20e9), device_index=dev)
+                                status_ptr=status, timeout_ns=int(20e9), device_index=dev)
                     epoch += 2
 
                 group.barrier()

@@ -59,7 +59,7 @@ def main():
         def agg():
             K.aggregate(inputs=[buf.data_ptr()], outputs=[buf.data_ptr()], my_rank=0, shard_start=0, shard_len=n,
                         kind=K.AGG_AVG, sig_ptr=base + 4096, sig_peers=[base + 4096], epoch=e[0],
-                        status_ptr=base + 128, timeout_cycles=int(5e9), blocks=blocks)
+                        status_ptr=base + 128, timeout_ns=int(5e9), blocks=blocks)
             e[0] += 2
 
         t = timed(agg)
@@ -72,7 +72,7 @@ def main():
         K.aggregate(inputs=[buf.data_ptr()], outputs=[buf.data_ptr()], my_rank=0, shard_start=0, shard_len=n,
                     kind=K.AGG_FEDAVGM, master_ptr=master.data_ptr(), mom_ptr=mom.data_ptr(), lr=1.0, momentum=0.9,
                     sig_ptr=base + 4096, sig_peers=[base + 4096], epoch=e[0], status_ptr=base + 128,
-                    timeout_cycles=int(5e9))
+                    timeout_ns=int(5e9))
         e[0] += 2
 
     t = timed(agg_sgd)
@@ -83,7 +83,7 @@ def main():
         plan = K.AggregatePlan(inputs=[buf.data_ptr()], outputs=[buf.data_ptr()], my_rank=0, shard_start=0,
                                shard_len=n, kind=kind, master_ptr=master.data_ptr(), mom_ptr=mom.data_ptr(), lr=1.0,
                                momentum=0.9, sig_ptr=base + 8192, sig_peers=[base + 8192], epoch_dev_ptr=base + 256,
-                               agg_done_ptr=base + 260, status_ptr=base + 264, timeout_cycles=int(5e9))
+                               agg_done_ptr=base + 260, status_ptr=base + 264, timeout_ns=int(5e9))
         t = timed(lambda: plan.launch(0, 1))
         byts = n * (4 if kind == K.AGG_AVG else 20)
         out[f"aggregate_plan_{name}_n1"] = {"us": t * 1e6, "GBps": byts / t / 1e9, "frac_hbm": byts / t / hbm}
@@ -91,7 +91,7 @@ def main():
     plan = K.AggregatePlan(inputs=[tiny.data_ptr()], outputs=[tiny.data_ptr()], my_rank=0, shard_start=0,
                            shard_len=4096, kind=K.AGG_AVG, sig_ptr=base + 8192, sig_peers=[base + 8192],
                            epoch_dev_ptr=base + 256, agg_done_ptr=base + 260, status_ptr=base + 264,
-                           timeout_cycles=int(5e9))
+                           timeout_ns=int(5e9))
     t = timed(lambda: plan.launch(0, 1), iters=200)
     out["aggregate_plan_launch_floor_us"] = t * 1e6
     # K3 tcgen05 LoRA merge, Llama-3-8B q_proj shape, 8 parties x r=16 (loopback operands)

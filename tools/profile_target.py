@@ -30,7 +30,7 @@ Wout = torch.empty_like(W)
 plan = K.AggregatePlan(inputs=[buf.data_ptr()], outputs=[buf.data_ptr()], my_rank=0, shard_start=0, shard_len=n,
                        kind=K.AGG_FEDAVGM, master_ptr=master.data_ptr(), mom_ptr=mom.data_ptr(), lr=1.0,
                        momentum=0.9, sig_ptr=base + 4096, sig_peers=[base + 4096], epoch_dev_ptr=base + 256,
-                       agg_done_ptr=base + 260, status_ptr=base + 264, timeout_cycles=int(5e9))
+                       agg_done_ptr=base + 260, status_ptr=base + 264, timeout_ns=int(5e9))
 for _ in range(3):
     K.push(big.data_ptr(), big2.data_ptr(), 256 << 20, flag_ptr=base, flag_value=1, done_counter_ptr=base + 64,
            use_bulk=False)
