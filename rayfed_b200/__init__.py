@@ -12,10 +12,16 @@ Drop-in API of ray-project/rayfed (``import rayfed_b200 as fed``)::
 plus the B200-native federated-learning layer (``fed.fl``), the NVLink
 transport and the sm_100a kernels (``fed.ops``).
 """
-from .api import get, init, kill, remote, shutdown  # noqa: F401
-from .exceptions import FedRemoteError, FedTaskError  # noqa: F401
-from .fed_object import FedObject  # noqa: F401
-from .proxy.barriers import recv, send  # noqa: F401
+import os as _os
+
+# Streams are multiplexed onto a small number of GPU front-end queues (default 8);
+# kernels that wait for a peer must not sit in front of unrelated local work.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+from .api import get, init, kill, remote, shutdown  # noqa: E402,F401
+from .exceptions import FedRemoteError, FedTaskError  # noqa: E402,F401
+from .fed_object import FedObject  # noqa: E402,F401
+from .proxy.barriers import recv, send  # noqa: E402,F401
 
 __all__ = [
     "get",

@@ -40,12 +40,6 @@ OFF_ARENA = 128 * 1024
 SIGNAL_BYTES = 64 * 1024
 ALIGN = 256
 
-import os as _os
-
-_DEBUG_SYNC_SEND = _os.environ.get("RAYFED_DEBUG_SYNC_SEND") == "1"
-_DEBUG_MODE = _os.environ.get("RAYFED_DEBUG_PUSH_MODE", "")
-_DEBUG_SYNC_RECV = _os.environ.get("RAYFED_DEBUG_SYNC_RECV") == "1"
-
 _WIRE = {None: None, "none": None, "bf16": "bf16", "fp8_e4m3": "fp8_e4m3", "fp8": "fp8_e4m3"}
 
 
@@ -164,13 +158,7 @@ class DeviceChannel:
             dst = self._peer(dest_rank, region + off)
             dst_scales = dst + pay_pad if scales_bytes else 0
             stream = self._push_stream
-            if _DEBUG_MODE == "same_stream" and producer_stream is not None:
-                stream = producer_stream
-            elif _DEBUG_MODE == "wait_stream" and producer_stream is not None:
-                stream.wait_stream(producer_stream)
-            elif ready_event is not None:
-                if _DEBUG_SYNC_SEND:
-                    ready_event.synchronize()
+            if ready_event is not None:
                 stream.wait_event(ready_event)
             else:
                 stream.wait_stream(torch.cuda.current_stream(self._dev))
@@ -184,6 +172,15 @@ class DeviceChannel:
             "off": off, "seq": seq, "end": end_head, "mode": mode, "numel": numel, "dtype": str(t.dtype)[6:],
             "shape": tuple(tensor.shape), "pay": payload_bytes, "pad": pay_pad, "scales": scales_bytes,
         }
+
+    def record_push_event(self):
+        """Event after everything launched so far on the push stream."""
+        import torch
+
+        with torch.cuda.device(self.device_index):
+            ev = torch.cuda.Event()
+            ev.record(self._push_stream)
+        return ev
 
     # -- receive -----------------------------------------------------------------------
     def unpack_tensor(self, src_rank: int, desc: dict):
@@ -220,8 +217,6 @@ class DeviceChannel:
             ev = torch.cuda.Event()
             ev.record(stream)
             out.record_stream(stream)
-            if _DEBUG_SYNC_RECV:
-                ev.synchronize()
         self.stats["tensors_received"] += 1
         self.stats["bytes_received"] += desc["pay"] + desc["scales"]
         return out, ev

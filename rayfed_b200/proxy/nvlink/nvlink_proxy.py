@@ -19,6 +19,7 @@ from __future__ import annotations
 import io
 import logging
 import pickle
+import queue
 import threading
 from typing import Dict, Optional
 
@@ -32,9 +33,6 @@ from ..native.socket_proxy import NativeReceiverProxy, NativeSenderProxy, _ack_d
 
 logger = logging.getLogger(__name__)
 
-import os as _os
-
-_DEBUG_CONSUMER_SYNC = _os.environ.get("RAYFED_DEBUG_CONSUMER_SYNC") == "1"
 _DEVQ = "__devq__"
 _TAG = "fedcuda"
 _DEFAULT_MIN_BYTES = 4096
@@ -96,6 +94,32 @@ class NvlinkSenderProxy(NativeSenderProxy):
         self._min_bytes = cfg.device_min_bytes if cfg.device_min_bytes is not None else _DEFAULT_MIN_BYTES
         self._order_lock = threading.Lock()
         self._k = {}  # dest -> number of device messages sent
+        # Descriptor frames are released only once the push kernel has *finished*:
+        # the receiver then launches its unpack kernel against data that is already
+        # there.  (An eagerly launched unpack kernel that spins on the flag can
+        # deadlock: its GPU front-end queue may be shared with a later-submitted
+        # kernel the producer transitively waits for — measured on B200, see
+        # profiles/README.md.)
+        self._done_q = queue.SimpleQueue()
+        self._done_thread = threading.Thread(target=self._completion_loop, name="fed-push-done", daemon=True)
+        self._done_thread.start()
+
+    def _completion_loop(self):
+        while True:
+            item = self._done_q.get()
+            if item is None:
+                return
+            ev, dest_party, k, blob = item
+            try:
+                ev.synchronize()  # releases the GIL
+                self._transport.send(dest_party, f"{_DEVQ}/{self._party}", str(k), blob, False, _ack_decoder)
+            except Exception:  # noqa: BLE001
+                logger.exception("failed to publish device descriptors")
+
+    def stop(self):
+        self._done_q.put(None)
+        self._done_thread.join(timeout=5)
+        super().stop()
 
     def send(self, dest_party, data, upstream_seq_id, downstream_seq_id):
         ready_event = None
@@ -126,8 +150,7 @@ class NvlinkSenderProxy(NativeSenderProxy):
             k = self._k.get(dest_party, 0) + 1
             self._k[dest_party] = k
             descs = [channel.push_tensor(dest_rank, t, ready_event, producer_stream=producer_stream) for t in tensors]
-            self._transport.send(dest_party, f"{_DEVQ}/{self._party}", str(k), pickle.dumps(descs), False,
-                                 _ack_decoder)
+            self._done_q.put((channel.record_push_event(), dest_party, k, pickle.dumps(descs)))
         frame = pickle.dumps((_TAG, k, buf.getvalue()), protocol=5)
         return self._transport.send(dest_party, str(upstream_seq_id), str(downstream_seq_id), frame, False,
                                     _ack_decoder)
@@ -200,10 +223,6 @@ class NvlinkReceiverProxy(NativeReceiverProxy):
                 _, k, skeleton = obj
                 parts = self._take(src_party, k)
                 value = _DeviceUnpickler(io.BytesIO(skeleton), lambda idx: parts[idx][0]).load()
-                if _DEBUG_CONSUMER_SYNC:
-                    import torch
-
-                    torch.cuda.synchronize()
                 # the receive stream is in-order: the last unpack's event covers them all
                 return _Produced(value, parts[-1][1])
             if isinstance(obj, FedRemoteError):
