@@ -88,8 +88,11 @@ def _fedavg(party, addresses, kind):
 
     class DiagWorker(FedAvgWorker):
         def snap(self):
+            # NOTE: no host sync here on purpose — the value is handed to the transport
+            # while the (peer-dependent) aggregate kernel may still be running; this is
+            # the regression test for the eager-unpack deadlock (profiles/README.md).
             c = self.bucket.flat_w.clone()
-            return c, float(c.float().sum())
+            return c, c.float().sum()
 
     Worker = fed.remote(DiagWorker)
     workers = {p: Worker.party(p).remote(lambda: resnet18(10, width=16), parties=parties, party=p,
@@ -113,8 +116,8 @@ def _fedavg(party, addresses, kind):
         "max_abs_err": (a[0] - exp).abs().max().item(),
         "n_bad": int(((a[0] - exp).abs() > (2.0 ** -7) * exp.abs() + 1e-6).sum().item()),
         "max_after_diff": (a[0] - a[1]).abs().max().item(),
-        "before_recv_vs_sender": [(float(t.sum()), x[1]) for t, x in zip(b, before_s)],
-        "after_recv_vs_sender": [(float(t.sum()), x[1]) for t, x in zip(a, after_s)],
+        "before_recv_vs_sender": [(float(t.sum()), float(x[1])) for t, x in zip(b, before_s)],
+        "after_recv_vs_sender": [(float(t.sum()), float(x[1])) for t, x in zip(a, after_s)],
     }
     import json
     import os
