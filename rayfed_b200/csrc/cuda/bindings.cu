@@ -62,6 +62,24 @@ void cu_check(CUresult r, const char* what) {
 
 size_t round_up(size_t x, size_t g) { return (x + g - 1) / g * g; }
 
+// [rows, cols] row-major bf16 matrix -> TMA descriptor with a {64 cols, 128 rows} box, SWIZZLE_128B.
+CUtensorMap make_bf16_tile_map(uint64_t ptr, uint64_t rows, uint64_t cols) {
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = drv<EncodeFn>("cuTensorMapEncodeTiled");
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  cu_check(encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, P<void>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
+           "cuTensorMapEncodeTiled");
+  return m;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(_fedcuda, m) {
@@ -447,7 +465,7 @@ PYBIND11_MODULE(_fedcuda, m) {
       "lora_merge",
       [](const std::vector<uint64_t>& b, const std::vector<uint64_t>& at, uint64_t w_base, uint64_t w_base_scales,
          uint64_t out, uint64_t out_scales, uint64_t m_rows, uint64_t n_cols, int r, float scale,
-         const std::vector<float>& weights, bool base_fp8, bool out_fp8, uint64_t stream) {
+         const std::vector<float>& weights, bool base_fp8, bool out_fp8, uint64_t stream, bool use_tma) {
         LoraMergeArgs a{};
         fill_peers(a.b, b);
         fill_peers(a.at, at);
@@ -463,11 +481,21 @@ PYBIND11_MODULE(_fedcuda, m) {
         for (int i = 0; i < kMaxParties; ++i) a.w[i] = i < (int)weights.size() ? weights[i] : 1.f;
         a.base_fp8 = base_fp8;
         a.out_fp8 = out_fp8;
-        check(fedk_launch_lora_merge(&a, (cudaStream_t)(uintptr_t)stream), "fed_lora_merge launch");
+        if (use_tma && !base_fp8 && !out_fp8 && n_cols % 64 == 0 && (out % 16 == 0) && (w_base % 16 == 0)) {
+          struct alignas(64) Maps {
+            CUtensorMap w;
+            CUtensorMap out;
+          } maps;
+          maps.out = make_bf16_tile_map(out, m_rows, n_cols);
+          maps.w = w_base ? make_bf16_tile_map(w_base, m_rows, n_cols) : maps.out;
+          check(fedk_launch_lora_merge_tma(&a, &maps, (cudaStream_t)(uintptr_t)stream), "fed_lora_merge_tma launch");
+        } else {
+          check(fedk_launch_lora_merge(&a, (cudaStream_t)(uintptr_t)stream), "fed_lora_merge launch");
+        }
       },
       py::arg("b"), py::arg("at"), py::arg("w_base"), py::arg("w_base_scales"), py::arg("out"),
       py::arg("out_scales"), py::arg("m"), py::arg("n"), py::arg("r"), py::arg("scale"), py::arg("weights"),
-      py::arg("base_fp8"), py::arg("out_fp8"), py::arg("stream"));
+      py::arg("base_fp8"), py::arg("out_fp8"), py::arg("stream"), py::arg("use_tma") = true);
 
   m.def(
       "local_sgd",

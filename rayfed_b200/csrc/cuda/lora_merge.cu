@@ -19,6 +19,8 @@
 // Storage convention (ours, chosen for the hardware): B_i is [M, r] row-major
 // and A_i is stored transposed, At_i = [N, r] row-major, so both operands are
 // K-major and a party's slice of K is r contiguous elements.
+#include <cuda.h>
+
 #include "kernels.h"
 
 namespace fedk {
@@ -276,6 +278,168 @@ __global__ void __launch_bounds__(kLoraThreads) fed_lora_merge_kernel(const __gr
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kLoraBN) : "memory");
   }
+}
+
+
+// ---------------------------------------------------------------------------
+// TMA-tiled variant (bf16 base/out): the W_base tile is fetched by the TMA engine
+// (cp.async.bulk.tensor.2d, SWIZZLE_128B) while the SMs gather the operands from the
+// peers, the epilogue updates the tile in shared memory (row-per-thread after
+// tcgen05.ld, conflict-free thanks to the hardware swizzle) and one thread writes
+// it back with a TMA store.  Global traffic is fully coalesced both ways.
+struct LoraTmaMaps {
+  CUtensorMap w;
+  CUtensorMap out;
+};
+
+__device__ __forceinline__ void lm_tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(lm_smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(lm_smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void lm_tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0),
+               "r"(c1), "r"(lm_smem_u32(smem_src))
+               : "memory");
+}
+__device__ __forceinline__ void lm_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(lm_smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+__global__ void __launch_bounds__(kLoraThreads)
+fed_lora_merge_tma_kernel(const __grid_constant__ LoraMergeArgs a, const __grid_constant__ LoraTmaMaps maps) {
+  extern __shared__ unsigned char lm_smem[];
+  __shared__ __align__(8) uint64_t mma_done;
+  __shared__ __align__(8) uint64_t w_full;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int K = a.n_parties * a.r;
+  const int atoms = (K + 63) >> 6;
+  const uint32_t raw = lm_smem_u32(lm_smem);
+  unsigned char* tile0 = lm_smem + (((raw + 1023u) & ~1023u) - raw);
+  unsigned char* sW = tile0;                                   // [2 atoms][128 rows][128 B] output tile
+  unsigned char* sA = tile0 + 2 * (kLoraBM * 128);
+  unsigned char* sB = sA + (size_t)atoms * (kLoraBM * 128);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const size_t m0 = (size_t)blockIdx.y * kLoraBM;
+  const size_t n0 = (size_t)blockIdx.x * kLoraBN;
+  const bool has_base = a.w_base != nullptr;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     lm_smem_u32(&tmem_base_slot)),
+                 "n"(kLoraBN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lm_smem_u32(&mma_done)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lm_smem_u32(&w_full)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (has_base) {
+      // W_base tile by TMA: overlaps the operand gather below
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lm_smem_u32(&w_full)),
+                   "r"(2u * kLoraBM * 128u)
+                   : "memory");
+      lm_tma_load_2d(sW, &maps.w, (int)n0, (int)m0, &w_full);
+      lm_tma_load_2d(sW + kLoraBM * 128, &maps.w, (int)n0 + 64, (int)m0, &w_full);
+    }
+  }
+
+  lm_gather_tile(sA, a.b, a.n_parties, a.r, m0, a.m, a.w);
+  lm_gather_tile(sB, a.at, a.n_parties, a.r, n0, a.n, nullptr);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_slot;
+
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = lm_instr_desc();
+    const uint32_t a_base = lm_smem_u32(sA), b_base = lm_smem_u32(sB);
+    const int ksteps = K >> 4;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint32_t off = (uint32_t)(ks >> 2) * (kLoraBM * 128) + (uint32_t)(ks & 3) * 32;
+      lm_mma(tmem_d, lm_make_desc(a_base + off), lm_make_desc(b_base + off), idesc, ks > 0 ? 1u : 0u);
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     lm_smem_u32(&mma_done))
+                 : "memory");
+  }
+
+  lm_mbar_wait(&mma_done, 0);
+  if (has_base) lm_mbar_wait(&w_full, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  const int r = warp * 32 + lane;  // tile row owned by this thread (TMEM lane)
+  const float scale = a.scale;
+#pragma unroll 1
+  for (int c = 0; c < kLoraBN / 32; ++c) {
+    uint32_t v[32];
+    lm_tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+    unsigned char* row = sW + (size_t)(c >> 1) * (kLoraBM * 128) + (size_t)r * 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = (c & 1) * 4 + j;  // logical 16 B chunk within the 128 B atom row
+      uint4* slot = reinterpret_cast<uint4*>(row + ((q ^ (r & 7)) << 4));
+      float f[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[j * 8 + k]) * scale;
+      if (has_base) {
+        const uint4 x = *slot;
+        f[0] += bf16_lo(x.x); f[1] += bf16_hi(x.x); f[2] += bf16_lo(x.y); f[3] += bf16_hi(x.y);
+        f[4] += bf16_lo(x.z); f[5] += bf16_hi(x.z); f[6] += bf16_lo(x.w); f[7] += bf16_hi(x.w);
+      }
+      uint4 y;
+      y.x = pack_bf16x2(f[0], f[1]);
+      y.y = pack_bf16x2(f[2], f[3]);
+      y.z = pack_bf16x2(f[4], f[5]);
+      y.w = pack_bf16x2(f[6], f[7]);
+      *slot = y;
+    }
+  }
+  // generic-proxy writes of the tile -> visible to the TMA engine
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    lm_tma_store_2d(&maps.out, (int)n0, (int)m0, sW);
+    lm_tma_store_2d(&maps.out, (int)n0 + 64, (int)m0, sW + kLoraBM * 128);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem may be released after this
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kLoraBN) : "memory");
+  }
+}
+
+extern "C" cudaError_t fedk_launch_lora_merge_tma(const LoraMergeArgs* a, const void* maps, cudaStream_t stream) {
+  const int K = a->n_parties * a->r;
+  if (a->r % 16 != 0 || K > 256 || K < 16 || a->n % 64 != 0 || a->base_fp8 || a->out_fp8) return cudaErrorInvalidValue;
+  const int atoms = (K + 63) / 64;
+  const int smem = (2 + 2 * atoms) * kLoraBM * 128 + 1024;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(fed_lora_merge_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  dim3 grid((unsigned)((a->n + kLoraBN - 1) / kLoraBN), (unsigned)((a->m + kLoraBM - 1) / kLoraBM));
+  fed_lora_merge_tma_kernel<<<grid, kLoraThreads, smem, stream>>>(*a, *reinterpret_cast<const LoraTmaMaps*>(maps));
+  return cudaGetLastError();
 }
 
 extern "C" cudaError_t fedk_launch_lora_merge(const LoraMergeArgs* a, cudaStream_t stream) {

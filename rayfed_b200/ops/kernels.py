@@ -185,7 +185,7 @@ def barrier(*, n_parties: int, my_rank: int, sig_ptr: int, sig_peers: Sequence[i
 def lora_merge(*, b_ptrs: Sequence[int], at_ptrs: Sequence[int], out_ptr: int, m: int, n: int, r: int,
                scale: Optional[float] = None, weights: Optional[Sequence[float]] = None, w_base_ptr: int = 0,
                w_base_scales_ptr: int = 0, out_scales_ptr: int = 0, base_fp8: bool = False, out_fp8: bool = False,
-               stream=None) -> None:
+               stream=None, use_tma: bool = True) -> None:
     """K3 GEMM (tcgen05/TMEM): ``out = W_base + scale * sum_i w_i * B_i @ A_i`` with the
     operands gathered from every party's adapter buffers. ``B_i``: [m, r]; ``A_i^T``: [n, r]."""
     p = len(b_ptrs)
@@ -197,7 +197,7 @@ def lora_merge(*, b_ptrs: Sequence[int], at_ptrs: Sequence[int], out_ptr: int, m
         raise ValueError("lora_merge needs n % 32 == 0")
     cuda_ext().lora_merge(list(b_ptrs), list(at_ptrs), w_base_ptr, w_base_scales_ptr, out_ptr, out_scales_ptr, m, n,
                           r, float(scale), [float(w) for w in (weights or [1.0] * p)], bool(base_fp8),
-                          bool(out_fp8), _stream_handle(stream))
+                          bool(out_fp8), _stream_handle(stream), bool(use_tma))
     launch_counter.add("fed_lora_merge")
 
 

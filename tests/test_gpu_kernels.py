@@ -257,8 +257,10 @@ def test_two_virtual_parties_on_one_gpu_rendezvous_in_kernel():
 
 
 # -- K3: tcgen05/TMEM LoRA merge -----------------------------------------------------------------
-@pytest.mark.parametrize("parties,r,m,n", [(2, 16, 256, 256), (8, 16, 512, 384), (4, 32, 128, 1024), (1, 64, 200, 96)])
-def test_lora_merge_tcgen05_matches_torch(parties, r, m, n):
+@pytest.mark.parametrize("use_tma", [True, False])
+@pytest.mark.parametrize("parties,r,m,n", [(2, 16, 256, 256), (8, 16, 512, 384), (4, 32, 128, 1024), (1, 64, 200, 96),
+                                           (8, 16, 200, 192)])
+def test_lora_merge_tcgen05_matches_torch(parties, r, m, n, use_tma):
     torch.manual_seed(parties * 1000 + r)
     Bs = [(torch.randn(m, r, device=DEV) * 0.5).to(torch.bfloat16) for _ in range(parties)]
     Ats = [(torch.randn(n, r, device=DEV) * 0.5).to(torch.bfloat16) for _ in range(parties)]
@@ -267,7 +269,7 @@ def test_lora_merge_tcgen05_matches_torch(parties, r, m, n):
     weights = [1.0] * parties
     weights[0] = 0.5
     K.lora_merge(b_ptrs=[b.data_ptr() for b in Bs], at_ptrs=[a.data_ptr() for a in Ats], out_ptr=out.data_ptr(),
-                 m=m, n=n, r=r, scale=1.0 / parties, weights=weights, w_base_ptr=base.data_ptr())
+                 m=m, n=n, r=r, scale=1.0 / parties, weights=weights, w_base_ptr=base.data_ptr(), use_tma=use_tma)
     torch.cuda.synchronize()
     dw = torch.zeros(m, n, device=DEV)
     for i, (b, at) in enumerate(zip(Bs, Ats)):
