@@ -120,9 +120,10 @@ class FedAggregator:
             mc = bucket.buffer.mc_ptr if bucket.buffer is not None else 0
         mc_out = bucket.buffer.mc_ptr if bucket.buffer is not None else 0
         if use_multicast is None:
-            # measured on B200: below 4 parties the P2P path is faster than NVLS
-            # (same link bytes, cheaper instructions); NVLS wins as N grows.
-            use_multicast = n >= 4
+            # measured on B200 (profiles/README.md): at 2 and 4 parties the P2P path is
+            # faster than NVLS (N=4: 148 vs 161 us for 51 MB); NVLS halves the egress
+            # bytes only asymptotically, so it is enabled from 8 parties.
+            use_multicast = n >= 8
         if use_multicast is False or n == 1:
             mc = mc_out = 0
         uniform = all(abs(w - self.weights[0]) < 1e-12 for w in self.weights)
