@@ -35,16 +35,19 @@ logger = logging.getLogger(__name__)
 
 _DEVQ = "__devq__"
 _TAG = "fedcuda"
+_SMALL = "fedcuda-small"
 _DEFAULT_MIN_BYTES = 4096
 
 
 class _DevicePickler(cloudpickle.Pickler):
     """Pickles an object graph, diverting big CUDA tensors to ``sink``."""
 
-    def __init__(self, file, sink, min_bytes):
+    def __init__(self, file, sink, min_bytes, before_host_copy=None):
         super().__init__(file, protocol=5)
         self._sink = sink
         self._min_bytes = min_bytes
+        self._before_host_copy = before_host_copy
+        self.small_tensors = 0
 
     def persistent_id(self, obj):
         import torch
@@ -52,17 +55,27 @@ class _DevicePickler(cloudpickle.Pickler):
         if isinstance(obj, torch.Tensor) and obj.is_cuda and obj.layout == torch.strided:
             if obj.numel() * obj.element_size() >= self._min_bytes:
                 return (_TAG, self._sink(obj.detach()))
+            # small tensors ride the host frame — as CPU data, re-homed on the *receiver's*
+            # device (a plain pickle would resurrect them on the sender's device index and
+            # make every party open a CUDA context on every other party's GPU)
+            if self._before_host_copy is not None and self.small_tensors == 0:
+                self._before_host_copy()  # the producer's stream must be done before a D2H read
+            self.small_tensors += 1
+            return (_SMALL, obj.detach().cpu())
         return None
 
 
 class _DeviceUnpickler(pickle.Unpickler):
-    def __init__(self, file, resolve):
+    def __init__(self, file, resolve, rehome=None):
         super().__init__(file)
         self._resolve = resolve
+        self._rehome = rehome or (lambda t: t)
 
     def persistent_load(self, pid):
         if isinstance(pid, tuple) and pid and pid[0] == _TAG:
             return self._resolve(pid[1])
+        if isinstance(pid, tuple) and pid and pid[0] == _SMALL:
+            return self._rehome(pid[1])
         raise pickle.UnpicklingError(f"unsupported persistent id {pid!r}")
 
 
@@ -139,11 +152,15 @@ class NvlinkSenderProxy(NativeSenderProxy):
             return len(tensors) - 1
 
         buf = io.BytesIO()
-        _DevicePickler(buf, sink, self._min_bytes).dump(data)
+        pickler = _DevicePickler(buf, sink, self._min_bytes,
+                                 ready_event.synchronize if ready_event is not None else None)
+        pickler.dump(data)
         if not tensors:
-            if ready_event is not None:
-                ready_event.synchronize()  # host-resident payload: bytes must be final
-            return self._transport.send(dest_party, str(upstream_seq_id), str(downstream_seq_id), buf.getvalue(),
+            if pickler.small_tensors:
+                frame = pickle.dumps((_TAG, 0, buf.getvalue()), protocol=5)
+            else:
+                frame = buf.getvalue()  # plain host object: nothing to re-home
+            return self._transport.send(dest_party, str(upstream_seq_id), str(downstream_seq_id), frame,
                                         False, _ack_decoder)
         dest_rank = channel.group.parties.index(dest_party)
         with self._order_lock:
@@ -203,6 +220,12 @@ class NvlinkReceiverProxy(NativeReceiverProxy):
                 self._unpacked[(src, k)] = out
                 self._cv.notify_all()
 
+    def _rehome(self, cpu_tensor):
+        ch = current_channel()
+        if ch is None:
+            return cpu_tensor
+        return cpu_tensor.to(f"cuda:{ch.device_index}", non_blocking=False)
+
     def _take(self, src: str, k: int, timeout: float = 120.0):
         with self._cv:
             ok = self._cv.wait_for(lambda: (src, k) in self._unpacked or self._stopping, timeout)
@@ -221,8 +244,13 @@ class NvlinkReceiverProxy(NativeReceiverProxy):
             obj = loads(data)
             if isinstance(obj, tuple) and len(obj) == 3 and obj[0] == _TAG:
                 _, k, skeleton = obj
+                if k == 0:  # no device parts: only (possibly) small tensors to re-home
+                    value = _DeviceUnpickler(io.BytesIO(skeleton), None, self._rehome).load()
+                    if isinstance(value, FedRemoteError):
+                        raise FedTaskError(value, "", "recv")
+                    return value
                 parts = self._take(src_party, k)
-                value = _DeviceUnpickler(io.BytesIO(skeleton), lambda idx: parts[idx][0]).load()
+                value = _DeviceUnpickler(io.BytesIO(skeleton), lambda idx: parts[idx][0], self._rehome).load()
                 # the receive stream is in-order: the last unpack's event covers them all
                 return _Produced(value, parts[-1][1])
             if isinstance(obj, FedRemoteError):
