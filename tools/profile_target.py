@@ -31,7 +31,7 @@ plan = K.AggregatePlan(inputs=[buf.data_ptr()], outputs=[buf.data_ptr()], my_ran
                        kind=K.AGG_FEDAVGM, master_ptr=master.data_ptr(), mom_ptr=mom.data_ptr(), lr=1.0,
                        momentum=0.9, sig_ptr=base + 4096, sig_peers=[base + 4096], epoch_dev_ptr=base + 256,
                        agg_done_ptr=base + 260, status_ptr=base + 264, timeout_ns=int(5e9))
-for _ in range(3):
+for _ in range(2):
     K.push(big.data_ptr(), big2.data_ptr(), 256 << 20, flag_ptr=base, flag_value=1, done_counter_ptr=base + 64,
            use_bulk=False)
     K.push(big.data_ptr(), big2.data_ptr(), 256 << 20, flag_ptr=base, flag_value=1, done_counter_ptr=base + 64,
@@ -41,6 +41,8 @@ for _ in range(3):
     plan.launch(0, 1)
     K.local_sgd(buf.data_ptr(), g.data_ptr(), mo.data_ptr(), n, lr=0.01, momentum=0.9)
     K.lora_merge(b_ptrs=[b.data_ptr() for b in Bs], at_ptrs=[a.data_ptr() for a in Ats], out_ptr=Wout.data_ptr(),
-                 m=M, n=N, r=r, w_base_ptr=W.data_ptr())
+                 m=M, n=N, r=r, w_base_ptr=W.data_ptr(), use_tma=True)
+    K.lora_merge(b_ptrs=[b.data_ptr() for b in Bs], at_ptrs=[a.data_ptr() for a in Ats], out_ptr=Wout.data_ptr(),
+                 m=M, n=N, r=r, w_base_ptr=W.data_ptr(), use_tma=False)
 torch.cuda.synchronize()
 print("profile target done")
