@@ -43,6 +43,7 @@ class CleanupManager:
         self._pending = 0
         self._pending_err = 0
         self._pending_cv = threading.Condition()
+        self._draining = False  # a stop() is waiting: completions must notify
 
     def start(self, exit_on_sending_failure=False, expose_error_trace=False):
         self._exit_on_sending_failure = exit_on_sending_failure
@@ -51,7 +52,7 @@ class CleanupManager:
         self._sending_error_q.start()
         logger.debug("Started the send-checking threads.")
 
-    def stop(self, wait_for_sending=False, drain_timeout_s: float = 600.0, error_drain_timeout_s: float = 10.0):
+    def stop(self, wait_for_sending=False, drain_timeout_s: float = 600.0, error_drain_timeout_s: float = 5.0):
         """Stop watching sends.
 
         ``wait_for_sending`` waits for every *unresolved* send first.  Failures
@@ -60,6 +61,7 @@ class CleanupManager:
         otherwise a party that shuts down right after a failure would leave its
         peers waiting for data that will never come.
         """
+        self._draining = True
         if wait_for_sending:
             with self._pending_cv:
                 self._pending_cv.wait_for(lambda: self._pending <= 0 or not self._sending_data_q.is_started(),
@@ -103,7 +105,7 @@ class CleanupManager:
             self._pending -= 1
             if is_error:
                 self._pending_err -= 1
-            if self._pending <= 0 or self._pending_err <= 0:
+            if self._draining:  # nobody waits on the hot path: skip the notify
                 self._pending_cv.notify_all()
 
     def pending_sends(self) -> int:

@@ -360,10 +360,17 @@ def _job_name() -> str:
     return ctx.get_job_name() if ctx is not None else constants.RAYFED_DEFAULT_JOB_NAME
 
 
+_HOSTS = {"sender": None, "receiver": None}  # hot-path cache of the two proxy hosts
+
+
 def _register(host: ProxyHost, *names):
     rt = get_runtime()
     for n in dict.fromkeys(names):
         rt.register_named(n, host)
+        if n == sender_proxy_actor_name():
+            _HOSTS["sender"] = host
+        if n == receiver_proxy_actor_name():
+            _HOSTS["receiver"] = host
 
 
 def _start_receiver_proxy(addresses: Dict, party: str, logging_level: str, tls_config=None, proxy_cls=None,
@@ -411,6 +418,7 @@ def _start_sender_receiver_proxy(addresses: Dict, party: str, logging_level: str
 
 
 def _stop_proxies():
+    _HOSTS["sender"] = _HOSTS["receiver"] = None
     rt = get_runtime(create=False)
     if rt is None:
         return
@@ -440,7 +448,7 @@ def send(dest_party, data, upstream_seq_id, downstream_seq_id, is_error=False, c
     *failed*, the outcome Ref carries that ``FedTaskError`` — which is how the
     CleanupManager tells "producer failed" from "link failed".
     """
-    host: ProxyHost = get_runtime().get_named(sender_proxy_actor_name())
+    host: ProxyHost = _HOSTS["sender"] or get_runtime().get_named(sender_proxy_actor_name())
     if is_ref(data):
         if data.done():
             e = data.exception()
@@ -480,7 +488,7 @@ def send(dest_party, data, upstream_seq_id, downstream_seq_id, is_error=False, c
 def recv(party: str, src_party: str, upstream_seq_id, curr_seq_id):
     """`Ref` that resolves when the message keyed (upstream, curr) has arrived."""
     assert party, "Party can not be None."
-    host: ProxyHost = get_runtime().get_named(receiver_proxy_actor_name())
+    host: ProxyHost = _HOSTS["receiver"] or get_runtime().get_named(receiver_proxy_actor_name())
     return host.get_data(src_party, upstream_seq_id, curr_seq_id)
 
 
