@@ -16,6 +16,7 @@ Backends
 from __future__ import annotations
 
 import array
+import logging
 import os
 import pickle
 import socket
@@ -24,6 +25,8 @@ from typing import List, Optional
 
 from ..ops.kernels import cuda_ext
 from .group import PartyGroup
+
+logger = logging.getLogger(__name__)
 
 
 class _CudaArrayView:
@@ -91,20 +94,12 @@ class SymmetricHeap:
         nbytes = (nbytes + 255) // 256 * 256
         self._ext.set_device(self.group.device_index)  # cudaSetDevice is per thread
         if self.backend == "vmm" or multicast:
-            try:
-                buf = self._alloc_vmm(name, nbytes, multicast)
-            except Exception as e:  # noqa: BLE001
-                if self.backend == "vmm":
-                    raise
-                import logging
-
-                logging.getLogger(__name__).warning(f"VMM/multicast allocation failed ({e}); using cudaIpc.")
-                # every party must take the same branch: agree on the outcome
-                buf = None
-            ok = self.group.all_gather(self.group.next_tag(f"symm-ok/{name}"), b"1" if buf is not None else b"0")
-            if all(x == b"1" for x in ok):
+            buf = self._alloc_vmm(name, nbytes, multicast)  # agrees internally; None => fall back
+            if buf is not None:
                 self._buffers[name] = buf
                 return buf
+            if self.backend == "vmm":
+                raise RuntimeError("CUDA VMM symmetric allocation is not available on every party")
         buf = self._alloc_ipc(name, nbytes)
         self._buffers[name] = buf
         return buf
@@ -182,39 +177,106 @@ class SymmetricHeap:
             pass
         return [fd if p == g.me else got[p] for p in g.parties]
 
-    def _alloc_vmm(self, name: str, nbytes: int, multicast: bool) -> SymmetricBuffer:
+    def _agree(self, name: str, ok: bool) -> bool:
+        """Collective AND: every party takes the same branch after a step that can fail locally."""
+        votes = self.group.all_gather(self.group.next_tag(f"agree/{name}"), b"1" if ok else b"0")
+        return all(v == b"1" for v in votes)
+
+    def _alloc_vmm(self, name: str, nbytes: int, multicast: bool) -> Optional[SymmetricBuffer]:
+        """VMM-backed symmetric buffer, with an NVLS multicast alias when possible.
+
+        Every step that can fail on one party only is followed by an agreement, so
+        the parties never diverge in the exchange sequence: the result is the same
+        on all of them — (buffer with mc) / (buffer without mc) / None (→ cudaIpc).
+        """
         g = self.group
-        info = self.vmm_info()
-        if not info.get("vmm") or not info.get("posix_fd"):
-            raise RuntimeError(f"CUDA VMM with POSIX fds is not supported here: {info}")
-        want_mc = multicast and bool(info.get("multicast")) and g.size > 1
+        info = {}
+        ok = True
+        try:
+            info = self.vmm_info()
+            ok = bool(info.get("vmm")) and bool(info.get("posix_fd"))
+        except Exception:  # noqa: BLE001
+            ok = False
+        if not self._agree(f"{name}/vmm-cap", ok):
+            return None
+        want_mc = multicast and g.size > 1 and self._agree(f"{name}/mc-cap", bool(info.get("multicast")))
         size = nbytes
-        if want_mc:
-            gran = self._ext.mc_granularity(nbytes, g.size)
-            size = (nbytes + gran - 1) // gran * gran
-        ptr, fd, mapped, mem_handle = self._ext.vmm_alloc(size, g.device_index)
+        ptr = fd = mapped = mem_handle = None
+        try:
+            if want_mc:
+                gran = self._ext.mc_granularity(nbytes, g.size)
+                size = (nbytes + gran - 1) // gran * gran
+            ptr, fd, mapped, mem_handle = self._ext.vmm_alloc(size, g.device_index)
+            ok = True
+        except Exception as e:  # noqa: BLE001
+            logger.warning(f"vmm_alloc failed: {e}")
+            ok = False
+        if not self._agree(f"{name}/alloc", ok):
+            if fd is not None:
+                os.close(fd)
+            return None
         fds = self._exchange_fds(name, fd)
         peers = []
+        try:
+            for r, pfd in enumerate(fds):
+                if r == g.rank:
+                    peers.append(ptr)
+                else:
+                    va, _h = self._ext.vmm_import(pfd, mapped, g.device_index)
+                    peers.append(va)
+            ok = True
+        except Exception as e:  # noqa: BLE001
+            logger.warning(f"vmm_import failed: {e}")
+            ok = False
         for r, pfd in enumerate(fds):
-            if r == g.rank:
-                peers.append(ptr)
-            else:
-                va, _h = self._ext.vmm_import(pfd, mapped, g.device_index)
-                peers.append(va)
-                os.close(pfd)
+            if r != g.rank:
+                try:
+                    os.close(pfd)
+                except OSError:
+                    pass
+        if not self._agree(f"{name}/import", ok):
+            os.close(fd)
+            return None
+
         mc_ptr = 0
         if want_mc:
-            if g.rank == 0:
-                mc_handle, mc_fd = self._ext.mc_create(mapped, g.size)
-            else:
-                mc_handle, mc_fd = 0, -1
-            mc_fds = self._exchange_fds(name + "/mc", mc_fd if g.rank == 0 else fd)
-            if g.rank != 0:
-                mc_handle = self._ext.mc_import(mc_fds[0])
-            self._ext.mc_add_device(mc_handle, g.device_index)
-            g.barrier(g.next_tag(f"mc-added/{name}"))  # all devices added before any bind
-            mc_ptr = self._ext.mc_bind_and_map(mc_handle, mem_handle, mapped, g.device_index)
-            g.barrier(g.next_tag(f"mc-bound/{name}"))
-            self.multicast_ok = True
+            mc_handle, mc_fd = 0, -1
+            try:
+                if g.rank == 0:
+                    mc_handle, mc_fd = self._ext.mc_create(mapped, g.size)
+                ok = True
+            except Exception as e:  # noqa: BLE001
+                logger.warning(f"cuMulticastCreate failed: {e}")
+                ok = False
+            if self._agree(f"{name}/mc-create", ok):
+                mc_fds = self._exchange_fds(name + "/mc", mc_fd if g.rank == 0 else fd)
+                try:
+                    if g.rank != 0:
+                        mc_handle = self._ext.mc_import(mc_fds[0])
+                    self._ext.mc_add_device(mc_handle, g.device_index)
+                    ok = True
+                except Exception as e:  # noqa: BLE001
+                    logger.warning(f"multicast import/add_device failed: {e}")
+                    ok = False
+                for r, pfd in enumerate(mc_fds):
+                    if r != g.rank:
+                        try:
+                            os.close(pfd)
+                        except OSError:
+                            pass
+                if g.rank == 0 and mc_fd >= 0:
+                    os.close(mc_fd)
+                # all devices must be added before anyone binds
+                if self._agree(f"{name}/mc-added", ok):
+                    try:
+                        mc_ptr = self._ext.mc_bind_and_map(mc_handle, mem_handle, mapped, g.device_index)
+                        ok = True
+                    except Exception as e:  # noqa: BLE001
+                        logger.warning(f"cuMulticastBindMem/map failed: {e}")
+                        ok = False
+                    if not self._agree(f"{name}/mc-bound", ok):
+                        mc_ptr = 0
+            if mc_ptr:
+                self.multicast_ok = True
         os.close(fd)
         return SymmetricBuffer(name, mapped, ptr, peers, g.rank, g.device_index, mc_ptr, "vmm")
