@@ -232,17 +232,21 @@ def run_ours(args):
     def mean_weights(*ws):
         return torch.stack([w.float() for w in ws]).mean(0).to(ws[0].dtype)
 
-    def one_round(fetch_loss):
+    def submit_round():
+        """Issue one FedAvg round on every party; returns the FedObjects of the losses."""
         if args.impl == "ours":
-            losses = [workers[p].round.remote(L) for p in parties]
-        else:
-            # reference-style aggregation through the DAG API over the gRPC transport:
-            # local steps, weights -> p0, mean, -> every party
-            losses = [workers[p].local_round.remote(L) for p in parties]
-            ws = [workers[p].flat_weights_host.remote() for p in parties]
-            m = mean_weights.party(parties[0]).remote(*ws)
-            for p in parties:
-                workers[p].load_flat_weights.remote(m)
+            return [workers[p].round.remote(L) for p in parties]
+        # reference-style aggregation through the DAG API over the gRPC transport:
+        # local steps, weights -> p0, mean, -> every party
+        losses = [workers[p].local_round.remote(L) for p in parties]
+        ws = [workers[p].flat_weights_host.remote() for p in parties]
+        m = mean_weights.party(parties[0]).remote(*ws)
+        for p in parties:
+            workers[p].load_flat_weights.remote(m)
+        return losses
+
+    def one_round(fetch_loss):
+        losses = submit_round()
         if fetch_loss:
             return [float(x) for x in fed.get(losses)]
         return None
@@ -274,8 +278,15 @@ def run_ours(args):
     fed.get([workers[p].sync.remote() for p in parties])
     t0 = time.perf_counter()
     last = None
+    prev = None
     for _ in range(K_steps):
-        last = one_round(True)
+        # the controller issues round r, then reads round r-1's losses (D2H) while r runs:
+        # every step's result is still fetched inside the timed region
+        cur = submit_round()
+        if prev is not None:
+            last = [float(x) for x in fed.get(prev)]
+        prev = cur
+    last = [float(x) for x in fed.get(prev)]
     fed.get([workers[p].sync.remote() for p in parties])
     e2e_s = time.perf_counter() - t0
     # max over parties of the wall-clock (every party ran the same loop; exchange the numbers)
