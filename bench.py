@@ -119,12 +119,13 @@ def make_worker_cls():
     class BenchWorker(FedAvgWorker):
         """FedAvgWorker + party-local synthetic dataset in pinned host memory + timers."""
 
-        def __init__(self, parties, party, seed=0, use_cuda_graph=True, kind="fedavg"):
+        def __init__(self, parties, party, seed=0, use_cuda_graph=True, kind="fedavg", fused=True):
             from rayfed_b200.models import resnet50
 
             super().__init__(lambda: resnet50(NUM_CLASSES), parties=parties, party=party, lr=0.05, momentum=0.9,
-                             weight_decay=5e-5, kind=kind, seed=seed, use_cuda_graph=use_cuda_graph)
-            g = torch.Generator().manual_seed(1000 + self.group.rank)
+                             weight_decay=5e-5, kind=kind, seed=seed, use_cuda_graph=use_cuda_graph,
+                             fused_aggregate=fused)
+            g = torch.Generator().manual_seed(1000 + list(parties).index(party))
             nbuf = 8  # ring of distinct pinned batches (77 MB) — larger than any cache on the path
             self._x = [torch.randn(BATCH, 3, IMG, IMG, generator=g).to(torch.bfloat16).pin_memory()
                        for _ in range(nbuf)]
@@ -167,7 +168,8 @@ def make_worker_cls():
             return True
 
         def info(self):
-            return {"bucket_numel": self.bucket.numel, "multicast": self.agg.uses_multicast,
+            return {"bucket_numel": self.bucket.numel,
+                    "multicast": self.agg.uses_multicast if self.agg is not None else False,
                     "backend": self.bucket.buffer.backend if self.bucket.buffer is not None else "local",
                     "h2d_bytes_per_step": self.h2d_bytes_per_step}
 
@@ -224,7 +226,8 @@ def run_ours(args):
              job_name=f"bench-{base}")
 
     Worker = fed.remote(make_worker_cls())
-    workers = {p: Worker.party(p).remote(parties, p, use_cuda_graph=not args.no_graph) for p in parties}
+    workers = {p: Worker.party(p).remote(parties, p, use_cuda_graph=not args.no_graph, fused=args.impl == "ours")
+               for p in parties}
     info = fed.get(workers[parties[0]].info.remote())
     L, K_steps, W = args.local_steps, args.steps, args.warmup
 

@@ -191,8 +191,15 @@ class FedAvgWorker:
                  batch_fn: Optional[Callable] = None, lr: float = 0.05, momentum: float = 0.9,
                  weight_decay: float = 5e-5, kind: str = "fedavg", server_lr: float = 1.0,
                  server_momentum: float = 0.0, channels_last: bool = True, multicast: bool = True,
-                 seed: int = 0, loss_fn=None, use_cuda_graph: bool = False):
-        group, heap, channel = device_context(parties, party)
+                 seed: int = 0, loss_fn=None, use_cuda_graph: bool = False, fused_aggregate: bool = True):
+        if fused_aggregate:
+            group, heap, channel = device_context(parties, party)
+        else:
+            # weights are exchanged through the DAG API instead (reference-style aggregation):
+            # plain local bucket, no symmetric heap, no aggregate kernel
+            dev_idx = torch.cuda.current_device()
+            group = PartyGroup([party], party, FedExchange(), device_index=dev_idx)
+            heap, channel = None, None
         self.group, self.heap, self.channel = group, heap, channel
         dev = torch.device(f"cuda:{group.device_index}")
         torch.cuda.set_device(dev)
@@ -203,8 +210,10 @@ class FedAvgWorker:
         self.model = model.to(torch.bfloat16)
         self.bucket = FlatBucket(self.model, heap, name="fedavg", n_parties=group.size, multicast=multicast)
         self.opt = LocalSGD(self.bucket, lr, momentum, weight_decay)
-        self.agg = FedAggregator(self.bucket, group, channel, kind=kind, lr=server_lr, momentum=server_momentum,
-                                 heap=heap)
+        self.agg = None
+        if fused_aggregate:
+            self.agg = FedAggregator(self.bucket, group, channel, kind=kind, lr=server_lr,
+                                     momentum=server_momentum, heap=heap)
         self.loss_fn = loss_fn or torch.nn.functional.cross_entropy
         self.batch_fn = batch_fn
         self.channels_last = channels_last
