@@ -306,3 +306,20 @@ def test_lora_merge_fp8_base_and_out():
     assert rel < 0.04, rel  # e4m3 has 3 mantissa bits
     e_ref = torch.ceil(torch.log2(ref.view(m, -1, 32).abs().amax(-1) / 448.0))
     assert (out_s.float() - 127 - e_ref).abs().max().item() <= 1
+
+
+def test_timed_out_wait_leaves_destination_untouched_and_flags_pinned_status():
+    """A device wait that times out must not hand out garbage: no copy, credit still
+    returned, and the host sees the failure through a pinned status word (no CUDA call)."""
+    status = torch.zeros(16, dtype=torch.int32).pin_memory()
+    ctrlw = torch.zeros(64, dtype=torch.int32, device=DEV)
+    credit = torch.zeros(2, dtype=torch.int64, device=DEV)
+    arena = torch.full((4096,), 7, dtype=torch.uint8, device=DEV)
+    dst = torch.full((4096,), 42, dtype=torch.uint8, device=DEV)
+    K.unpack(arena.data_ptr(), dst.data_ptr(), 4096, flag_ptr=ctrlw.data_ptr(), flag_value=3,
+             done_counter_ptr=ctrlw.data_ptr() + 8, credit_ptr=credit.data_ptr(), credit_value=1234,
+             status_ptr=status.data_ptr(), timeout_ns=int(3e6))
+    torch.cuda.synchronize()
+    assert int(status[0]) == 1  # visible to the host without a device read
+    assert torch.all(dst == 42)  # destination untouched
+    assert credit[0].item() == 1234  # flow control still advances

@@ -1,0 +1,131 @@
+"""Concurrency stress of the native runtime (no sanitizer available for the embedded
+interpreter, so races are hunted by load): many threads submit / claim / deliver /
+complete concurrently and every result is checked."""
+import random
+import threading
+import time
+
+import pytest
+
+from rayfed_b200 import core
+
+
+def test_executor_under_concurrent_submitters():
+    rt = core.PartyRuntime(pool_threads=4)
+    try:
+        class Counter:
+            def __init__(self):
+                self.n = 0
+
+            def add(self, k):
+                self.n += k
+                return self.n
+
+        actors = [rt.create_actor(Counter) for _ in range(4)]
+        results = {}
+        errors = []
+
+        def submitter(tid):
+            try:
+                rng = random.Random(tid)
+                local = []
+                for i in range(400):
+                    a = actors[rng.randrange(len(actors))]
+                    gate = rt.submit(lambda x=i: x)  # pool task feeding an actor task
+                    local.append((a.submit_method("add", (1,), {}), rt.submit(lambda v: v * 2, (gate,)), i))
+                for r_act, r_pool, i in local:
+                    assert core.get(r_pool, timeout=20) == 2 * i
+                    assert core.get(r_act, timeout=20) >= 1
+                results[tid] = len(local)
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        threads = [threading.Thread(target=submitter, args=(t,)) for t in range(8)]
+        [t.start() for t in threads]
+        [t.join(60) for t in threads]
+        assert not errors, errors
+        assert sum(results.values()) == 8 * 400
+        totals = [core.get(a.submit_method("add", (0,), {}), timeout=10) for a in actors]
+        assert sum(totals) == 8 * 400  # every actor increment ran exactly once, in mailbox order
+    finally:
+        rt.shutdown()
+
+
+def test_mailbox_rendezvous_under_racing_producers_and_consumers():
+    nat = core.native()
+    mb = nat.Mailbox()
+    n = 3000
+    got = {}
+    errors = []
+
+    def producer(lo, hi):
+        for i in range(lo, hi):
+            mb.deliver_raw(str(i), "d", str(i).encode(), False)
+
+    def consumer(lo, hi):
+        try:
+            for i in range(lo, hi):
+                got[i] = mb.claim(str(i), "d").result(20)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    ts = []
+    for k in range(4):
+        lo, hi = k * n // 4, (k + 1) * n // 4
+        ts.append(threading.Thread(target=producer, args=(lo, hi)))
+        ts.append(threading.Thread(target=consumer, args=(lo, hi)))
+    random.Random(0).shuffle(ts)
+    [t.start() for t in ts]
+    [t.join(60) for t in ts]
+    assert not errors, errors
+    assert all(got[i] == str(i).encode() for i in range(n))
+    assert mb.pending() == 0
+
+
+def test_socket_transport_many_inflight_messages_and_acks(tmp_path):
+    nat = core.native()
+    mb = nat.Mailbox()
+    server = nat.SocketTransport("bob", "job", mb)
+    assert server.listen("unix:" + str(tmp_path / "b.sock")) == ""
+    client = nat.SocketTransport("alice", "job", nat.Mailbox())
+    client.add_peer("bob", "unix:" + str(tmp_path / "b.sock"), 5, 0.05, 0.2, 2.0, 20.0)
+    n = 2000
+    payload = b"x" * 3000
+    acks = []
+
+    def sender(lo, hi):
+        for i in range(lo, hi):
+            acks.append(client.send("bob", str(i), "k", payload + str(i).encode(), False, None))
+
+    ts = [threading.Thread(target=sender, args=(k * n // 4, (k + 1) * n // 4)) for k in range(4)]
+    [t.start() for t in ts]
+    [t.join(30) for t in ts]
+    assert client.drain(20.0)
+    assert all(a.exception(10) is None for a in acks)
+    for i in range(n):
+        assert mb.claim(str(i), "k").result(10) == payload + str(i).encode()
+    stats = server.stats()
+    assert stats["receive_op_count"] == n and stats["bytes_received"] >= n * 3000
+    client.stop()
+    server.stop()
+
+
+def test_ref_callbacks_fire_exactly_once_under_races():
+    hits = []
+    lock = threading.Lock()
+    for _ in range(300):
+        r = core.Ref()
+        barrier = threading.Barrier(3)
+
+        def adder():
+            barrier.wait()
+            r.add_done_callback(lambda ref: (lock.acquire(), hits.append(1), lock.release()))
+
+        def setter():
+            barrier.wait()
+            r.set_value(1)
+
+        ts = [threading.Thread(target=adder), threading.Thread(target=adder), threading.Thread(target=setter)]
+        [t.start() for t in ts]
+        [t.join(5) for t in ts]
+    assert len(hits) == 600
