@@ -60,24 +60,29 @@ def test_push_unpack_bit_exact(ctrl, nbytes, bulk):
 
 
 def test_unpack_waits_for_flag_on_device(ctrl):
-    """K4: the unpack kernel parks on the flag; data published later by another stream."""
+    """K4: the unpack kernel parks on the flag and only then copies.  The flag lives in
+    pinned host memory and is flipped by a CPU store, so no second GPU stream is needed
+    (a later-submitted kernel may share a front-end queue with the spinning one — the
+    hazard described in profiles/README.md §8)."""
     f = _flags(ctrl)
     ctrl.zero_()
     n = 1 << 16
     src = torch.arange(n, dtype=torch.int32, device=DEV)
-    arena = torch.zeros(n, dtype=torch.int32, device=DEV)
+    arena = src.clone()  # the payload is already in the arena; only the flag is missing
     dst = torch.zeros(n, dtype=torch.int32, device=DEV)
-    s_recv, s_send = torch.cuda.Stream(), torch.cuda.Stream()
+    flag = torch.zeros(4, dtype=torch.int32).pin_memory()
+    s_recv = torch.cuda.Stream()
     torch.cuda.synchronize()
-    with torch.cuda.stream(s_recv):
-        K.unpack(arena.data_ptr(), dst.data_ptr(), n * 4, flag_ptr=f["flag"], flag_value=1,
-                 done_counter_ptr=f["undone"], status_ptr=f["status"], timeout_ns=int(10e9), stream=s_recv)
-    assert not s_recv.query()  # still waiting
-    with torch.cuda.stream(s_send):
-        K.push(src.data_ptr(), arena.data_ptr(), n * 4, flag_ptr=f["flag"], flag_value=1,
-               done_counter_ptr=f["done"], stream=s_send)
+    K.unpack(arena.data_ptr(), dst.data_ptr(), n * 4, flag_ptr=flag.data_ptr(), flag_value=1,
+             done_counter_ptr=f["undone"], status_ptr=f["status"], timeout_ns=int(20e9), stream=s_recv)
+    import time
+
+    time.sleep(0.05)
+    assert not s_recv.query()  # still waiting on the device
+    flag[0] = 1  # host store, observed by ld.acquire.sys over PCIe
     s_recv.synchronize()
     assert torch.equal(src, dst)
+    assert ctrl[18].item() == 0
 
 
 def test_unpack_timeout_sets_status(ctrl):
