@@ -18,6 +18,7 @@ import logging
 import os
 import signal
 import threading
+import time
 
 from ._private.message_queue import MessageQueueManager
 from .exceptions import FedRemoteError, FedTaskError
@@ -44,6 +45,9 @@ class CleanupManager:
         self._pending_err = 0
         self._pending_cv = threading.Condition()
         self._draining = False  # a stop() is waiting: completions must notify
+        # sends whose completion callback has not run yet (id -> ref); lets stop() close the
+        # window between "the future resolved" and "its failure was queued"
+        self._watch = {}
 
     def start(self, exit_on_sending_failure=False, expose_error_trace=False):
         self._exit_on_sending_failure = exit_on_sending_failure
@@ -62,6 +66,11 @@ class CleanupManager:
         peers waiting for data that will never come.
         """
         self._draining = True
+        # A send future may have resolved an instant ago on another thread while its
+        # completion callback (which queues a failure) is still running: let it settle.
+        deadline = time.monotonic() + 2.0
+        while time.monotonic() < deadline and any(r.done() for r in list(self._watch.values())):
+            time.sleep(0.0005)
         if wait_for_sending:
             with self._pending_cv:
                 self._pending_cv.wait_for(lambda: self._pending <= 0 or not self._sending_data_q.is_started(),
@@ -86,8 +95,11 @@ class CleanupManager:
             if is_error:
                 self._pending_err += 1
         q = self._sending_error_q if is_error else self._sending_data_q
+        key = id(pack)
+        self._watch[key] = obj_ref
 
         def on_done(r):
+            self._watch.pop(key, None)
             ok = False
             try:
                 ok = r.exception() is None and bool(r.result())

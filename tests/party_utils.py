@@ -32,9 +32,20 @@ def make_addresses(parties):
     return {p: f"127.0.0.1:{port}" for p, port in zip(parties, ports)}
 
 
+FAST_GRPC_RETRY = {
+    "maxAttempts": 5,
+    "initialBackoff": "0.1s",
+    "maxBackoff": "1s",
+    "backoffMultiplier": 2,
+    "retryableStatusCodes": ["UNAVAILABLE"],
+}
+
+
 def comm_config(transport="native", **extra):
     cfg = dict(FAST_RETRY)
     cfg["transport"] = transport
+    if transport in ("grpc", "auto"):
+        cfg["grpc_retry_policy"] = dict(FAST_GRPC_RETRY)  # default backs off 5 s .. 30 s
     cfg.update(extra)
     return cfg
 

@@ -1,6 +1,7 @@
 """Fault injection (mirrors fed/tests/test_cross_silo_error.py,
 test_exit_on_failure_sending.py, serializations_tests/test_unpickle_with_whitelist.py)."""
 import multiprocessing
+import os
 
 import pytest
 
@@ -13,11 +14,15 @@ class MyError(Exception):
     pass
 
 
-def _init(party, addresses, transport="native", handler=None, **comm):
+def _init(party, addresses, transport="native", handler=None, barrier=False, **comm):
     import rayfed_b200 as fed
 
-    fed.init(addresses=addresses, party=party, logging_level="error",
-             config={"cross_silo_comm": comm_config(transport, **comm)}, sending_failure_handler=handler)
+    fed.init(addresses=addresses, party=party, logging_level=os.environ.get("FED_TEST_LOG", "error"),
+             config={"cross_silo_comm": comm_config(transport, **comm),
+                     # both parties are up before anything can fail: the tests are about error
+                     # propagation, not about start-up races
+                     "barrier_on_initializing": barrier},
+             sending_failure_handler=handler)
     return fed
 
 
@@ -114,8 +119,8 @@ def _peer_never_started(party, addresses, q):
     def handler(error):
         q.put("failure handler")
 
-    fed = _init(party, addresses, handler=handler, exit_on_sending_failure=True, retry_max_attempts=2,
-                retry_initial_backoff_s=0.1, retry_max_backoff_s=0.1)
+    fed = _init(party, addresses, handler=handler, barrier=False, exit_on_sending_failure=True,
+                retry_max_attempts=2, retry_initial_backoff_s=0.1, retry_max_backoff_s=0.1)
 
     @fed.remote
     def f():
