@@ -436,16 +436,22 @@ def get(fed_objects: Union[FedObject, List[FedObject], Any]) -> Any:
             ref = fed_object.get_ref()
             assert ref is not None
             refs.append(ref)
-            for party_name in addresses:
-                if party_name == current_party or fed_object._was_sending_or_sent_to_party(party_name):
-                    continue
+            todo = [p for p in addresses
+                    if p != current_party and not fed_object._was_sending_or_sent_to_party(p)]
+            for party_name in todo:
                 fed_object._mark_is_sending_to_party(party_name)
-                send(
-                    dest_party=party_name,
-                    data=ref,
-                    upstream_seq_id=fed_object.get_fed_task_id(),
-                    downstream_seq_id=fake_fed_task_id,
-                )
+            if len(todo) == len(addresses) - 1 and len(todo) >= 1:
+                # nobody has it yet: one broadcast (a single multicast push where the
+                # transport supports it, N-1 unicast sends otherwise)
+                barriers.send_broadcast(todo, ref, fed_object.get_fed_task_id(), fake_fed_task_id)
+            else:
+                for party_name in todo:
+                    send(
+                        dest_party=party_name,
+                        data=ref,
+                        upstream_seq_id=fed_object.get_fed_task_id(),
+                        downstream_seq_id=fake_fed_task_id,
+                    )
         else:
             ref = fed_object.get_ref()
             if ref is None:

@@ -310,6 +310,24 @@ PYBIND11_MODULE(_fedcuda, m) {
       py::arg("flag_value"), py::arg("done_counter"), py::arg("mode"), py::arg("blocks"), py::arg("use_bulk"),
       py::arg("stream"));
   m.def(
+      "push_mc",
+      [](uint64_t src, uint64_t mc_dst, uint64_t nbytes, const std::vector<uint64_t>& flag_ptrs, uint32_t flag_value,
+         uint64_t done_counter, int blocks, uint64_t stream) {
+        if (nbytes % 16) throw std::runtime_error("push_mc needs a multiple of 16 bytes");
+        PushArgs a{};
+        a.src = P<const void>(src);
+        a.dst = P<void>(mc_dst);
+        a.n = nbytes;
+        a.flag_value = flag_value;
+        a.done_counter = P<uint32_t>(done_counter);
+        PeerPtrs flags{};
+        fill_peers(flags, flag_ptrs);
+        check(fedk_launch_push_mc(&a, &flags, (int)flag_ptrs.size(), blocks, (cudaStream_t)(uintptr_t)stream),
+              "fed_push_mc launch");
+      },
+      py::arg("src"), py::arg("mc_dst"), py::arg("nbytes"), py::arg("flag_ptrs"), py::arg("flag_value"),
+      py::arg("done_counter"), py::arg("blocks"), py::arg("stream"));
+  m.def(
       "unpack",
       [](uint64_t src, uint64_t dst, uint64_t scales, uint64_t n, float scale, uint64_t flag, uint32_t flag_value,
          uint64_t done_counter, uint64_t credit, uint64_t credit_value, uint64_t status, long long timeout_ns,

@@ -334,7 +334,54 @@ __global__ void __launch_bounds__(128) fed_push_bulk_kernel(PushArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// K1b fed_push_mc: one multimem.st stream through the NVSwitch reaches every party
+// bound to the multicast object (fed.get's owner -> all broadcast, weight
+// redistribution).  Byte copy only; the release flag is then stored to each peer.
+__global__ void __launch_bounds__(512) fed_push_mc_kernel(const __grid_constant__ PushArgs a,
+                                                          const __grid_constant__ PeerPtrs flags, int n_flags) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t nvec = a.n >> 4;  // host guarantees n % 16 == 0
+  const uint4* s = reinterpret_cast<const uint4*>(a.src);
+  char* d = reinterpret_cast<char*>(a.dst);  // multicast alias of the broadcast arena slot
+  size_t i = tid;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    uint4 v0 = ld_stream_v4(s + i), v1 = ld_stream_v4(s + i + stride);
+    uint4 v2 = ld_stream_v4(s + i + 2 * stride), v3 = ld_stream_v4(s + i + 3 * stride);
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(d + (i << 4)), "r"(v0.x),
+                 "r"(v0.y), "r"(v0.z), "r"(v0.w) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(d + ((i + stride) << 4)),
+                 "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(d + ((i + 2 * stride) << 4)),
+                 "r"(v2.x), "r"(v2.y), "r"(v2.z), "r"(v2.w) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(d + ((i + 3 * stride) << 4)),
+                 "r"(v3.x), "r"(v3.y), "r"(v3.z), "r"(v3.w) : "memory");
+  }
+  for (; i < nvec; i += stride) {
+    uint4 v = ld_stream_v4(s + i);
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(d + (i << 4)), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+  fence_acq_rel_sys();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned prev = atomicAdd(a.done_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *a.done_counter = 0;
+      fence_acq_rel_sys();
+      for (int p = 0; p < n_flags; ++p) st_release_sys_u32(reinterpret_cast<uint32_t*>(flags.p[p]), a.flag_value);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 extern "C" {
+
+cudaError_t fedk_launch_push_mc(const PushArgs* a, const PeerPtrs* flags, int n_flags, int blocks,
+                                cudaStream_t stream) {
+  fed_push_mc_kernel<<<blocks, 512, 0, stream>>>(*a, *flags, n_flags);
+  return cudaGetLastError();
+}
 
 cudaError_t fedk_launch_push(const PushArgs* a, int mode, int blocks, int use_bulk, cudaStream_t stream) {
   if (use_bulk && mode == kCopy) {

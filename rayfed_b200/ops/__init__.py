@@ -36,6 +36,7 @@ from .kernels import (  # noqa: F401
     local_sgd,
     lora_merge,
     push,
+    push_mc,
     sm_count,
     unpack,
 )

@@ -96,6 +96,17 @@ def push(src_ptr: int, dst_ptr: int, n: int, *, mode: int = MODE_COPY, scale: fl
     launch_counter.add("fed_push_bulk" if use_bulk else "fed_push")
 
 
+def push_mc(src_ptr: int, mc_dst_ptr: int, nbytes: int, *, flag_ptrs: Sequence[int], flag_value: int,
+            done_counter_ptr: int, stream=None, device_index: int = 0, blocks: Optional[int] = None) -> None:
+    """K1b: multicast push — one ``multimem.st`` stream lands in every party's copy of the
+    destination; then the release flag is stored to each listed peer."""
+    if blocks is None:
+        blocks = _blocks_for(nbytes, device_index)
+    cuda_ext().push_mc(src_ptr, mc_dst_ptr, nbytes, list(flag_ptrs), flag_value, done_counter_ptr, blocks,
+                       _stream_handle(stream))
+    launch_counter.add("fed_push_mc")
+
+
 _BULK_DEFAULT = None
 
 

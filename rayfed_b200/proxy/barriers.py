@@ -485,6 +485,61 @@ def send(dest_party, data, upstream_seq_id, downstream_seq_id, is_error=False, c
     return result
 
 
+def send_broadcast(dest_parties, data, upstream_seq_id, downstream_seq_id):
+    """Owner -> all-other-parties push of one value (what ``fed.get`` does).  When the
+    transport can multicast (NVLink channel with an NVLS mapping) every big CUDA tensor is
+    written ONCE and the switch replicates it (K1b); otherwise this is N-1 ``send``s, like
+    the reference (fed/api.py:564-579).  Returns {dest: outcome Ref}."""
+    host: ProxyHost = _HOSTS["sender"] or get_runtime().get_named(sender_proxy_actor_name())
+    proxy = host.proxy
+    can = getattr(proxy, "can_broadcast", None)
+    dest_parties = list(dest_parties)
+    if not dest_parties:
+        return {}
+    if can is None or not can() or len(dest_parties) != len(proxy._addresses) - 1:
+        return {d: send(d, data, upstream_seq_id, downstream_seq_id) for d in dest_parties}
+
+    results = {d: native().Ref() for d in dest_parties}
+
+    def issue(value):
+        try:
+            for _ in dest_parties:
+                host._send_seen = next(host._send_ops)
+            acks = proxy.broadcast(dest_parties, value, upstream_seq_id, downstream_seq_id)
+        except BaseException as e:  # noqa: BLE001
+            for r in results.values():
+                r.set_error(e)
+            return
+        for d, ack in acks.items():
+            ack.add_done_callback(lambda a, r=results[d]: _copy_outcome(a, r))
+
+    if is_ref(data):
+        if data.done():
+            e = data.exception()
+            if e is not None:
+                for r in results.values():
+                    r.set_error(e)
+            else:
+                issue(data.result())
+        else:
+            def on_ready(r):
+                e = r.exception()
+                if e is not None:
+                    for res in results.values():
+                        res.set_error(e)
+                else:
+                    issue(r.result())
+
+            data.add_done_callback(on_ready)
+    else:
+        issue(data)
+    ctx = get_global_context()
+    if ctx is not None:
+        for d, r in results.items():
+            ctx.get_cleanup_manager().push_to_sending(r, d, upstream_seq_id, downstream_seq_id, False)
+    return results
+
+
 def recv(party: str, src_party: str, upstream_seq_id, curr_seq_id):
     """`Ref` that resolves when the message keyed (upstream, curr) has arrived."""
     assert party, "Party can not be None."

@@ -5,8 +5,12 @@ Layout of the (symmetric) channel buffer, identical in every party::
     [0      , 256 )  flags[s]   u32  written by *source* s: #messages from s completed
     [256    , 512 )  credits[d] u64  written by *dest* d: bytes of my sends d has consumed
     [512    , 1024)  status u32 | push_done u32 | unpack_done u32      (local use)
+    [1024   , 1280)  bflags[s]   u32  like flags, for the broadcast ring of source s
+    [1280   , 1536)  bcredits[d] u64  like credits, for my broadcast ring
     [64 KiB , 128K)  signal pad (K5 barrier / K2 aggregate per-CTA flags)
-    [128 KiB, ... )  arena: one region of R bytes per source party
+    [128 KiB, ... )  arena: one unicast region of R bytes per source party, then one
+                     broadcast region of R bytes per source party (K1b: written once with
+                     multimem.st, lands at the same offset in every party)
 
 Send p→d: the sender owns the allocation of ``region[p]`` in d's arena (a byte
 ring with monotonically increasing ``head``), so no negotiation is needed — the
@@ -35,6 +39,8 @@ OFF_CREDITS = 256
 OFF_STATUS = 512
 OFF_PUSH_DONE = 516
 OFF_UNPACK_DONE = 520
+OFF_BFLAGS = 1024  # bflags[s] u32: #broadcast messages from source s completed
+OFF_BCREDITS = 1280  # bcredits[d] u64 (in the *sender's* buffer): bytes of my broadcasts d has consumed
 OFF_SIGNAL = 64 * 1024
 OFF_ARENA = 128 * 1024
 SIGNAL_BYTES = 64 * 1024
@@ -45,15 +51,20 @@ _WIRE = {None: None, "none": None, "bf16": "bf16", "fp8_e4m3": "fp8_e4m3", "fp8"
 
 class DeviceChannel:
     def __init__(self, group: PartyGroup, heap: Optional[SymmetricHeap] = None, region_bytes: int = 256 << 20,
-                 wire_dtype: Optional[str] = None, timeout_s: float = 120.0):
+                 wire_dtype: Optional[str] = None, timeout_s: float = 120.0, multicast: bool = True):
         import torch
 
         self.group = group
         self.heap = heap or SymmetricHeap(group)
         self.region_bytes = int(region_bytes) // ALIGN * ALIGN
         self.wire_dtype = _WIRE[wire_dtype]
-        total = OFF_ARENA + group.size * self.region_bytes
-        self.buf = self.heap.alloc("fed-channel", total)
+        self._barena_off = OFF_ARENA + group.size * self.region_bytes
+        total = OFF_ARENA + 2 * group.size * self.region_bytes
+        # VMM + NVLS multicast when the box supports it (falls back to cudaIpc collectively)
+        self.buf = self.heap.alloc("fed-channel", total, multicast=multicast and group.size > 1)
+        self._bhead = 0
+        self._bcredit_seen = [0] * group.size
+        self._bseq = 0
         self.device_index = group.device_index
         self._dev = f"cuda:{self.device_index}"
         self._send_lock = threading.Lock()
@@ -71,7 +82,7 @@ class DeviceChannel:
         # ~1.9 GHz SM clock: cycles until a device-side wait declares a timeout
         self._timeout_ns = int(timeout_s * 1e9)  # device waits use %globaltimer (ns)
         self.stats = {"tensors_sent": 0, "bytes_sent": 0, "tensors_received": 0, "bytes_received": 0,
-                      "credit_stalls": 0}
+                      "credit_stalls": 0, "bcast_tensors_sent": 0, "bcast_bytes_sent": 0}
 
     # -- addresses ---------------------------------------------------------------
     def _peer(self, party_rank: int, off: int) -> int:
@@ -173,6 +184,76 @@ class DeviceChannel:
             "shape": tuple(tensor.shape), "pay": payload_bytes, "pad": pay_pad, "scales": scales_bytes,
         }
 
+    # -- broadcast (K1b) -------------------------------------------------------------
+    @property
+    def can_multicast(self) -> bool:
+        return bool(self.buf.mc_ptr) and self.group.size > 1
+
+    def _alloc_bcast(self, nbytes: int):
+        need = (nbytes + ALIGN - 1) // ALIGN * ALIGN
+        if need > self.region_bytes:
+            raise ValueError("tensor exceeds the broadcast arena region")
+        head = self._bhead
+        off = head % self.region_bytes
+        if off + need > self.region_bytes:
+            head += self.region_bytes - off
+            off = 0
+        end = head + need
+        deadline = time.time() + 120
+        peers = [d for d in range(self.group.size) if d != self.group.rank]
+        while end - min(self._bcredit_seen[d] for d in peers) > self.region_bytes:
+            for d in peers:  # every receiver must have consumed before the ring wraps
+                self._bcredit_seen[d] = K.cuda_ext().read_u64(self._local(OFF_BCREDITS + 8 * d))
+            if end - min(self._bcredit_seen[d] for d in peers) <= self.region_bytes:
+                break
+            self.stats["credit_stalls"] += 1
+            if time.time() > deadline:
+                raise TimeoutError("broadcast arena full: a receiver is not consuming")
+            time.sleep(0.0002)
+        self._bhead = end
+        return off, end
+
+    def can_bcast_tensor(self, tensor) -> bool:
+        nbytes = tensor.numel() * tensor.element_size()
+        return (self.can_multicast and self.wire_dtype is None and tensor.is_contiguous() and nbytes > 0
+                and nbytes % 16 == 0 and tensor.data_ptr() % 16 == 0 and nbytes <= self.region_bytes)
+
+    def push_tensor_bcast(self, tensor, ready_event=None) -> Optional[dict]:
+        """K1b: ONE multimem.st kernel puts the tensor into every party's broadcast region.
+        Returns the descriptor, or None when this tensor has to go unicast."""
+        import torch
+
+        if not self.can_multicast or self.wire_dtype is not None:
+            return None
+        with torch.cuda.device(self.device_index):
+            t = tensor if tensor.is_contiguous() else tensor.contiguous()
+            nbytes = t.numel() * t.element_size()
+            if nbytes % 16 or t.data_ptr() % 16 or nbytes == 0:
+                return None
+            with self._send_lock:
+                off, end_head = self._alloc_bcast(nbytes)
+                self._bseq += 1
+                seq = self._bseq
+                slot = self._barena_off + self.group.rank * self.region_bytes + off
+                stream = self._push_stream
+                if ready_event is not None:
+                    stream.wait_event(ready_event)
+                else:
+                    stream.wait_stream(torch.cuda.current_stream(self._dev))
+                flags = [self._peer(d, OFF_BFLAGS + 4 * self.group.rank) for d in range(self.group.size)
+                         if d != self.group.rank]
+                K.push_mc(t.data_ptr(), self.buf.mc_ptr + slot, nbytes, flag_ptrs=flags, flag_value=seq,
+                          done_counter_ptr=self._local(OFF_PUSH_DONE), stream=stream,
+                          device_index=self.device_index)
+                t.record_stream(stream)
+            self.stats["bcast_tensors_sent"] += 1
+            self.stats["bcast_bytes_sent"] += nbytes
+            return {
+                "off": off, "seq": seq, "end": end_head, "mode": K.MODE_COPY, "numel": t.numel(),
+                "dtype": str(t.dtype)[6:], "shape": tuple(tensor.shape), "pay": nbytes,
+                "pad": (nbytes + ALIGN - 1) // ALIGN * ALIGN, "scales": 0, "bcast": True,
+            }
+
     def record_push_event(self):
         """Event after everything launched so far on the push stream."""
         import torch
@@ -195,8 +276,11 @@ class DeviceChannel:
 
         dtype = getattr(torch, desc["dtype"])
         out = torch.empty(desc["shape"], dtype=dtype, device=self._dev)
-        region = OFF_ARENA + src_rank * self.region_bytes
+        bcast = bool(desc.get("bcast"))
+        region = (self._barena_off if bcast else OFF_ARENA) + src_rank * self.region_bytes
         src = self._local(region + desc["off"])
+        flag_off = (OFF_BFLAGS if bcast else OFF_FLAGS) + 4 * src_rank
+        credit_off = (OFF_BCREDITS if bcast else OFF_CREDITS) + 8 * self.group.rank
         mode = desc["mode"]
         if mode == K.MODE_F32_TO_BF16:
             un_mode, n_arg, scales = K.MODE_BF16_TO_F32, desc["numel"], 0
@@ -209,9 +293,9 @@ class DeviceChannel:
             # the fresh tensor's memory may still be in use by earlier work on the caller's stream
             stream.wait_stream(torch.cuda.current_stream(self._dev))
             K.unpack(src, out.data_ptr(), n_arg, mode=un_mode, scales_ptr=scales,
-                     flag_ptr=self._local(OFF_FLAGS + 4 * src_rank), flag_value=desc["seq"],
+                     flag_ptr=self._local(flag_off), flag_value=desc["seq"],
                      done_counter_ptr=self._local(OFF_UNPACK_DONE),
-                     credit_ptr=self._peer(src_rank, OFF_CREDITS + 8 * self.group.rank), credit_value=desc["end"],
+                     credit_ptr=self._peer(src_rank, credit_off), credit_value=desc["end"],
                      status_ptr=self._status_host.data_ptr(), timeout_ns=self._timeout_ns, stream=stream,
                      device_index=self.device_index)
             ev = torch.cuda.Event()

@@ -33,6 +33,11 @@ from ..native.socket_proxy import NativeReceiverProxy, NativeSenderProxy, _ack_d
 
 logger = logging.getLogger(__name__)
 
+import os as _os
+
+# K1b multicast push for owner -> everyone broadcasts (fed.get).  On by default where the
+# channel got an NVLS mapping; RAYFED_B200_MC_PUSH=0 forces per-destination unicast pushes.
+_MC_PUSH_ENABLED = _os.environ.get("RAYFED_B200_MC_PUSH", "1") != "0"
 _DEVQ = "__devq__"
 _TAG = "fedcuda"
 _SMALL = "fedcuda-small"
@@ -171,6 +176,60 @@ class NvlinkSenderProxy(NativeSenderProxy):
         frame = pickle.dumps((_TAG, k, buf.getvalue()), protocol=5)
         return self._transport.send(dest_party, str(upstream_seq_id), str(downstream_seq_id), frame, False,
                                     _ack_decoder)
+
+
+    # -- K1b: owner -> all-parties broadcast (fed.get, weight redistribution) -------------------
+    def can_broadcast(self) -> bool:
+        ch = current_channel()
+        return ch is not None and ch.can_multicast and _MC_PUSH_ENABLED
+
+    def broadcast(self, dest_parties, data, upstream_seq_id, downstream_seq_id):
+        """Send the same object to every party in ``dest_parties`` (all the others): each big
+        CUDA tensor is pushed ONCE with the multicast kernel; the skeleton + descriptors go
+        to each destination.  Returns {dest: ack Ref}."""
+        ready_event = None
+        if type(data) is _Produced:
+            ready_event, data = data.event, data.value
+        channel = current_channel()
+        tensors = []
+
+        def sink(t):
+            tensors.append(t)
+            return len(tensors) - 1
+
+        buf = io.BytesIO()
+        pickler = _DevicePickler(buf, sink, self._min_bytes,
+                                 ready_event.synchronize if ready_event is not None else None)
+        pickler.dump(data)
+        acks = {}
+        if not tensors:
+            frame = pickle.dumps((_TAG, 0, buf.getvalue()), protocol=5) if pickler.small_tensors else buf.getvalue()
+            for d in dest_parties:
+                acks[d] = self._transport.send(d, str(upstream_seq_id), str(downstream_seq_id), frame, False,
+                                               _ack_decoder)
+            return acks
+        with self._order_lock:
+            descs = None
+            if all(channel.can_bcast_tensor(t) for t in tensors):  # all or nothing: no ring leaks
+                descs = [channel.push_tensor_bcast(t, ready_event) for t in tensors]
+                if any(d is None for d in descs):
+                    raise RuntimeError("multicast push refused a tensor it had accepted")
+            if descs is not None:
+                ev = channel.record_push_event()
+                blob = pickle.dumps(descs)
+                ks = {}
+                for d in dest_parties:
+                    ks[d] = self._k.get(d, 0) + 1
+                    self._k[d] = ks[d]
+                    self._done_q.put((ev, d, ks[d], blob))
+        if descs is None:
+            data_again = _Produced(data, ready_event) if ready_event is not None else data
+            return {d: self.send(d, data_again, upstream_seq_id, downstream_seq_id) for d in dest_parties}
+        for d in dest_parties:
+            frame = pickle.dumps((_TAG, ks[d], buf.getvalue()), protocol=5)
+            acks[d] = self._transport.send(d, str(upstream_seq_id), str(downstream_seq_id), frame, False,
+                                           _ack_decoder)
+        return acks
 
 
 class NvlinkReceiverProxy(NativeReceiverProxy):

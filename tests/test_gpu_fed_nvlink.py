@@ -148,6 +148,47 @@ def test_fedavg_two_parties_fused_aggregate(kind):
     run_parties(_fedavg, ["alice", "bob"], args=(addresses, kind), timeout=150)
 
 
+def _bcast_loop(party, addresses):
+    """fed.get broadcasts: with an NVLS mapping each value is pushed once with the
+    multicast kernel (K1b); interleaved with unicast pushes to check ring/descriptor order."""
+    import rayfed_b200 as fed
+    from rayfed_b200.proxy.nvlink import nvlink_proxy
+
+    fed, dev = _init(party, addresses)
+    parties = list(addresses)
+
+    @fed.remote
+    def make(n, seed):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        return torch.randn(n, device="cuda", generator=g)
+
+    @fed.remote
+    def total(x):
+        return x.sum()
+
+    sizes = [1 << 12, 300_000, 1 << 20, 4 * 12345, 1 << 16, 2_000_000]
+    for i, n in enumerate(sizes):
+        owner = parties[i % len(parties)]
+        other = parties[(i + 1) % len(parties)]
+        o = make.party(owner).remote(n, 50 + i)
+        if i % 3 == 2:  # sometimes a unicast push of another object goes first
+            fed.get(total.party(other).remote(make.party(owner).remote(n // 2, 90 + i)))
+        got = fed.get(o)  # owner -> everyone
+        g = torch.Generator(device="cuda").manual_seed(50 + i)
+        exp = torch.randn(n, device="cuda", generator=g)
+        assert torch.equal(got.to(exp.device), exp), (i, n)
+    ch = nvlink_proxy.current_channel()
+    assert ch.check_status() == 0
+    if ch.can_multicast:
+        assert ch.stats["bcast_tensors_sent"] >= len(sizes) // len(parties)
+    fed.shutdown()
+
+
+def test_fed_get_broadcast_uses_multicast_push_when_available():
+    addresses = make_addresses(["alice", "bob"])
+    run_parties(_bcast_loop, ["alice", "bob"], args=(addresses,), timeout=150)
+
+
 def _fed_lora(party, addresses, base_dtype):
     import rayfed_b200 as fed
     from rayfed_b200.fl import FedLoRAAdam, FedLoRAExactMerge, device_context
