@@ -207,6 +207,7 @@ class SymmetricHeap:
                 gran = self._ext.mc_granularity(nbytes, g.size)
                 size = (nbytes + gran - 1) // gran * gran
             ptr, fd, mapped, mem_handle = self._ext.vmm_alloc(size, g.device_index)
+            self._ext.device_synchronize()  # the zero-fill must land before any peer can write
             ok = True
         except Exception as e:  # noqa: BLE001
             logger.warning(f"vmm_alloc failed: {e}")
