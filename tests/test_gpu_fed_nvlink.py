@@ -70,7 +70,8 @@ def _tensor_dag(party, addresses, wire):
     else:
         assert torch.allclose(got, exp, rtol=0.02, atol=0.05)
     ch = nvlink_proxy.current_channel()
-    assert ch is not None and ch.stats["tensors_sent"] >= 1 and ch.check_status() == 0
+    sent = ch.stats["tensors_sent"] + ch.stats["bcast_tensors_sent"]  # unicast (K1) + multicast (K1b)
+    assert ch is not None and sent >= 1 and ch.check_status() == 0, ch.stats
     if party == "bob":
         assert ch.stats["tensors_received"] >= 1  # the fed.get broadcast arrived on the device path
     fed.shutdown()
