@@ -483,7 +483,8 @@ PYBIND11_MODULE(_fedcuda, m) {
       "lora_merge",
       [](const std::vector<uint64_t>& b, const std::vector<uint64_t>& at, uint64_t w_base, uint64_t w_base_scales,
          uint64_t out, uint64_t out_scales, uint64_t m_rows, uint64_t n_cols, int r, float scale,
-         const std::vector<float>& weights, bool base_fp8, bool out_fp8, uint64_t stream, bool use_tma) {
+         const std::vector<float>& weights, bool base_fp8, bool out_fp8, uint64_t stream, bool use_tma,
+         uint64_t bcat, uint64_t atcat, int kpad) {
         LoraMergeArgs a{};
         fill_peers(a.b, b);
         fill_peers(a.at, at);
@@ -499,7 +500,27 @@ PYBIND11_MODULE(_fedcuda, m) {
         for (int i = 0; i < kMaxParties; ++i) a.w[i] = i < (int)weights.size() ? weights[i] : 1.f;
         a.base_fp8 = base_fp8;
         a.out_fp8 = out_fp8;
-        if (use_tma && !base_fp8 && !out_fp8 && n_cols % 64 == 0 && (out % 16 == 0) && (w_base % 16 == 0)) {
+        if (bcat && atcat) {
+          // staged persistent path: gather once, then TMA -> tcgen05 -> TMA
+          if (base_fp8 || out_fp8 || n_cols % 8 || out % 16 || w_base % 16 || bcat % 16 || atcat % 16)
+            throw std::runtime_error("lora_merge(staged): needs bf16 base/out, n % 8 == 0 and aligned buffers");
+          struct alignas(64) Maps {
+            CUtensorMap w;
+            CUtensorMap out;
+            CUtensorMap bcat;
+            CUtensorMap atcat;
+          } maps;
+          maps.out = make_bf16_tile_map(out, m_rows, n_cols);
+          maps.w = w_base ? make_bf16_tile_map(w_base, m_rows, n_cols) : maps.out;
+          maps.bcat = make_bf16_tile_map(bcat, m_rows, (uint64_t)kpad);
+          maps.atcat = make_bf16_tile_map(atcat, n_cols, (uint64_t)kpad);
+          int dev = 0, sms = 0;
+          check(cudaGetDevice(&dev), "cudaGetDevice");
+          check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "sm count");
+          check(fedk_launch_lora_merge_staged(&a, &maps, P<void>(bcat), P<void>(atcat), kpad, sms,
+                                              (cudaStream_t)(uintptr_t)stream),
+                "fed_lora_merge_staged launch");
+        } else if (use_tma && !base_fp8 && !out_fp8 && n_cols % 64 == 0 && (out % 16 == 0) && (w_base % 16 == 0)) {
           struct alignas(64) Maps {
             CUtensorMap w;
             CUtensorMap out;
@@ -513,7 +534,8 @@ PYBIND11_MODULE(_fedcuda, m) {
       },
       py::arg("b"), py::arg("at"), py::arg("w_base"), py::arg("w_base_scales"), py::arg("out"),
       py::arg("out_scales"), py::arg("m"), py::arg("n"), py::arg("r"), py::arg("scale"), py::arg("weights"),
-      py::arg("base_fp8"), py::arg("out_fp8"), py::arg("stream"), py::arg("use_tma") = true);
+      py::arg("base_fp8"), py::arg("out_fp8"), py::arg("stream"), py::arg("use_tma") = true, py::arg("bcat") = 0,
+      py::arg("atcat") = 0, py::arg("kpad") = 0);
 
   m.def(
       "local_sgd",

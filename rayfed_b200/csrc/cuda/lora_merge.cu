@@ -426,6 +426,268 @@ fed_lora_merge_tma_kernel(const __grid_constant__ LoraMergeArgs a, const __grid_
   }
 }
 
+// ---------------------------------------------------------------------------
+// Staged, persistent, warp-specialised variant (default for bf16 base/out, K <= 128).
+//
+// The direct kernels above pull every operand tile from the peers once per *output
+// tile*: a 4096 x 4096 merge moves 1024 x 64 KB = 64 MB of adapter data through the
+// LSUs (56 MB of it over NVLink at 8 parties) to produce 32 MB of output.  Here the
+// all-gather is hoisted into a tiny first phase — every peer slice crosses NVLink
+// exactly once (2 MB) into K-major concatenated operands [M, Kpad] / [N, Kpad] that
+// stay L2-resident — and the GEMM becomes a persistent TMA -> tcgen05 -> TMA pipeline:
+//
+//   warp 0      producer : TMA loads {W tile, A tile, B tile} into a 2-stage smem ring
+//   warp 1      MMA      : tcgen05.mma into one of two 128-column TMEM accumulators
+//   warps 2..9  epilogue : tcgen05.ld -> W += scale * dW in the swizzled smem tile
+//                          -> TMA store; the next tile's loads and MMAs run underneath
+//
+// All hand-offs are mbarriers: full[s] (TMA bytes landed), tmem_full[s] (tcgen05.commit),
+// tmem_empty[s] (8 epilogue warps drained the accumulator), empty[s] (TMA store finished
+// reading the stage).
+constexpr int kStgStages = 2;
+constexpr int kStgThreads = 320;        // 10 warps
+constexpr int kStgEpiThreads = 256;     // warps 2..9
+constexpr int kAtomBytes = kLoraBM * 128;  // one 64-column SWIZZLE_128B atom of a 128-row tile
+
+struct LoraStagedMaps {
+  CUtensorMap w;
+  CUtensorMap out;
+  CUtensorMap bcat;   // [M, Kpad]
+  CUtensorMap atcat;  // [N, Kpad]
+};
+
+__global__ void __launch_bounds__(256) fed_lora_gather_kernel(const __grid_constant__ LoraMergeArgs a,
+                                                              __nv_bfloat16* __restrict__ bcat,
+                                                              __nv_bfloat16* __restrict__ atcat, int kpad) {
+  const int cpp = a.r >> 3;  // 16 B chunks per party row
+  const size_t nb = (size_t)a.n_parties * a.m * cpp;
+  const size_t na = (size_t)a.n_parties * a.n * cpp;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nb + na; idx += stride) {
+    const bool is_b = idx < nb;
+    const size_t j = is_b ? idx : idx - nb;
+    const size_t rows = is_b ? a.m : a.n;
+    // (party, row, chunk): consecutive threads read consecutive bytes of ONE peer
+    const int i = (int)(j / (rows * cpp));
+    const size_t rem = j - (size_t)i * rows * cpp;
+    const size_t row = rem / cpp;
+    const int c = (int)(rem - row * cpp);
+    const char* src = reinterpret_cast<const char*>(is_b ? a.b.p[i] : a.at.p[i]);
+    uint4 v = ld_v4(src + (row * (size_t)a.r + (size_t)c * 8) * 2);
+    if (is_b && a.w[i] != 1.0f) {
+      const float w = a.w[i];
+      v.x = pack_bf16x2(bf16_lo(v.x) * w, bf16_hi(v.x) * w);
+      v.y = pack_bf16x2(bf16_lo(v.y) * w, bf16_hi(v.y) * w);
+      v.z = pack_bf16x2(bf16_lo(v.z) * w, bf16_hi(v.z) * w);
+      v.w = pack_bf16x2(bf16_lo(v.w) * w, bf16_hi(v.w) * w);
+    }
+    __nv_bfloat16* dst = (is_b ? bcat : atcat) + row * (size_t)kpad + (size_t)i * a.r + (size_t)c * 8;
+    *reinterpret_cast<uint4*>(dst) = v;  // default caching: the GEMM phase reads this from L2
+  }
+}
+
+__device__ __forceinline__ void lm_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lm_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void lm_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lm_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void lm_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lm_smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kStgThreads, 1)
+fed_lora_gemm_kernel(const __grid_constant__ LoraMergeArgs a, const __grid_constant__ LoraStagedMaps maps,
+                     int atoms, int tiles_n, int n_tiles) {
+  extern __shared__ unsigned char lm_smem[];
+  __shared__ __align__(8) uint64_t full_bar[kStgStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStgStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[kStgStages];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[kStgStages];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t raw = lm_smem_u32(lm_smem);
+  unsigned char* ring = lm_smem + (((raw + 1023u) & ~1023u) - raw);
+  const int stage_bytes = (2 + 2 * atoms) * kAtomBytes;  // [W: 2 atoms][A: atoms][B: atoms]
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool has_base = a.w_base != nullptr;
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStgStages; ++s) {
+      lm_mbar_init(&full_bar[s], 1);
+      lm_mbar_init(&empty_bar[s], 1);
+      lm_mbar_init(&tmem_full_bar[s], 1);
+      lm_mbar_init(&tmem_empty_bar[s], kStgEpiThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     lm_smem_u32(&tmem_base_slot)),
+                 "n"(kStgStages * kLoraBN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ---------------- producer: TMA loads ----------------------------------------------------
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)((has_base ? 2 : 0) + 2 * atoms) * kAtomBytes;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int t = (int)blockIdx.x + it * (int)gridDim.x;
+        const int m0 = (t / tiles_n) * kLoraBM, n0 = (t % tiles_n) * kLoraBN;
+        const int s = it & 1;
+        const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+        lm_mbar_wait(&empty_bar[s], ph ^ 1u);  // first pass over the ring falls through
+        unsigned char* st = ring + (size_t)s * stage_bytes;
+        lm_mbar_expect_tx(&full_bar[s], tx);
+        if (has_base) {
+          lm_tma_load_2d(st, &maps.w, n0, m0, &full_bar[s]);
+          lm_tma_load_2d(st + kAtomBytes, &maps.w, n0 + 64, m0, &full_bar[s]);
+        }
+        unsigned char* sA = st + 2 * kAtomBytes;
+        unsigned char* sB = sA + (size_t)atoms * kAtomBytes;
+        for (int k = 0; k < atoms; ++k) {
+          lm_tma_load_2d(sA + (size_t)k * kAtomBytes, &maps.bcat, k * 64, m0, &full_bar[s]);
+          lm_tma_load_2d(sB + (size_t)k * kAtomBytes, &maps.atcat, k * 64, n0, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer -----------------------------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = lm_instr_desc();
+      const int ksteps = (a.n_parties * a.r) >> 4;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+        lm_mbar_wait(&full_bar[s], ph);
+        lm_mbar_wait(&tmem_empty_bar[s], ph ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        unsigned char* st = ring + (size_t)s * stage_bytes;
+        const uint32_t a_base = lm_smem_u32(st + 2 * kAtomBytes);
+        const uint32_t b_base = a_base + (uint32_t)atoms * kAtomBytes;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(s * kLoraBN);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2) * kAtomBytes + (uint32_t)(ks & 3) * 32;
+          lm_mma(tmem_d, lm_make_desc(a_base + off), lm_make_desc(b_base + off), idesc, ks > 0 ? 1u : 0u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         lm_smem_u32(&tmem_full_bar[s]))
+                     : "memory");
+      }
+    }
+  } else {
+    // ---------------- epilogue: 8 warps; warp%4 selects the TMEM lane quarter, two warps per quarter
+    //                  split the 128 accumulator columns (= the two 64-column smem atoms) ----------
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const float scale = a.scale;
+    const bool storer = threadIdx.x == 64;  // first epilogue thread
+    for (int it = 0; it < my_tiles; ++it) {
+      const int t = (int)blockIdx.x + it * (int)gridDim.x;
+      const int m0 = (t / tiles_n) * kLoraBM, n0 = (t % tiles_n) * kLoraBN;
+      const int s = it & 1;
+      const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+      unsigned char* sW = ring + (size_t)s * stage_bytes;
+      lm_mbar_wait(&full_bar[s], ph);       // W tile landed (and the stage is ours)
+      lm_mbar_wait(&tmem_full_bar[s], ph);  // accumulator complete
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      unsigned char* row = sW + (size_t)h * kAtomBytes + (size_t)r * 128;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        lm_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kLoraBN + h * 64 + c * 32), v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int chunk = c * 4 + j;
+          uint4* slot = reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4));
+          float f[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[j * 8 + k]) * scale;
+          if (has_base) {
+            const uint4 x = *slot;
+            f[0] += bf16_lo(x.x); f[1] += bf16_hi(x.x); f[2] += bf16_lo(x.y); f[3] += bf16_hi(x.y);
+            f[4] += bf16_lo(x.z); f[5] += bf16_hi(x.z); f[6] += bf16_lo(x.w); f[7] += bf16_hi(x.w);
+          }
+          uint4 y;
+          y.x = pack_bf16x2(f[0], f[1]);
+          y.y = pack_bf16x2(f[2], f[3]);
+          y.z = pack_bf16x2(f[4], f[5]);
+          y.w = pack_bf16x2(f[6], f[7]);
+          *slot = y;
+        }
+      }
+      // accumulator drained: hand the TMEM stage back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) lm_mbar_arrive(&tmem_empty_bar[s]);
+      // tile complete in smem -> TMA store
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("barrier.sync 1, %0;" ::"n"(kStgEpiThreads) : "memory");
+      if (storer) {
+        lm_tma_store_2d(&maps.out, n0, m0, sW);
+        lm_tma_store_2d(&maps.out, n0 + 64, m0, sW + kAtomBytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem of this stage is reusable
+        lm_mbar_arrive(&empty_bar[s]);
+      }
+    }
+    if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kStgStages * kLoraBN)
+                 : "memory");
+  }
+}
+
+extern "C" cudaError_t fedk_launch_lora_merge_staged(const LoraMergeArgs* a, const void* maps, void* bcat, void* atcat,
+                                                     int kpad, int sm_count, cudaStream_t stream) {
+  const int K = a->n_parties * a->r;
+  if (a->r % 16 != 0 || K > 128 || K < 16 || kpad % 64 != 0 || kpad < K || a->n % 8 != 0 || a->base_fp8 ||
+      a->out_fp8)
+    return cudaErrorInvalidValue;
+  const int atoms = kpad / 64;
+  // phase 1: all-gather of the adapter slices (each peer byte crosses NVLink once)
+  {
+    const size_t chunks = (size_t)a->n_parties * (a->m + a->n) * (a->r / 8);
+    size_t blocks = (chunks + 255) / 256;
+    const size_t cap = (size_t)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    fed_lora_gather_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*a, reinterpret_cast<__nv_bfloat16*>(bcat),
+                                                                 reinterpret_cast<__nv_bfloat16*>(atcat), kpad);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  // phase 2: persistent GEMM + update
+  const int smem = kStgStages * (2 + 2 * atoms) * kAtomBytes + 1024;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(fed_lora_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const int tiles_m = (int)((a->m + kLoraBM - 1) / kLoraBM), tiles_n = (int)((a->n + kLoraBN - 1) / kLoraBN);
+  const int n_tiles = tiles_m * tiles_n;
+  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
+  fed_lora_gemm_kernel<<<grid, kStgThreads, smem, stream>>>(*a, *reinterpret_cast<const LoraStagedMaps*>(maps), atoms,
+                                                            tiles_n, n_tiles);
+  return cudaGetLastError();
+}
+
 extern "C" cudaError_t fedk_launch_lora_merge_tma(const LoraMergeArgs* a, const void* maps, cudaStream_t stream) {
   const int K = a->n_parties * a->r;
   if (a->r % 16 != 0 || K > 256 || K < 16 || a->n % 64 != 0 || a->base_fp8 || a->out_fp8) return cudaErrorInvalidValue;

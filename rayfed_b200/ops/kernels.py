@@ -193,12 +193,36 @@ def barrier(*, n_parties: int, my_rank: int, sig_ptr: int, sig_peers: Sequence[i
     launch_counter.add("fed_barrier")
 
 
+_lora_ws = {}
+
+
+def _lora_workspace(m: int, n: int, kpad: int, stream_handle: int):
+    """K-major concatenated operands [m, kpad] / [n, kpad] for the staged LoRA merge,
+    cached per (device, shape, stream) so graph replays and repeated rounds reuse them."""
+    import torch
+
+    key = (torch.cuda.current_device(), m, n, kpad, stream_handle)
+    ws = _lora_ws.get(key)
+    if ws is None:
+        ws = (torch.zeros(m, kpad, dtype=torch.bfloat16, device="cuda"),
+              torch.zeros(n, kpad, dtype=torch.bfloat16, device="cuda"))
+        _lora_ws[key] = ws
+    return ws
+
+
 def lora_merge(*, b_ptrs: Sequence[int], at_ptrs: Sequence[int], out_ptr: int, m: int, n: int, r: int,
                scale: Optional[float] = None, weights: Optional[Sequence[float]] = None, w_base_ptr: int = 0,
                w_base_scales_ptr: int = 0, out_scales_ptr: int = 0, base_fp8: bool = False, out_fp8: bool = False,
-               stream=None, use_tma: bool = True) -> None:
+               stream=None, use_tma: bool = True, impl: Optional[str] = None) -> None:
     """K3 GEMM (tcgen05/TMEM): ``out = W_base + scale * sum_i w_i * B_i @ A_i`` with the
-    operands gathered from every party's adapter buffers. ``B_i``: [m, r]; ``A_i^T``: [n, r]."""
+    operands gathered from every party's adapter buffers. ``B_i``: [m, r]; ``A_i^T``: [n, r].
+
+    ``impl``: ``"staged"`` (gather once + persistent TMA/tcgen05 pipeline; default where it
+    applies: bf16 base/out, parties*r <= 128), ``"tma"`` (per-tile gather, TMA epilogue),
+    ``"direct"`` (per-tile gather, register epilogue; the only one for fp8 base/out).
+    ``RAYFED_B200_LORA_IMPL`` overrides the default."""
+    import os
+
     p = len(b_ptrs)
     if scale is None:
         scale = 1.0 / p
@@ -206,10 +230,26 @@ def lora_merge(*, b_ptrs: Sequence[int], at_ptrs: Sequence[int], out_ptr: int, m
         raise ValueError(f"lora_merge needs r % 16 == 0 and 16 <= parties*r <= 256 (got r={r}, parties={p})")
     if n % 32:
         raise ValueError("lora_merge needs n % 32 == 0")
+    if impl is None:
+        impl = os.environ.get("RAYFED_B200_LORA_IMPL", "staged") if use_tma else "direct"
+    if impl not in ("staged", "tma", "direct"):
+        raise ValueError(f"unknown lora_merge impl {impl!r}")
+    if impl == "staged" and (base_fp8 or out_fp8 or p * r > 128):
+        impl = "tma"
+    sh = _stream_handle(stream)
+    bcat = atcat = kpad = 0
+    if impl == "staged":
+        kpad = (p * r + 63) // 64 * 64
+        ws = _lora_workspace(m, n, kpad, sh)
+        bcat, atcat = ws[0].data_ptr(), ws[1].data_ptr()
     cuda_ext().lora_merge(list(b_ptrs), list(at_ptrs), w_base_ptr, w_base_scales_ptr, out_ptr, out_scales_ptr, m, n,
                           r, float(scale), [float(w) for w in (weights or [1.0] * p)], bool(base_fp8),
-                          bool(out_fp8), _stream_handle(stream), bool(use_tma))
-    launch_counter.add("fed_lora_merge")
+                          bool(out_fp8), sh, impl != "direct", bcat, atcat, kpad)
+    if impl == "staged":
+        launch_counter.add("fed_lora_gather")
+        launch_counter.add("fed_lora_gemm")
+    else:
+        launch_counter.add("fed_lora_merge")
 
 
 def local_sgd(w_ptr: int, g_ptr: int, mom_ptr: int, n: int, *, lr: float, momentum: float = 0.0,

@@ -265,10 +265,10 @@ def test_two_virtual_parties_on_one_gpu_rendezvous_in_kernel():
 
 
 # -- K3: tcgen05/TMEM LoRA merge -----------------------------------------------------------------
-@pytest.mark.parametrize("use_tma", [True, False])
+@pytest.mark.parametrize("impl", ["staged", "tma", "direct"])
 @pytest.mark.parametrize("parties,r,m,n", [(2, 16, 256, 256), (8, 16, 512, 384), (4, 32, 128, 1024), (1, 64, 200, 96),
                                            (8, 16, 200, 192)])
-def test_lora_merge_tcgen05_matches_torch(parties, r, m, n, use_tma):
+def test_lora_merge_tcgen05_matches_torch(parties, r, m, n, impl):
     torch.manual_seed(parties * 1000 + r)
     Bs = [(torch.randn(m, r, device=DEV) * 0.5).to(torch.bfloat16) for _ in range(parties)]
     Ats = [(torch.randn(n, r, device=DEV) * 0.5).to(torch.bfloat16) for _ in range(parties)]
@@ -277,7 +277,7 @@ def test_lora_merge_tcgen05_matches_torch(parties, r, m, n, use_tma):
     weights = [1.0] * parties
     weights[0] = 0.5
     K.lora_merge(b_ptrs=[b.data_ptr() for b in Bs], at_ptrs=[a.data_ptr() for a in Ats], out_ptr=out.data_ptr(),
-                 m=m, n=n, r=r, scale=1.0 / parties, weights=weights, w_base_ptr=base.data_ptr(), use_tma=use_tma)
+                 m=m, n=n, r=r, scale=1.0 / parties, weights=weights, w_base_ptr=base.data_ptr(), impl=impl)
     torch.cuda.synchronize()
     dw = torch.zeros(m, n, device=DEV)
     for i, (b, at) in enumerate(zip(Bs, Ats)):
@@ -287,6 +287,27 @@ def test_lora_merge_tcgen05_matches_torch(parties, r, m, n, use_tma):
     err = (out.float() - ref.float()).abs().max().item()
     assert err <= 2 ** -6 * max(1.0, ref.float().abs().max().item()), err
     assert torch.equal(out, ref) or (out.float() - ref.float()).abs().mean().item() < 1e-3
+
+
+@pytest.mark.parametrize("has_base", [True, False])
+def test_lora_merge_staged_persistent_ring_wraps_in_place(has_base):
+    """512 tiles on <=148 persistent CTAs: every smem/TMEM stage is reused (both mbarrier
+    parities), and the update runs in place (out aliases W_base) as FedLoRAExactMerge does."""
+    parties, r, m, n = 8, 16, 4096, 2048
+    torch.manual_seed(7)
+    Bs = [(torch.randn(m, r, device=DEV) * 0.5).to(torch.bfloat16) for _ in range(parties)]
+    Ats = [(torch.randn(n, r, device=DEV) * 0.5).to(torch.bfloat16) for _ in range(parties)]
+    w = torch.randn(m, n, device=DEV).to(torch.bfloat16)
+    dw = torch.cat(Bs, 1).float() @ torch.cat(Ats, 1).float().t()
+    ref = ((w.float() if has_base else 0) + dw / parties).to(torch.bfloat16)
+    for _ in range(2):  # second call reuses the cached workspace
+        out = w.clone()
+        K.lora_merge(b_ptrs=[b.data_ptr() for b in Bs], at_ptrs=[a.data_ptr() for a in Ats], out_ptr=out.data_ptr(),
+                     m=m, n=n, r=r, w_base_ptr=out.data_ptr() if has_base else 0, impl="staged")
+        torch.cuda.synchronize()
+        err = (out.float() - ref.float()).abs().max().item()
+        assert err <= 2 ** -6 * max(1.0, ref.float().abs().max().item()), err
+        assert (out.float() - ref.float()).abs().mean().item() < 1e-3
 
 
 def test_lora_merge_fp8_base_and_out():

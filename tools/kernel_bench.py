@@ -104,10 +104,14 @@ def main():
                                    out_ptr=Wout.data_ptr(), m=M, n=N, r=r, w_base_ptr=W.data_ptr()))
     byts = 2 * M * N * 2
     flops = 2.0 * M * N * P * r
+    out["lora_merge_staged_4096x4096_k128"] = {"us": t * 1e6, "GBps": byts / t / 1e9, "frac_hbm": byts / t / hbm,
+                                               "TFLOPs": flops / t / 1e12}
+    t = timed(lambda: K.lora_merge(b_ptrs=[b.data_ptr() for b in Bs], at_ptrs=[a.data_ptr() for a in Ats],
+                                   out_ptr=Wout.data_ptr(), m=M, n=N, r=r, w_base_ptr=W.data_ptr(), impl="tma"))
     out["lora_merge_tma_4096x4096_k128"] = {"us": t * 1e6, "GBps": byts / t / 1e9, "frac_hbm": byts / t / hbm,
                                             "TFLOPs": flops / t / 1e12}
     t = timed(lambda: K.lora_merge(b_ptrs=[b.data_ptr() for b in Bs], at_ptrs=[a.data_ptr() for a in Ats],
-                                   out_ptr=Wout.data_ptr(), m=M, n=N, r=r, w_base_ptr=W.data_ptr(), use_tma=False))
+                                   out_ptr=Wout.data_ptr(), m=M, n=N, r=r, w_base_ptr=W.data_ptr(), impl="direct"))
     out["lora_merge_direct_4096x4096_k128"] = {"us": t * 1e6, "GBps": byts / t / 1e9, "frac_hbm": byts / t / hbm,
                                                "TFLOPs": flops / t / 1e12}
     Bc = torch.cat(Bs, 1)
