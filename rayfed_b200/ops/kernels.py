@@ -239,7 +239,7 @@ def lora_merge(*, b_ptrs: Sequence[int], at_ptrs: Sequence[int], out_ptr: int, m
     sh = _stream_handle(stream)
     bcat = atcat = kpad = 0
     if impl == "staged":
-        kpad = (p * r + 63) // 64 * 64
+        kpad = max((p * r + 63) // 64 * 64, int(os.environ.get("RAYFED_B200_LORA_KPAD_MIN", "0")))
         ws = _lora_workspace(m, n, kpad, sh)
         bcat, atcat = ws[0].data_ptr(), ws[1].data_ptr()
     cuda_ext().lora_merge(list(b_ptrs), list(at_ptrs), w_base_ptr, w_base_scales_ptr, out_ptr, out_scales_ptr, m, n,
