@@ -19,12 +19,14 @@ from __future__ import annotations
 import functools
 import inspect
 import logging
+import os
 import pickle
 import signal
 import sys
 import threading
 from typing import Any, Callable, Dict, List, Union
 
+from . import _tracing
 from . import config as fed_config
 from . import utils as fed_utils
 from ._private import constants
@@ -149,6 +151,9 @@ def init(
         party_val=_get_party(job_name),
         job_name=job_name,
     )
+    trace_prefix = config.get("trace") or os.environ.get("RAYFED_B200_TRACE")
+    if trace_prefix:
+        _tracing.enable(party, str(trace_prefix))
     logger.info(f"Started rayfed_b200 with {cluster_config}")
 
     if threading.current_thread() is threading.main_thread():
@@ -287,6 +292,9 @@ def _shutdown(intended=True):
     fed_kv._clear_internal_kv()
     clear_global_context(wait_for_sending=wait_for_sending)
     _teardown_runtime(wait_for_sending)
+    trace_file = _tracing.disable(dump=True)
+    if trace_file:
+        logger.info(f"Wrote the fed timeline to {trace_file}.")
     logger.info("Shutdowned rayfed_b200.")
 
     if not intended and exit_on_sending_failure:
@@ -423,6 +431,14 @@ def get(fed_objects: Union[FedObject, List[FedObject], Any]) -> Any:
 
     ctx = get_global_context()
     fake_fed_task_id = ctx.next_seq_id()  # fed.get is a DAG node too
+    tl = _tracing._TRACER
+    if tl is not None:
+        with tl.span("fed.get", seq_id=fake_fed_task_id):
+            return _get(ctx, fed_objects, fake_fed_task_id)
+    return _get(ctx, fed_objects, fake_fed_task_id)
+
+
+def _get(ctx, fed_objects, fake_fed_task_id):
     job_name = ctx.get_job_name()
     addresses = _get_addresses(job_name)
     current_party = ctx.get_current_party()

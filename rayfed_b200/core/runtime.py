@@ -30,7 +30,7 @@ import sys
 import threading
 from typing import Any, Callable, Dict, List, Optional, Sequence
 
-from .. import _build
+from .. import _build, _tracing
 from ..exceptions import FedActorDiedError, FedGetTimeoutError, FedTaskError
 
 _native = None
@@ -191,6 +191,8 @@ class PartyRuntime:
         return _StreamContext(self._device)  # resolved per pool thread in the trampoline
 
     def _submit(self, lane_id, fn, args, kwargs, num_returns, stream_ctx):
+        if _tracing._TRACER is not None:
+            fn = _tracing.traced_task(fn, getattr(fn, "__name__", "task"))
         if stream_ctx is not None and stream_ctx.device is not None:
             fn = _device_trampoline(fn, stream_ctx, self._pool_tls if lane_id == 0 else None)
         refs = self._executor.submit(lane_id, fn, tuple(args), kwargs or None, num_returns)

@@ -6,6 +6,7 @@ from typing import Callable, List, Optional, Sequence
 
 import torch
 
+from .. import _tracing
 from ..ops import kernels as K
 from ..parallel.group import FedExchange, PartyGroup
 from ..parallel.symmetric import SymmetricHeap
@@ -151,7 +152,16 @@ class FedAggregator:
     def aggregate(self, stream=None, lr: Optional[float] = None):
         """Enqueue the fused aggregate on ``stream`` (default: current). Collective."""
         self.step_count += 1
+        tl = _tracing._TRACER
+        if tl is None or torch.cuda.is_current_stream_capturing():
+            self._plan.launch(0, self.step_count, lr, stream)
+            return
+        s = stream if stream is not None else torch.cuda.current_stream()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(s)
         self._plan.launch(0, self.step_count, lr, stream)
+        ev1.record(s)
+        tl.device_span("fed_aggregate", ev0, ev1, round=self.step_count, shard_elems=self.shard_len)
 
     def status(self) -> int:
         """0 = healthy; 2 = an in-kernel party barrier timed out."""

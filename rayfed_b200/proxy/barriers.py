@@ -35,6 +35,7 @@ from .._private.global_context import get_global_context
 from ..core import Ref, get_runtime, is_ref, native
 from ..core.runtime import _Produced
 from ..exceptions import FedRemoteError, FedTaskError
+from .. import _tracing
 from .base_proxy import ReceiverProxy, SenderProxy, SenderReceiverProxy
 
 logger = logging.getLogger(__name__)
@@ -476,6 +477,9 @@ def send(dest_party, data, upstream_seq_id, downstream_seq_id, is_error=False, c
     else:
         result = host.send(dest_party, data, upstream_seq_id, downstream_seq_id, is_error)
 
+    if _tracing._TRACER is not None:
+        _tracing.trace_ref("send", result, seq_id=f"{upstream_seq_id}->{downstream_seq_id}", dest=dest_party,
+                           is_error=bool(is_error))
     if check_sending:
         ctx = get_global_context()
         if ctx is not None:
@@ -544,7 +548,10 @@ def recv(party: str, src_party: str, upstream_seq_id, curr_seq_id):
     """`Ref` that resolves when the message keyed (upstream, curr) has arrived."""
     assert party, "Party can not be None."
     host: ProxyHost = _HOSTS["receiver"] or get_runtime().get_named(receiver_proxy_actor_name())
-    return host.get_data(src_party, upstream_seq_id, curr_seq_id)
+    ref = host.get_data(src_party, upstream_seq_id, curr_seq_id)
+    if _tracing._TRACER is not None:
+        _tracing.trace_ref("recv", ref, seq_id=f"{upstream_seq_id}->{curr_seq_id}", src=src_party)
+    return ref
 
 
 def ping_others(addresses: Dict[str, Dict], self_party: str, max_retries=3600):

@@ -28,6 +28,7 @@ import threading
 import time
 from typing import Dict, List, Optional, Tuple
 
+from ... import _tracing
 from ...ops import kernels as K
 from ...parallel.group import PartyGroup
 from ...parallel.symmetric import SymmetricHeap
@@ -173,9 +174,17 @@ class DeviceChannel:
                 stream.wait_event(ready_event)
             else:
                 stream.wait_stream(torch.cuda.current_stream(self._dev))
+            tl = _tracing._TRACER
+            if tl is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record(stream)
             K.push(t.data_ptr(), dst, n_arg, mode=mode, scale=scale, dst_scales_ptr=dst_scales,
                    flag_ptr=self._peer(dest_rank, OFF_FLAGS + 4 * self.group.rank), flag_value=seq,
                    done_counter_ptr=self._local(OFF_PUSH_DONE), stream=stream, device_index=self.device_index)
+            if tl is not None:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record(stream)
+                tl.device_span("fed_push", ev0, ev1, dest=dest_rank, seq=seq, bytes=payload_bytes + scales_bytes)
             t.record_stream(stream)
         self.stats["tensors_sent"] += 1
         self.stats["bytes_sent"] += payload_bytes + scales_bytes

@@ -117,6 +117,40 @@ def test_timeline_dumps_chrome_trace(tmp_path):
     assert ev[0]["name"] == "send" and ev[0]["args"]["seq_id"] == 3 and ev[0]["pid"] == "alice"
 
 
+def _traced_job(party, addresses, prefix):
+    import rayfed_b200 as fed
+
+    fed.init(addresses=addresses, party=party, config={"trace": prefix, "cross_silo_comm": comm_config()})
+
+    @fed.remote
+    def produce(x):
+        return x + 1
+
+    @fed.remote
+    def consume(x):
+        return x * 2
+
+    a = produce.party("alice").remote(1)
+    b = consume.party("bob").remote(a)
+    assert fed.get(b) == 4
+    fed.shutdown()
+    ev = json.load(open(f"{prefix}.{party}.json"))["traceEvents"]
+    names = {e["name"] for e in ev}
+    assert "fed.get" in names, names
+    if party == "alice":  # owner of `a`: pushed it to bob; received b's broadcast
+        assert {"produce", "send", "recv"} <= names, names
+        send = next(e for e in ev if e["name"] == "send")
+        assert send["args"]["dest"] == "bob" and send["args"]["ok"] is True and "->" in send["args"]["seq_id"]
+    else:
+        assert {"consume", "send", "recv"} <= names, names
+    assert all(e["pid"] == party for e in ev)
+
+
+def test_runtime_hooks_write_a_timeline_per_party(tmp_path):
+    """per-seq-id spans for sends / receives / tasks / fed.get, dumped at shutdown."""
+    run_parties(_traced_job, ["alice", "bob"], args=(make_addresses(["alice", "bob"]), str(tmp_path / "tl")))
+
+
 def test_checkpoint_roundtrip_cpu(tmp_path):
     from rayfed_b200.fl.bucket import FlatBucket
     from rayfed_b200.models import MLP
