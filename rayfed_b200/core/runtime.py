@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import atexit
 import importlib
+import importlib.util
 import os
 import sys
 import threading
@@ -43,8 +44,17 @@ def native():
     if _native is None:
         with _native_lock:
             if _native is None:
-                _build.ensure_core()
-                _native = importlib.import_module("rayfed_b200._fedcore")
+                alt = os.environ.get("RAYFED_B200_CORE_SO")
+                if alt:
+                    # an instrumented build of the same sources (tools/sanitize_core.sh: TSAN / ASAN)
+                    spec = importlib.util.spec_from_file_location("rayfed_b200._fedcore", alt)
+                    mod = importlib.util.module_from_spec(spec)
+                    spec.loader.exec_module(mod)
+                    sys.modules["rayfed_b200._fedcore"] = mod
+                    _native = mod
+                else:
+                    _build.ensure_core()
+                    _native = importlib.import_module("rayfed_b200._fedcore")
     return _native
 
 

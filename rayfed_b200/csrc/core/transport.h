@@ -196,7 +196,13 @@ class Peer {
     cv_.notify_all();
     close_conn();
     if (writer_.joinable()) writer_.join();
-    if (reader_.joinable()) reader_.join();
+    {
+      // an inline sender (push() on a caller thread) may still be inside write(); the
+      // shutdown above makes it fail fast — let it leave before the descriptor goes away
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait_for(lk, std::chrono::seconds(1), [&] { return !writing_; });
+    }
+    reap_reader();
     fail_all("transport stopped");
   }
 
@@ -251,11 +257,12 @@ class Peer {
   // Retry with exponential backoff; gives up after max_attempts.
   bool ensure_connected() {
     if (fd_.load() >= 0) return true;
-    if (reader_.joinable()) reader_.join();
+    reap_reader();
     double backoff = retry_.initial_backoff_s;
     for (int attempt = 1; attempt <= retry_.max_attempts; ++attempt) {
       int fd = connect_once();
       if (fd >= 0) {
+        reader_fd_ = fd;
         fd_.store(fd);
         reader_ = std::thread([this, fd] { reader_loop(fd); });
         return true;
@@ -268,11 +275,22 @@ class Peer {
     return false;
   }
 
+  // Descriptor lifecycle: any thread may *retire* the connection (fd_ -> -1 + shutdown,
+  // which wakes the reader and fails writers); the descriptor itself is closed only by
+  // whoever joins the reader thread (reap_reader), so no thread ever sits in a syscall
+  // on a number that was closed — and possibly reused — under it.
   void close_conn() {
     int fd = fd_.exchange(-1);
-    if (fd >= 0) {
-      ::shutdown(fd, SHUT_RDWR);
-      ::close(fd);
+    if (fd >= 0) ::shutdown(fd, SHUT_RDWR);
+  }
+
+  // Callers: the writer thread while it holds the `writing_` token, or stop() after
+  // it joined the writer — never concurrently.
+  void reap_reader() {
+    if (reader_.joinable()) reader_.join();
+    if (reader_fd_ >= 0) {
+      ::close(reader_fd_);
+      reader_fd_ = -1;
     }
   }
 
@@ -422,6 +440,7 @@ class Peer {
   bool stopping_ = false;
   bool writing_ = false;
   std::atomic<int> fd_{-1};
+  int reader_fd_ = -1;  // descriptor the running reader_ was started on (see reap_reader)
   std::thread writer_, reader_;
 };
 
@@ -505,11 +524,9 @@ class SocketTransport {
   void stop() {
     if (stopped_.exchange(true)) return;
     int lfd = listen_fd_.exchange(-1);
-    if (lfd >= 0) {
-      ::shutdown(lfd, SHUT_RDWR);
-      ::close(lfd);
-    }
+    if (lfd >= 0) ::shutdown(lfd, SHUT_RDWR);  // wakes accept(); close only after the join
     if (accept_thread_.joinable()) accept_thread_.join();
+    if (lfd >= 0) ::close(lfd);
     std::map<std::string, std::unique_ptr<Peer>> peers;
     std::vector<std::pair<int, std::thread>> conns;
     {
@@ -534,6 +551,12 @@ class SocketTransport {
  private:
   void accept_loop(int lfd) {
     for (;;) {
+      pollfd p{lfd, POLLIN, 0};
+      int pr = ::poll(&p, 1, 100);  // bounded wait: stop() does not rely on shutdown() waking accept()
+      if (stopped_.load()) return;
+      if (pr < 0 && errno != EINTR) return;
+      if (pr <= 0) continue;
+      if (p.revents & (POLLERR | POLLHUP | POLLNVAL)) return;
       int cfd = ::accept(lfd, nullptr, nullptr);
       if (cfd < 0) {
         if (errno == EINTR) continue;
