@@ -80,7 +80,6 @@ class DeviceChannel:
         # error word in pinned host memory (UVA: same pointer on the device): kernels
         # store to it on a wait timeout, the host reads it with a plain load
         self._status_host = torch.zeros(16, dtype=torch.int32).pin_memory()
-        # ~1.9 GHz SM clock: cycles until a device-side wait declares a timeout
         self._timeout_ns = int(timeout_s * 1e9)  # device waits use %globaltimer (ns)
         self.stats = {"tensors_sent": 0, "bytes_sent": 0, "tensors_received": 0, "bytes_received": 0,
                       "credit_stalls": 0, "bcast_tensors_sent": 0, "bcast_bytes_sent": 0}
