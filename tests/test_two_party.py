@@ -276,3 +276,63 @@ def _three(party, addresses):
 def test_three_parties():
     parties = ["alice", "bob", "carol"]
     run_parties(_three, parties, args=(make_addresses(parties),))
+
+
+# -- N parties (parametrise N in {2, 4, 8}): the reference's FedAvg-like flow
+#    (fed/tests/test_fed_get.py:50-85) generalised — per-party actors train, one party averages,
+#    every party installs the mean; checked in EVERY controller ---------------------------------
+def _n_party_fedavg(party, addresses, transport):
+    fed = _init(party, addresses, transport)
+    parties = list(addresses)
+    n = len(parties)
+
+    @fed.remote
+    class Trainer:
+        def __init__(self, rank):
+            self.w = float(rank)
+            self.seen = []
+
+        def train(self):
+            self.w += 1.0
+            return self.w
+
+        def set_weights(self, w):
+            self.w = w
+            self.seen.append(w)
+            return w
+
+        def history(self):
+            return self.seen
+
+    @fed.remote
+    def mean(*ws):
+        return sum(ws) / len(ws)
+
+    trainers = {p: Trainer.party(p).remote(i) for i, p in enumerate(parties)}
+    server = parties[-1]
+    expected = []
+    cur = [float(i) for i in range(n)]
+    for rnd in range(3):
+        ws = [trainers[p].train.remote() for p in parties]
+        avg = mean.party(server).remote(*ws)
+        acks = [trainers[p].set_weights.remote(avg) for p in parties]
+        cur = [c + 1.0 for c in cur]
+        m = sum(cur) / n
+        cur = [m] * n
+        expected.append(m)
+        got = fed.get(acks)
+        assert got == [m] * n, (rnd, got, m)
+    hist = fed.get([trainers[p].history.remote() for p in parties])
+    assert hist == [expected] * n, hist
+    fed.shutdown()
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_n_party_fedavg_rounds(n):
+    parties = [f"p{i}" for i in range(n)]
+    run_parties(_n_party_fedavg, parties, args=(make_addresses(parties), "native"), timeout=150)
+
+
+def test_four_party_fedavg_rounds_over_grpc():
+    parties = [f"p{i}" for i in range(4)]
+    run_parties(_n_party_fedavg, parties, args=(make_addresses(parties), "grpc"), timeout=150)
