@@ -1,5 +1,6 @@
 """One tiny FedAvg round on a single GPU: exercises fwd/bwd, the fused local SGD
-kernel, the fused aggregate kernel (N=1 degenerate all-reduce) and push/unpack."""
+kernel, the fused aggregate kernel (N=1 degenerate all-reduce), push/unpack and the
+tcgen05 LoRA merge."""
 from __future__ import annotations
 
 import torch
@@ -40,7 +41,19 @@ def run(device: str = "cuda:0"):
     K.unpack(buf.local_ptr, dst.data_ptr(), src.numel() * 4, flag_ptr=ctrl.data_ptr(), flag_value=1,
              done_counter_ptr=ctrl.data_ptr() + 12, status_ptr=ctrl.data_ptr() + 16, timeout_ns=int(5e9),
              device_index=dev.index or 0)
+    # exact LoRA merge on the tensor cores (tcgen05/TMEM, TMA-fed persistent pipeline)
+    m = n = 256
+    r = 64
+    B = (torch.randn(m, r, device=dev) * 0.25).to(torch.bfloat16)
+    At = (torch.randn(n, r, device=dev) * 0.25).to(torch.bfloat16)
+    W = torch.randn(m, n, device=dev).to(torch.bfloat16)
+    Wm = W.clone()
+    K.lora_merge(b_ptrs=[B.data_ptr()], at_ptrs=[At.data_ptr()], out_ptr=Wm.data_ptr(), m=m, n=n, r=r, scale=0.5,
+                 w_base_ptr=Wm.data_ptr())
     torch.cuda.synchronize()
+    ref = (W.float() + 0.5 * (B.float() @ At.float().t())).to(torch.bfloat16)
+    assert (Wm.float() - ref.float()).abs().max().item() <= 2 ** -5 * max(1.0, ref.float().abs().max().item()), \
+        "tcgen05 LoRA merge mismatch"
     assert torch.equal(src, dst), "push/unpack loopback mismatch"
     assert torch.isfinite(loss).item()
     assert not torch.equal(w0, bucket.flat_w), "weights did not change"
