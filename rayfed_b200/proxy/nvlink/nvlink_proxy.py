@@ -47,10 +47,11 @@ _DEFAULT_MIN_BYTES = 4096
 class _DevicePickler(cloudpickle.Pickler):
     """Pickles an object graph, diverting big CUDA tensors to ``sink``."""
 
-    def __init__(self, file, sink, min_bytes, before_host_copy=None):
+    def __init__(self, file, sink, min_bytes, before_host_copy=None, max_bytes=None):
         super().__init__(file, protocol=5)
         self._sink = sink
         self._min_bytes = min_bytes
+        self._max_bytes = max_bytes  # tensors that do not fit an arena region spill to the host frame
         self._before_host_copy = before_host_copy
         self.small_tensors = 0
 
@@ -58,9 +59,10 @@ class _DevicePickler(cloudpickle.Pickler):
         import torch
 
         if isinstance(obj, torch.Tensor) and obj.is_cuda and obj.layout == torch.strided:
-            if obj.numel() * obj.element_size() >= self._min_bytes:
+            nbytes = obj.numel() * obj.element_size()
+            if nbytes >= self._min_bytes and (self._max_bytes is None or nbytes + 4096 <= self._max_bytes):
                 return (_TAG, self._sink(obj.detach()))
-            # small tensors ride the host frame — as CPU data, re-homed on the *receiver's*
+            # small (and oversize) tensors ride the host frame — as CPU data, re-homed on the *receiver's*
             # device (a plain pickle would resurrect them on the sender's device index and
             # make every party open a CUDA context on every other party's GPU)
             if self._before_host_copy is not None and self.small_tensors == 0:
@@ -158,7 +160,8 @@ class NvlinkSenderProxy(NativeSenderProxy):
 
         buf = io.BytesIO()
         pickler = _DevicePickler(buf, sink, self._min_bytes,
-                                 ready_event.synchronize if ready_event is not None else None)
+                                 ready_event.synchronize if ready_event is not None else None,
+                                 max_bytes=channel.region_bytes)
         pickler.dump(data)
         if not tensors:
             if pickler.small_tensors:
@@ -199,7 +202,8 @@ class NvlinkSenderProxy(NativeSenderProxy):
 
         buf = io.BytesIO()
         pickler = _DevicePickler(buf, sink, self._min_bytes,
-                                 ready_event.synchronize if ready_event is not None else None)
+                                 ready_event.synchronize if ready_event is not None else None,
+                                 max_bytes=channel.region_bytes if channel is not None else None)
         pickler.dump(data)
         acks = {}
         if not tensors:
