@@ -37,7 +37,7 @@ from ._private.global_context import clear_global_context, get_global_context, i
 from .config import CrossSiloMessageConfig
 from .core import get as _local_get
 from .core import get_runtime, is_refs, shutdown_runtime
-from .exceptions import FedRemoteError, FedTaskError
+from .exceptions import FedGetTimeoutError, FedRemoteError, FedTaskError
 from .fed_object import FedObject
 from .proxy import barriers
 from .proxy.barriers import (
@@ -476,7 +476,7 @@ def _get(ctx, fed_objects, fake_fed_task_id):
             refs.append(ref)
 
     try:
-        values = _local_get(refs)
+        values = _get_with_stall_diagnostic(refs, fake_fed_task_id)
         _raise_on_device_failure()
         return values[0] if is_individual_id else values
     except FedTaskError as e:
@@ -485,6 +485,33 @@ def _get(ctx, fed_objects, fake_fed_task_id):
             if get_global_context() is not None:
                 get_global_context().set_last_recevied_error(e.cause)
         raise
+
+
+_STALL_WARN_S = float(os.environ.get("RAYFED_B200_STALL_WARN_S", "30"))
+
+
+def _get_with_stall_diagnostic(refs, fed_task_id):
+    """``_local_get`` that never gives up but says *why* it may be stuck: a receiver cannot tell
+    a late message from one that will never come, and the reference simply hangs when two
+    controllers disagree on the number of fed calls.  Every ``RAYFED_B200_STALL_WARN_S`` seconds
+    (0 disables) of blocking we log which keys are awaited and which messages arrived that no
+    consumer ever asked for — the latter is the signature of diverged scripts."""
+    if _STALL_WARN_S <= 0:
+        return _local_get(refs)
+    waited = 0.0
+    while True:
+        try:
+            return _local_get(refs, timeout=_STALL_WARN_S)
+        except FedGetTimeoutError:
+            waited += _STALL_WARN_S
+            waiting, unclaimed = barriers.pending_summary()
+            msg = (f"fed.get (seq id {fed_task_id}) has been blocked for {waited:.0f}s; awaited message keys "
+                   f"(upstream, downstream): {waiting or 'none'}.")
+            if unclaimed:
+                msg += (f" Messages that arrived but that no task or fed.get of this party asked for: {unclaimed}. "
+                        "If these do not get consumed, the parties' driver scripts have most likely diverged "
+                        "(a different number of .remote()/fed.get calls was issued in some party).")
+            logger.warning(msg)
 
 
 def _raise_on_device_failure():

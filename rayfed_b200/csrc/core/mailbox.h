@@ -11,6 +11,8 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <utility>
+#include <vector>
 
 #include "ref.h"
 
@@ -73,6 +75,23 @@ class Mailbox {
   size_t pending() {
     std::lock_guard<std::mutex> lk(mu_);
     return slots_.size();
+  }
+  // Diagnostics: keys a consumer is waiting for vs. messages nobody asked for.  A growing
+  // second list while the first one stalls is the signature of controller divergence
+  // (the parties' scripts issued different numbers of fed calls).
+  void snapshot(std::vector<std::pair<std::string, std::string>>* waiting,
+                std::vector<std::pair<std::string, std::string>>* unclaimed, size_t limit) {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto& kv : slots_) {
+      auto sep = kv.first.find('\x1f');
+      std::pair<std::string, std::string> k{kv.first.substr(0, sep),
+                                            sep == std::string::npos ? "" : kv.first.substr(sep + 1)};
+      if (kv.second.claimed && !kv.second.filled) {
+        if (waiting->size() < limit) waiting->push_back(std::move(k));
+      } else if (kv.second.filled && !kv.second.claimed) {
+        if (unclaimed->size() < limit) unclaimed->push_back(std::move(k));
+      }
+    }
   }
   void clear() {
     std::unordered_map<std::string, Slot> dead;

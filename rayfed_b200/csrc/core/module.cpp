@@ -174,6 +174,14 @@ PYBIND11_MODULE(_fedcore, m) {
           },
           py::arg("up"), py::arg("down"), py::arg("data"), py::arg("is_error") = false)
       .def("pending", &Mailbox::pending)
+      .def(
+          "snapshot",
+          [](Mailbox& mb, size_t limit) {
+            std::vector<std::pair<std::string, std::string>> waiting, unclaimed;
+            mb.snapshot(&waiting, &unclaimed, limit);
+            return py::make_tuple(waiting, unclaimed);
+          },
+          py::arg("limit") = 32)
       .def("clear", &Mailbox::clear)
       .def("stats", [](Mailbox& mb) {
         py::dict d;

@@ -554,6 +554,22 @@ def recv(party: str, src_party: str, upstream_seq_id, curr_seq_id):
     return ref
 
 
+def pending_summary(limit: int = 16):
+    """(waiting, unclaimed) message keys of this party's receiver — ``waiting``: a consumer asked,
+    nothing arrived yet; ``unclaimed``: arrived, nobody asked.  Used by the stall diagnostic of
+    ``fed.get`` (controller-divergence detection)."""
+    try:
+        host = _HOSTS["receiver"] or get_runtime().get_named(receiver_proxy_actor_name())
+    except Exception:  # noqa: BLE001
+        return [], []
+    mailbox = getattr(host.proxy, "_mailbox", None)
+    if mailbox is None or not hasattr(mailbox, "snapshot"):
+        return [], []
+    waiting, unclaimed = mailbox.snapshot(limit)
+    unclaimed = [k for k in unclaimed if k != ("ping", "ping") and not k[0].startswith("__devq__")]
+    return list(waiting), unclaimed
+
+
 def ping_others(addresses: Dict[str, Dict], self_party: str, max_retries=3600):
     """Init barrier: ping every peer until each one has acknowledged.
 

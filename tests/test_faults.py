@@ -210,3 +210,56 @@ def _whitelist(party, addresses, transport):
 @pytest.mark.parametrize("transport", ["native", "grpc"])
 def test_serializing_allowed_list(transport):
     run_parties(_whitelist, PARTIES, args=(make_addresses(PARTIES), transport))
+
+
+# -- controller divergence: the reference hangs silently; here the stalled fed.get says why ----------
+def _diverged(party, addresses, log_path):
+    import logging
+
+    os.environ["RAYFED_B200_STALL_WARN_S"] = "0.5"
+    import rayfed_b200 as fed
+    from rayfed_b200 import api as fed_api
+
+    fed_api._STALL_WARN_S = 0.5
+    fed.init(addresses=addresses, party=party, logging_level="warning",
+             config={"cross_silo_comm": comm_config("native"), "barrier_on_initializing": True})
+    records = []
+
+    class Grab(logging.Handler):
+        def emit(self, rec):
+            records.append(rec.getMessage())
+
+    logging.getLogger("rayfed_b200.api").addHandler(Grab())
+
+    @fed.remote
+    def f(x):
+        return x + 1
+
+    if party == "alice":
+        f.party("alice").remote(0)  # BUG in alice's copy of the script: one extra fed call
+    a = f.party("alice").remote(1)  # seq ids now differ between the two controllers
+    import threading
+
+    out = []
+    t = threading.Thread(target=lambda: out.append(fed.get(a)), daemon=True)
+    t.start()
+    t.join(2.5)
+    if party == "bob":
+        # bob waits for (1#0 -> 2) but alice sent (2#0 -> 3): never satisfiable
+        assert t.is_alive()
+        text = "\n".join(records)
+        with open(log_path, "w") as fh:
+            fh.write(text)
+        assert "has been blocked" in text and "diverged" in text and "('2#0', '3')" in text, text
+    else:
+        import time
+
+        deadline = time.time() + 40  # stay reachable until bob has made his observation
+        while not os.path.exists(log_path) and time.time() < deadline:
+            time.sleep(0.05)
+    os._exit(0)  # the job is wedged by construction; leave without the drain
+
+
+def test_diverged_controllers_are_diagnosed(tmp_path):
+    addresses = make_addresses(["alice", "bob"])
+    run_parties(_diverged, ["alice", "bob"], args=(addresses, str(tmp_path / "bob.log")), timeout=60)
