@@ -34,9 +34,8 @@ class FedActorHandle:
     def __getattr__(self, method_name: str):
         # Raises AttributeError for unknown methods — in every party.
         getattr(self._body, method_name)
-        return FedActorMethod(self._addresses, self._party, self._node_party, self, method_name).options(
-            **self._options
-        )
+        # actor-level options apply to every method (reference: fed_actor.py:67,76)
+        return FedActorMethod(self._addresses, self._party, self._node_party, self, method_name, self._options)
 
     def _execute_impl(self, cls_args, cls_kwargs):
         """Instantiate — owner party only."""
@@ -56,14 +55,17 @@ class FedActorHandle:
 
 
 class FedActorMethod:
-    def __init__(self, addresses, party, node_party, fed_actor_handle, method_name) -> None:
+    __slots__ = ("_addresses", "_party", "_node_party", "_fed_actor_handle", "_method_name", "_options",
+                 "_fed_call_holder")
+
+    def __init__(self, addresses, party, node_party, fed_actor_handle, method_name, options=None) -> None:
         self._addresses = addresses
         self._party = party
         self._node_party = node_party
         self._fed_actor_handle = fed_actor_handle
         self._method_name = method_name
-        self._options = {}
-        self._fed_call_holder = FedCallHolder(node_party, self._execute_impl)
+        self._options = dict(options) if options else {}
+        self._fed_call_holder = FedCallHolder(node_party, self._execute_impl, self._options)
 
     def remote(self, *args, **kwargs):
         return self._fed_call_holder.internal_remote(*args, **kwargs)

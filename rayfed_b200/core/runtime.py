@@ -138,16 +138,20 @@ class ActorHandle:
         self._instance = None
         self._dead = False
         self._ready_ref = None
+        self._callers: Dict[str, Callable] = {}
 
     @property
     def name(self) -> str:
         return self._name
 
     def submit_method(self, method_name: str, args: tuple, kwargs: dict, num_returns: int = 1):
-        def call(*a, **kw):
-            return getattr(self._instance, method_name)(*a, **kw)
+        call = self._callers.get(method_name)
+        if call is None:  # one trampoline per method, not per call
+            def call(*a, **kw):
+                return getattr(self._instance, method_name)(*a, **kw)
 
-        call.__name__ = f"{self._name}.{method_name}"
+            call.__name__ = f"{self._name}.{method_name}"
+            self._callers[method_name] = call
         return self._runtime._submit(self._lane_id, call, args, kwargs, num_returns, self._stream_ctx)
 
     def submit_call(self, fn: Callable, args: tuple, kwargs: dict, num_returns: int = 1):

@@ -281,6 +281,7 @@ class Executor : public std::enable_shared_from_this<Executor> {
   }
 
   static void run(Task& t, ExecStats& stats, py::object& wrap) {
+    pre_gil_spin();  // see ref.h: avoid sleeping on the GIL while the driver is mid-submit
     py::gil_scoped_acquire gil;
     py::object dep_err;
     py::tuple in_args = py::reinterpret_borrow<py::tuple>(t.args);
@@ -315,16 +316,21 @@ class Executor : public std::enable_shared_from_this<Executor> {
         }
       }
     }
+    // Outcome is computed first and PUBLISHED LAST: the waiter (usually the driver spinning
+    // in fed.get) wakes the moment a Ref completes and immediately wants the GIL, so every
+    // microsecond this thread keeps holding it after publishing is a chance for the waiter to
+    // fall asleep on the GIL instead of running.
+    std::vector<py::object> values;
+    py::object error;
     if (dep_err) {
       // An upstream task failed: the failure flows along the edge (Ray semantics).
-      for (auto& o : t.outs) o->set_error(dep_err);
-      stats.failed.fetch_add(1, std::memory_order_relaxed);
+      error = dep_err;
     } else {
       try {
         py::object res = t.fn(*call_args, **call_kwargs);
         size_t n = t.outs.size();
         if (n == 1) {
-          t.outs[0]->set_value(res);
+          values.push_back(std::move(res));
         } else {
           py::list parts(res);
           if (parts.size() != n) {
@@ -333,11 +339,10 @@ class Executor : public std::enable_shared_from_this<Executor> {
             PyErr_SetString(PyExc_ValueError, msg.c_str());
             throw py::error_already_set();
           }
-          for (size_t i = 0; i < n; ++i) t.outs[i]->set_value(parts[i]);
+          for (size_t i = 0; i < n; ++i) values.push_back(parts[i]);
         }
-        stats.completed.fetch_add(1, std::memory_order_relaxed);
       } catch (py::error_already_set& e) {
-        py::object exc;
+        values.clear();
         try {
           e.restore();
           PyObject *ty, *val, *tb;
@@ -347,24 +352,30 @@ class Executor : public std::enable_shared_from_this<Executor> {
           py::object v = py::reinterpret_steal<py::object>(val);
           Py_XDECREF(ty);
           Py_XDECREF(tb);
-          exc = wrap ? wrap(v) : v;
+          error = wrap ? wrap(v) : v;
         } catch (py::error_already_set& e2) {
-          exc = py::reinterpret_borrow<py::object>(e2.value());
+          error = py::reinterpret_borrow<py::object>(e2.value());
         }
-        for (auto& o : t.outs) o->set_error(exc);
-        stats.failed.fetch_add(1, std::memory_order_relaxed);
       } catch (std::exception& e) {
-        py::object exc = py::reinterpret_steal<py::object>(
-            PyObject_CallFunction(PyExc_RuntimeError, "s", e.what()));
-        for (auto& o : t.outs) o->set_error(exc);
-        stats.failed.fetch_add(1, std::memory_order_relaxed);
+        values.clear();
+        error = py::reinterpret_steal<py::object>(PyObject_CallFunction(PyExc_RuntimeError, "s", e.what()));
       }
     }
-    // release Python payloads while we still hold the GIL
+    // release Python payloads while we still hold the GIL — before anyone is woken
+    call_args = py::tuple();
+    call_kwargs = py::dict();
+    in_args = py::tuple();
     t.fn = py::object();
     t.args = py::object();
     t.kwargs = py::object();
     t.deps.clear();
+    if (error) {
+      stats.failed.fetch_add(1, std::memory_order_relaxed);
+      for (auto& o : t.outs) o->set_error(error);
+    } else {
+      stats.completed.fetch_add(1, std::memory_order_relaxed);
+      for (size_t i = 0; i < t.outs.size(); ++i) t.outs[i]->set_value(std::move(values[i]));
+    }
   }
 
   std::mutex mu_;

@@ -50,6 +50,7 @@ bool wait_interruptible(Ref& r, double timeout_s) {
     bool ok;
     {
       py::gil_scoped_release rel;
+      NativeWaitScope parked;
       ok = r.wait(remaining);
     }
     if (ok) return true;
@@ -78,6 +79,7 @@ std::pair<std::vector<RefPtr>, std::vector<RefPtr>> wait_refs(const std::vector<
   if (num_ready > refs.size()) num_ready = refs.size();
   {
     py::gil_scoped_release rel;
+    NativeWaitScope parked;
     std::unique_lock<std::mutex> lk(sh->mu);
     auto pred = [&] { return sh->n >= num_ready; };
     if (timeout_s < 0)

@@ -40,6 +40,57 @@ inline int spin_budget_us() {
   return v;
 }
 
+// ---- GIL hand-off heuristic ------------------------------------------------------------
+// A worker that is notified while the driver thread is still executing Python (between its
+// `.remote()` calls and the `fed.get` that follows) would block in take_gil(), i.e. go to
+// sleep in the kernel on the GIL condition variable, and pay a futex wake-up (10-30 us on a
+// VM) when the driver finally parks.  We know when Python threads are parked in OUR waits
+// (they release the GIL there): `g_native_waiters` counts them.  Before taking the GIL a
+// worker spins in user space for a bounded time while nobody is parked; the moment the
+// driver enters its wait the GIL is free and the acquisition is the uncontended fast path.
+// The spin adapts: after repeated timeouts (the driver is busy elsewhere: sleeping, I/O,
+// long Python compute) it is skipped except for an occasional probe.
+inline std::atomic<int> g_native_waiters{0};
+inline std::atomic<int> g_gil_spin_misses{0};
+
+struct NativeWaitScope {
+  NativeWaitScope() { g_native_waiters.fetch_add(1, std::memory_order_release); }
+  ~NativeWaitScope() { g_native_waiters.fetch_sub(1, std::memory_order_release); }
+};
+
+inline int gil_spin_budget_us() {
+  static int v = [] {
+    const char* e = std::getenv("RAYFED_B200_GIL_SPIN_US");
+    return e ? std::atoi(e) : 80;
+  }();
+  return v;
+}
+
+inline void cpu_relax();
+
+inline void pre_gil_spin() {
+  if (g_native_waiters.load(std::memory_order_acquire) > 0) return;
+  const int budget = gil_spin_budget_us();
+  if (budget <= 0) return;
+  int misses = g_gil_spin_misses.load(std::memory_order_relaxed);
+  if (misses > 8 && (misses & 63) != 0) {  // heuristic is not paying off: only probe now and then
+    g_gil_spin_misses.store(misses + 1, std::memory_order_relaxed);
+    return;
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    for (int i = 0; i < 64; ++i) {
+      if (g_native_waiters.load(std::memory_order_acquire) > 0) {
+        g_gil_spin_misses.store(0, std::memory_order_relaxed);
+        return;
+      }
+      cpu_relax();
+    }
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(budget)) break;
+  }
+  g_gil_spin_misses.store(misses + 1, std::memory_order_relaxed);
+}
+
 inline void cpu_relax() {
 #if defined(__x86_64__) || defined(__i386__)
   __builtin_ia32_pause();

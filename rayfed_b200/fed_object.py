@@ -30,6 +30,9 @@ class FedObjectReceivingContext:
     __slots__ = ()
 
 
+_NO_RECEIVING_CONTEXT = FedObjectReceivingContext()
+
+
 class FedObject:
     __slots__ = ("_node_party", "_fed_task_id", "_ref", "_idx_in_task", "_sending_context", "_receiving_context")
 
@@ -38,8 +41,8 @@ class FedObject:
         self._fed_task_id = fed_task_id
         self._ref = ref
         self._idx_in_task = idx_in_task
-        self._sending_context = FedObjectSendingContext()
-        self._receiving_context = FedObjectReceivingContext()
+        self._sending_context = None  # allocated on the first push (most objects never leave)
+        self._receiving_context = _NO_RECEIVING_CONTEXT
 
     # -- identity ------------------------------------------------------------
     def get_party(self) -> str:
@@ -63,10 +66,14 @@ class FedObject:
 
     # -- push bookkeeping --------------------------------------------------------
     def _mark_is_sending_to_party(self, target_party: str) -> None:
-        self._sending_context.mark_is_sending_to_party(target_party)
+        ctx = self._sending_context
+        if ctx is None:
+            ctx = self._sending_context = FedObjectSendingContext()
+        ctx.mark_is_sending_to_party(target_party)
 
     def _was_sending_or_sent_to_party(self, target_party: str) -> bool:
-        return self._sending_context.was_sending_or_sent_to_party(target_party)
+        ctx = self._sending_context
+        return ctx is not None and ctx.was_sending_or_sent_to_party(target_party)
 
     def __repr__(self) -> str:
         where = "local" if self._ref is not None else "remote"

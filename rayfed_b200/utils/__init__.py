@@ -33,6 +33,18 @@ def get_package_version(package_name: str) -> Optional[str]:
         return None
 
 
+_RECV = None
+
+
+def _recv_fn():
+    global _RECV
+    if _RECV is None:  # late import: barriers imports this module
+        from ..proxy.barriers import recv
+
+        _RECV = recv
+    return _RECV
+
+
 def resolve_dependencies(current_party, current_fed_task_id, *args, **kwargs):
     """Swap every ``FedObject`` leaf of ``(args, kwargs)`` for a local future.
 
@@ -43,7 +55,7 @@ def resolve_dependencies(current_party, current_fed_task_id, *args, **kwargs):
     Top-level futures gate the task in the scheduler; nested ones reach the
     task body as futures and are read with ``fed.get`` (same as the reference).
     """
-    from ..proxy.barriers import recv
+    recv = _recv_fn()
 
     if not has_containers(args, kwargs):
         # hot path: flat argument list, no pytree walk

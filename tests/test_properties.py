@@ -11,6 +11,8 @@ from hypothesis import strategies as st  # noqa: E402
 
 from rayfed_b200.tree_util import tree_flatten, tree_map, tree_unflatten  # noqa: E402
 
+pytestmark = pytest.mark.filterwarnings("ignore::hypothesis.errors.HypothesisWarning")
+
 Point = collections.namedtuple("Point", ["x", "y"])
 
 leaves = st.one_of(st.integers(), st.text(max_size=5), st.none(), st.floats(allow_nan=False), st.binary(max_size=4))
