@@ -23,7 +23,17 @@ from .exceptions import FedRemoteError, FedTaskError  # noqa: E402,F401
 from .fed_object import FedObject  # noqa: E402,F401
 from .proxy.barriers import recv, send  # noqa: E402,F401
 
+
+
+def aggregate(fed_objects, weights=None, fused=None):
+    """Cross-party (weighted) mean of one value per party — see :mod:`rayfed_b200.collective`."""
+    from .collective import aggregate as _aggregate
+
+    return _aggregate(fed_objects, weights=weights, fused=fused)
+
+
 __all__ = [
+    "aggregate",
     "get",
     "init",
     "kill",

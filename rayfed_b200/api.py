@@ -289,8 +289,12 @@ def _shutdown(intended=True):
             logger.info(f"Executing failure handler {failure_handler} ...")
             failure_handler(last_sending_error)
 
+    job_name_at_exit = global_context.get_job_name()
     fed_kv._clear_internal_kv()
     clear_global_context(wait_for_sending=wait_for_sending)
+    coll = sys.modules.get("rayfed_b200.collective")
+    if coll is not None:
+        coll.reset(job_name_at_exit)
     _teardown_runtime(wait_for_sending)
     trace_file = _tracing.disable(dump=True)
     if trace_file:

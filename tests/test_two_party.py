@@ -336,3 +336,67 @@ def test_n_party_fedavg_rounds(n):
 def test_four_party_fedavg_rounds_over_grpc():
     parties = [f"p{i}" for i in range(4)]
     run_parties(_n_party_fedavg, parties, args=(make_addresses(parties), "grpc"), timeout=150)
+
+
+# -- fed.aggregate: cross-party mean as one DAG-level call (DAG path on CPU) ----------------------
+def _aggregate_job(party, addresses):
+    import numpy as np
+    import torch
+
+    fed = _init(party, addresses, "native")
+    parties = list(addresses)
+    n = len(parties)
+
+    @fed.remote
+    class Trainer:
+        def __init__(self, rank):
+            self.rank = rank
+            self.w = None
+
+        def weights(self):
+            r = float(self.rank)
+            return {"w": torch.full((3, 2), r), "b": np.full(4, r + 1.0), "steps": r * 10, "half": torch.full((2,), r).half()}
+
+        def set_weights(self, w):
+            self.w = w
+            return True
+
+        def check(self, expect_w, expect_b, expect_steps):
+            w = self.w
+            assert torch.allclose(w["w"], torch.full((3, 2), expect_w)) and w["w"].dtype == torch.float32
+            assert np.allclose(w["b"], expect_b) and abs(w["steps"] - expect_steps) < 1e-9
+            assert w["half"].dtype == torch.float16
+            return True
+
+    trainers = {p: Trainer.party(p).remote(i) for i, p in enumerate(parties)}
+    before = fed._private.global_context.get_global_context().current_seq_id()
+    new = fed.aggregate([trainers[p].weights.remote() for p in parties])
+    after = fed._private.global_context.get_global_context().current_seq_id()
+    assert after - before == n + 1 + (n - 1)  # n weights() calls + mean + (n-1) redistributions, in EVERY party
+    assert [o.get_party() for o in new] == parties
+    for p, w in zip(parties, new):
+        trainers[p].set_weights.remote(w)
+    m = (n - 1) / 2.0
+    assert all(fed.get([trainers[p].check.remote(m, m + 1.0, m * 10) for p in parties]))
+
+    # weighted, inputs given in a different order than the party list
+    ws = [float(i + 1) for i in range(n)]
+    tot = sum(ws)
+    objs = [trainers[p].weights.remote() for p in reversed(parties)]
+    new = fed.aggregate(objs, weights=[w / tot for w in reversed(ws)], fused=False)
+    assert [o.get_party() for o in new] == list(reversed(parties))
+    exp = sum(w * i for i, w in enumerate(ws)) / tot
+    got = fed.get(new[0])
+    assert torch.allclose(got["w"], torch.full((3, 2), exp))
+
+    with pytest.raises(ValueError):
+        fed.aggregate([trainers[parties[0]].weights.remote()])  # not one object per party
+    with pytest.raises(RuntimeError):
+        fed.aggregate([trainers[p].weights.remote() for p in parties], fused=True)  # no device channel here
+    fed.shutdown()
+
+
+@pytest.mark.parametrize("n", [2, 4])
+def test_fed_aggregate_dag_path(n):
+    parties = [f"p{i}" for i in range(n)]
+    run_parties(_aggregate_job, parties, args=(make_addresses(parties),), timeout=150)
