@@ -50,9 +50,19 @@ def comm_config(transport="native", **extra):
     return cfg
 
 
+def _child_main(target, watchdog_s, party, args, kwargs):
+    # a party that is about to be killed for hanging first dumps every thread's Python stack to
+    # stderr (pytest shows it on failure) — the only way to learn anything from a rare flake
+    import faulthandler
+
+    faulthandler.dump_traceback_later(max(1.0, watchdog_s), exit=False)
+    target(party, *args, **kwargs)
+
+
 def run_parties(target, parties, args=(), timeout=90, expect=0, kwargs=None):
     """Run ``target(party, *args)`` in one process per party; assert exit codes."""
-    procs = [_CTX.Process(target=target, args=(p, *args), kwargs=kwargs or {}) for p in parties]
+    procs = [_CTX.Process(target=_child_main, args=(target, timeout - 3.0, p, tuple(args), kwargs or {}))
+             for p in parties]
     for p in procs:
         p.start()
     for p in procs:
