@@ -8,7 +8,7 @@ once" (contract items 7 in SURVEY Appendix A).
 """
 from __future__ import annotations
 
-from typing import Optional, Set
+from typing import Set
 
 
 class FedObjectSendingContext:

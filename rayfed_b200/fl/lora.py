@@ -16,11 +16,9 @@ Two aggregation rules, both one collective per round with no host hop:
 """
 from __future__ import annotations
 
-from typing import List, Optional
-
 import torch
 
-from ..models.llama import LlamaLoRA, LoRALinear
+from ..models.llama import LlamaLoRA
 from ..ops import kernels as K
 from ..parallel.group import PartyGroup
 from .bucket import FlatBucket

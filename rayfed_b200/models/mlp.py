@@ -1,5 +1,4 @@
 """Small dense models for tests and the split-learning example."""
-import torch
 from torch import nn
 
 

@@ -11,9 +11,8 @@ Three interchangeable exchanges (all implement ``all_gather(tag, blob)``):
 from __future__ import annotations
 
 import os
-import pickle
 import time
-from typing import Dict, List, Sequence
+from typing import List, Sequence
 
 
 class PartyGroup:

@@ -15,7 +15,6 @@ Backends
 """
 from __future__ import annotations
 
-import array
 import logging
 import os
 import pickle

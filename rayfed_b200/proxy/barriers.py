@@ -32,11 +32,11 @@ from typing import Dict, Optional
 from .. import config as fed_config
 from .._private import constants
 from .._private.global_context import get_global_context
-from ..core import Ref, get_runtime, is_ref, native
+from ..core import get_runtime, is_ref, native
 from ..core.runtime import _Produced
 from ..exceptions import FedRemoteError, FedTaskError
 from .. import _tracing
-from .base_proxy import ReceiverProxy, SenderProxy, SenderReceiverProxy
+from .base_proxy import ReceiverProxy, SenderProxy, SenderReceiverProxy  # noqa: F401  (re-exported)
 
 logger = logging.getLogger(__name__)
 

@@ -21,7 +21,7 @@ import logging
 import pickle
 import queue
 import threading
-from typing import Dict, Optional
+from typing import Dict
 
 import cloudpickle
 
