@@ -95,6 +95,22 @@ class NativeSenderProxy(SenderProxy):
             _ack_decoder,
         )
 
+    # -- owner -> all-parties broadcast (fed.get): serialise ONCE, N-1 native sends ------------
+    def can_broadcast(self) -> bool:
+        return True
+
+    def broadcast(self, dest_parties, data, upstream_seq_id, downstream_seq_id):
+        """Same object to every party in ``dest_parties``; returns {dest: ack Ref}.  The
+        reference pickles and issues one RPC per destination (fed/api.py:564-579)."""
+        payload = dumps(data)
+        if self._max_bytes is not None and len(payload) > self._max_bytes:
+            raise RuntimeError(
+                f"message of {len(payload)} bytes exceeds messages_max_size_in_bytes={self._max_bytes}"
+            )
+        up, down, is_err = str(upstream_seq_id), str(downstream_seq_id), isinstance(data, FedRemoteError)
+        send = self._transport.send
+        return {d: send(d, up, down, payload, is_err, _ack_decoder) for d in dest_parties}
+
     def drain(self, timeout: float = 60.0) -> bool:
         return self._transport.drain(timeout)
 

@@ -183,8 +183,7 @@ class NvlinkSenderProxy(NativeSenderProxy):
 
     # -- K1b: owner -> all-parties broadcast (fed.get, weight redistribution) -------------------
     def can_broadcast(self) -> bool:
-        ch = current_channel()
-        return ch is not None and ch.can_multicast and _MC_PUSH_ENABLED
+        return True  # serialise once in any case; multicast the tensors when the channel can
 
     def broadcast(self, dest_parties, data, upstream_seq_id, downstream_seq_id):
         """Send the same object to every party in ``dest_parties`` (all the others): each big
@@ -194,6 +193,10 @@ class NvlinkSenderProxy(NativeSenderProxy):
         if type(data) is _Produced:
             ready_event, data = data.event, data.value
         channel = current_channel()
+        if channel is None or isinstance(data, FedRemoteError):
+            if ready_event is not None:
+                ready_event.synchronize()
+            return super().broadcast(dest_parties, data, upstream_seq_id, downstream_seq_id)
         tensors = []
 
         def sink(t):
@@ -203,7 +206,7 @@ class NvlinkSenderProxy(NativeSenderProxy):
         buf = io.BytesIO()
         pickler = _DevicePickler(buf, sink, self._min_bytes,
                                  ready_event.synchronize if ready_event is not None else None,
-                                 max_bytes=channel.region_bytes if channel is not None else None)
+                                 max_bytes=channel.region_bytes)
         pickler.dump(data)
         acks = {}
         if not tensors:
@@ -214,7 +217,7 @@ class NvlinkSenderProxy(NativeSenderProxy):
             return acks
         with self._order_lock:
             descs = None
-            if all(channel.can_bcast_tensor(t) for t in tensors):  # all or nothing: no ring leaks
+            if _MC_PUSH_ENABLED and all(channel.can_bcast_tensor(t) for t in tensors):  # all or nothing: no ring leaks
                 descs = [channel.push_tensor_bcast(t, ready_event) for t in tensors]
                 if any(d is None for d in descs):
                     raise RuntimeError("multicast push refused a tensor it had accepted")
