@@ -537,6 +537,10 @@ def send_broadcast(dest_parties, data, upstream_seq_id, downstream_seq_id):
             data.add_done_callback(on_ready)
     else:
         issue(data)
+    if _tracing._TRACER is not None:
+        for d, r in results.items():
+            _tracing.trace_ref("send", r, seq_id=f"{upstream_seq_id}->{downstream_seq_id}", dest=d, is_error=False,
+                               broadcast=True)
     ctx = get_global_context()
     if ctx is not None:
         for d, r in results.items():
