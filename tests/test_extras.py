@@ -151,6 +151,20 @@ def test_runtime_hooks_write_a_timeline_per_party(tmp_path):
     run_parties(_traced_job, ["alice", "bob"], args=(make_addresses(["alice", "bob"]), str(tmp_path / "tl")))
 
 
+def _example_aggregate(party, addresses):
+    import importlib.util
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "fed_aggregate.py")
+    spec = importlib.util.spec_from_file_location("example_fed_aggregate", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main(party, addresses, rounds=12) < 0.05
+
+
+def test_fed_aggregate_example_converges():
+    run_parties(_example_aggregate, ["alice", "bob"], args=(make_addresses(["alice", "bob"]),), timeout=120)
+
+
 def test_checkpoint_roundtrip_cpu(tmp_path):
     from rayfed_b200.fl.bucket import FlatBucket
     from rayfed_b200.models import MLP
