@@ -278,6 +278,10 @@ class FedAvgWorker:
             x, y = batches[i] if batches is not None else self.batch_fn(self.rounds, i)
             loss = self.local_step(x, y)
         self.rounds += 1
+        if self._use_graph and loss is not None:
+            # the graph's output tensor is overwritten by the next replay; hand out a snapshot
+            # (ordered on this stream) so a reader one round later still sees THIS round's loss
+            loss = loss.clone()
         return loss
 
     def aggregate(self):
