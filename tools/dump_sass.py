@@ -59,6 +59,24 @@ def main() -> int:
             f.write(f"// {dem}\n" + "\n".join(lines) + "\n")
         top = dict(counts.most_common(16))
         index.append(f"* `{dem}` → `{fn}`  \n  {top}")
+    # static resource usage (cuobjdump -res-usage): registers / static smem / stack / local per kernel
+    res = subprocess.run(["cuobjdump", "-res-usage", sos[0]], check=True, capture_output=True, text=True).stdout
+    rows = []
+    cur = None
+    for ln in res.splitlines():
+        m = re.match(r"\s*Function (\S+):", ln)
+        if m:
+            cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
+            continue
+        if cur and "REG:" in ln:
+            kv = dict(re.findall(r"(REG|STACK|SHARED|LOCAL|CONSTANT\[0\]):(\d+)", ln))
+            rows.append((cur.replace("void ", "").replace("fedk::", ""), kv))
+            cur = None
+    index += ["", "## Static resources per kernel (`cuobjdump -res-usage`; dynamic shared memory is set at launch)", "",
+              "| kernel | registers/thread | static smem (B) | stack (B) | local (B) |", "|---|---:|---:|---:|---:|"]
+    for name, kv in rows:
+        index.append(f"| `{name}` | {kv.get('REG', '?')} | {kv.get('SHARED', '?')} | {kv.get('STACK', '?')} | "
+                     f"{kv.get('LOCAL', '?')} |")
     with open(os.path.join(OUT, "INDEX.md"), "w") as f:
         f.write("\n".join(index) + "\n")
     print(f"{len(chunks)} kernels → {OUT}")
