@@ -32,8 +32,35 @@ def aggregate(fed_objects, weights=None, fused=None):
     return _aggregate(fed_objects, weights=weights, fused=fused)
 
 
+def init_from_env(**overrides):
+    """``fed.init`` with addresses / party / device / transport taken from the environment set
+    by ``python -m rayfed_b200.tool.launch`` (keyword arguments override, ``config`` is merged)."""
+    import json
+
+    from .tool import launch as _launch
+
+    env = _os.environ
+    if _launch.ENV_PARTY not in env or _launch.ENV_ADDRESSES not in env:
+        raise RuntimeError("init_from_env: not started by `python -m rayfed_b200.tool.launch` "
+                           f"({_launch.ENV_PARTY} / {_launch.ENV_ADDRESSES} are not set)")
+    config = {"cross_silo_comm": {"transport": env.get(_launch.ENV_TRANSPORT, "auto")},
+              "barrier_on_initializing": True}
+    if env.get(_launch.ENV_DEVICE):
+        config["device"] = env[_launch.ENV_DEVICE]
+    user_cfg = dict(overrides.pop("config", None) or {})
+    comm = dict(config["cross_silo_comm"])
+    comm.update(user_cfg.pop("cross_silo_comm", None) or {})
+    config.update(user_cfg)
+    config["cross_silo_comm"] = comm
+    kwargs = dict(addresses=json.loads(env[_launch.ENV_ADDRESSES]), party=env[_launch.ENV_PARTY], config=config,
+                  job_name=env.get(_launch.ENV_JOB))
+    kwargs.update(overrides)
+    return init(**kwargs)
+
+
 __all__ = [
     "aggregate",
+    "init_from_env",
     "get",
     "init",
     "kill",

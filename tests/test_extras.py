@@ -165,6 +165,46 @@ def test_fed_aggregate_example_converges():
     run_parties(_example_aggregate, ["alice", "bob"], args=(make_addresses(["alice", "bob"]),), timeout=120)
 
 
+_LAUNCH_SCRIPT = """
+import os, sys
+sys.path.insert(0, {root!r})
+import rayfed_b200 as fed
+fed.init_from_env(logging_level="warning", config={{"cross_silo_comm": {{"retry_initial_backoff_s": 0.05}}}})
+
+@fed.remote
+def whoami():
+    return os.environ["RAYFED_B200_PARTY"]
+
+parties = sorted(fed.config.get_cluster_config().cluster_addresses)
+assert fed.get([whoami.party(p).remote() for p in parties]) == parties
+if len(sys.argv) > 1 and sys.argv[1] == "fail" and os.environ["RAYFED_B200_PARTY"] == parties[-1]:
+    fed.shutdown()
+    sys.exit(7)
+fed.shutdown()
+"""
+
+
+def test_launcher_starts_one_controller_per_party(tmp_path):
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "job.py"
+    script.write_text(_LAUNCH_SCRIPT.format(root=root))
+    cmd = [sys.executable, "-m", "rayfed_b200.tool.launch", "--parties", "alice,bob,carol", str(script)]
+    assert subprocess.run(cmd, cwd=root, timeout=120).returncode == 0
+    # a failing party's exit status becomes the launcher's
+    assert subprocess.run(cmd + ["fail"], cwd=root, timeout=120).returncode == 7
+
+
+def test_init_from_env_requires_the_launcher(monkeypatch):
+    import rayfed_b200 as fed
+
+    monkeypatch.delenv("RAYFED_B200_PARTY", raising=False)
+    with pytest.raises(RuntimeError):
+        fed.init_from_env()
+
+
 def test_checkpoint_roundtrip_cpu(tmp_path):
     from rayfed_b200.fl.bucket import FlatBucket
     from rayfed_b200.models import MLP
