@@ -528,7 +528,7 @@ class SocketTransport {
     if (accept_thread_.joinable()) accept_thread_.join();
     if (lfd >= 0) ::close(lfd);
     std::map<std::string, std::unique_ptr<Peer>> peers;
-    std::vector<std::pair<int, std::thread>> conns;
+    std::vector<Conn> conns;
     {
       std::lock_guard<std::mutex> lk(mu_);
       peers.swap(peers_);
@@ -536,11 +536,11 @@ class SocketTransport {
     }
     for (auto& kv : peers) kv.second->stop();
     for (auto& c : conns) {
-      ::shutdown(c.first, SHUT_RDWR);
+      ::shutdown(c.fd, SHUT_RDWR);
     }
     for (auto& c : conns) {
-      if (c.second.joinable()) c.second.join();
-      ::close(c.first);
+      if (c.th.joinable()) c.th.join();
+      ::close(c.fd);
     }
     if (!unix_path_.empty()) ::unlink(unix_path_.c_str());
   }
@@ -569,7 +569,26 @@ class SocketTransport {
       int one = 1;
       setsockopt(cfd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
       std::lock_guard<std::mutex> lk(mu_);
-      conns_.emplace_back(cfd, std::thread([this, cfd] { serve(cfd); }));
+      // reap connections whose peer went away (a party that restarts reconnects: without this
+      // every reconnect would leave a thread and a descriptor behind until stop())
+      for (auto it = conns_.begin(); it != conns_.end();) {
+        if (it->done->load(std::memory_order_acquire)) {
+          if (it->th.joinable()) it->th.join();
+          ::close(it->fd);
+          it = conns_.erase(it);
+        } else {
+          ++it;
+        }
+      }
+      Conn c;
+      c.fd = cfd;
+      c.done = std::make_shared<std::atomic<bool>>(false);
+      auto done = c.done;
+      c.th = std::thread([this, cfd, done] {
+        serve(cfd);
+        done->store(true, std::memory_order_release);
+      });
+      conns_.push_back(std::move(c));
     }
   }
 
@@ -613,7 +632,12 @@ class SocketTransport {
   std::shared_ptr<Mailbox> mailbox_;
   std::mutex mu_;
   std::map<std::string, std::unique_ptr<Peer>> peers_;
-  std::vector<std::pair<int, std::thread>> conns_;
+  struct Conn {
+    int fd = -1;
+    std::thread th;
+    std::shared_ptr<std::atomic<bool>> done;
+  };
+  std::vector<Conn> conns_;
   std::atomic<int> listen_fd_{-1};
   std::atomic<bool> stopped_{false};
   std::thread accept_thread_;
