@@ -40,9 +40,8 @@ for _ in range(2):
            flag_value=1, done_counter_ptr=base + 64)
     plan.launch(0, 1)
     K.local_sgd(buf.data_ptr(), g.data_ptr(), mo.data_ptr(), n, lr=0.01, momentum=0.9)
-    K.lora_merge(b_ptrs=[b.data_ptr() for b in Bs], at_ptrs=[a.data_ptr() for a in Ats], out_ptr=Wout.data_ptr(),
-                 m=M, n=N, r=r, w_base_ptr=W.data_ptr(), use_tma=True)
-    K.lora_merge(b_ptrs=[b.data_ptr() for b in Bs], at_ptrs=[a.data_ptr() for a in Ats], out_ptr=Wout.data_ptr(),
-                 m=M, n=N, r=r, w_base_ptr=W.data_ptr(), use_tma=False)
+    for impl in ("staged", "tma", "direct"):  # fed_lora_gather + fed_lora_gemm / fed_lora_merge_tma / fed_lora_merge
+        K.lora_merge(b_ptrs=[b.data_ptr() for b in Bs], at_ptrs=[a.data_ptr() for a in Ats],
+                     out_ptr=Wout.data_ptr(), m=M, n=N, r=r, w_base_ptr=W.data_ptr(), impl=impl)
 torch.cuda.synchronize()
 print("profile target done")
