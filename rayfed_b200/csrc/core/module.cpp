@@ -251,6 +251,7 @@ PYBIND11_MODULE(_fedcore, m) {
         d["bytes_sent"] = s.bytes_sent.load();
         d["bytes_received"] = s.bytes_received.load();
         d["rejected"] = s.rejected.load();
+        d["shm_conns"] = s.shm_conns.load();
         return d;
       });
 }

@@ -1,0 +1,335 @@
+// fedcore::Conn — the byte channel under one transport connection.
+//
+// Every connection is a stream socket (TCP loopback / Unix): it provides connect-retry, the
+// connection life cycle and peer-death detection (EOF).  When both ends run on one machine and
+// `RAYFED_B200_SHM=1`, the DATA moves through a pair of single-producer/single-consumer byte
+// rings in a POSIX shared-memory segment instead (this is the "HostRing" of SURVEY §7.1): a
+// frame costs two memcpys and no system call, and a spinning reader sees it without a kernel
+// wake-up.  The socket then only carries (a) the one-frame handshake that hands the segment
+// name to the server, (b) a one-byte doorbell when the consumer announced it was going to
+// sleep in poll(), (c) EOF when a side goes away.  The creator unlinks the segment name as
+// soon as the peer has mapped it, so nothing is left in /dev/shm even after a crash.
+#pragma once
+#include <fcntl.h>
+#include <poll.h>
+#include <sys/mman.h>
+#include <sys/socket.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+
+#include "ref.h"
+
+namespace fedcore {
+
+static constexpr uint32_t kShmMagic = 0x52424653;  // "SFBR"
+
+struct ShmRing {  // in shared memory
+  alignas(64) std::atomic<uint64_t> head;             // bytes produced
+  alignas(64) std::atomic<uint64_t> tail;             // bytes consumed
+  alignas(64) std::atomic<uint32_t> consumer_asleep;  // consumer is (about to be) blocked in poll()
+};
+
+struct ShmHeader {
+  uint32_t magic;
+  uint32_t capacity;  // bytes per ring, power of two
+  ShmRing c2s;        // client -> server
+  ShmRing s2c;        // server -> client
+};
+static constexpr size_t kShmHeaderBytes = 4096;
+static_assert(sizeof(ShmHeader) <= kShmHeaderBytes, "header must fit its page");
+
+// Read per connection attempt (not cached): cheap, and lets one process hold both kinds.
+inline bool shm_enabled() {
+  const char* e = std::getenv("RAYFED_B200_SHM");
+  return e && e[0] == '1';
+}
+inline uint32_t shm_ring_bytes() {
+  const char* e = std::getenv("RAYFED_B200_SHM_RING_KB");
+  uint32_t kb = e ? (uint32_t)std::atoi(e) : 1024;
+  uint32_t b = 64 * 1024;
+  while (b < kb * 1024u && b < (1u << 30)) b <<= 1;
+  return b;
+}
+
+inline bool fd_write_all(int fd, const void* buf, size_t n) {
+  const char* p = (const char*)buf;
+  while (n > 0) {
+    ssize_t w = ::send(fd, p, n, MSG_NOSIGNAL);
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      return false;
+    }
+    p += w;
+    n -= (size_t)w;
+  }
+  return true;
+}
+inline bool fd_read_all(int fd, void* buf, size_t n) {
+  char* p = (char*)buf;
+  while (n > 0) {
+    ssize_t r = ::recv(fd, p, n, 0);
+    if (r == 0) return false;
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      return false;
+    }
+    p += r;
+    n -= (size_t)r;
+  }
+  return true;
+}
+
+class Conn {
+ public:
+  explicit Conn(int fd) : fd_(fd) {}
+  ~Conn() {
+    if (map_) ::munmap(map_, map_len_);
+  }
+  Conn(const Conn&) = delete;
+  Conn& operator=(const Conn&) = delete;
+
+  int fd() const { return fd_; }
+  bool uses_shm() const { return tx_ != nullptr; }
+  void mark_dead() { dead_.store(true, std::memory_order_release); }
+  bool dead() const { return dead_.load(std::memory_order_acquire); }
+
+  // ---- client side: create a segment, returns its name ("" on failure) ------------------
+  std::string create_segment() {
+    static std::atomic<uint64_t> seq{0};
+    std::string name = "/rfb." + std::to_string((long)getpid()) + "." + std::to_string(seq.fetch_add(1));
+    int sfd = ::shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (sfd < 0) return "";
+    const uint32_t cap = shm_ring_bytes();
+    size_t len = kShmHeaderBytes + 2 * (size_t)cap;
+    if (::ftruncate(sfd, (off_t)len) != 0) {
+      ::close(sfd);
+      ::shm_unlink(name.c_str());
+      return "";
+    }
+    void* m = ::mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, sfd, 0);
+    ::close(sfd);
+    if (m == MAP_FAILED) {
+      ::shm_unlink(name.c_str());
+      return "";
+    }
+    auto* h = new (m) ShmHeader();
+    h->capacity = cap;
+    h->c2s.head.store(0);
+    h->c2s.tail.store(0);
+    h->c2s.consumer_asleep.store(0);
+    h->s2c.head.store(0);
+    h->s2c.tail.store(0);
+    h->s2c.consumer_asleep.store(0);
+    h->magic = kShmMagic;
+    pending_map_ = m;
+    pending_len_ = len;
+    pending_name_ = name;
+    return name;
+  }
+  // handshake answered: switch to the rings (client view) or drop the segment
+  void finish_create(bool accepted) {
+    if (!pending_map_) return;
+    ::shm_unlink(pending_name_.c_str());  // both sides have it mapped (or nobody wants it)
+    if (accepted) {
+      adopt(pending_map_, pending_len_, /*is_client=*/true);
+    } else {
+      ::munmap(pending_map_, pending_len_);
+    }
+    pending_map_ = nullptr;
+  }
+  // ---- server side: map the client's segment ---------------------------------------------------
+  bool attach_segment(const std::string& name) {
+    if (name.size() < 2 || name[0] != '/' || name.find('/', 1) != std::string::npos) return false;
+    int sfd = ::shm_open(name.c_str(), O_RDWR, 0600);
+    if (sfd < 0) return false;
+    struct stat st {};
+    if (::fstat(sfd, &st) != 0 || (size_t)st.st_size < kShmHeaderBytes + 2 * 64 * 1024) {
+      ::close(sfd);
+      return false;
+    }
+    size_t len = (size_t)st.st_size;
+    void* m = ::mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, sfd, 0);
+    ::close(sfd);
+    if (m == MAP_FAILED) return false;
+    auto* h = reinterpret_cast<ShmHeader*>(m);
+    uint32_t cap = h->capacity;
+    if (h->magic != kShmMagic || cap < 64 * 1024 || (cap & (cap - 1)) != 0 ||
+        kShmHeaderBytes + 2 * (size_t)cap != len) {
+      ::munmap(m, len);
+      return false;
+    }
+    adopt(m, len, /*is_client=*/false);
+    return true;
+  }
+
+  // ---- byte stream -------------------------------------------------------------------------------
+  bool write_all(const void* buf, size_t n) {
+    if (!tx_) return fd_write_all(fd_, buf, n);
+    const char* p = (const char*)buf;
+    const uint64_t cap = cap_;
+    int idle = 0;
+    while (n > 0) {
+      uint64_t head = tx_->head.load(std::memory_order_relaxed);
+      uint64_t tail = tx_->tail.load(std::memory_order_acquire);
+      uint64_t space = cap - (head - tail);
+      if (space == 0) {
+        if (dead()) return false;
+        ring_doorbell();  // the consumer may be asleep with a full ring in front of it
+        if (++idle < 2000) {
+          cpu_relax();
+        } else {
+          if (peer_closed()) return false;
+          std::this_thread::sleep_for(std::chrono::microseconds(50));
+        }
+        continue;
+      }
+      idle = 0;
+      size_t chunk = (size_t)std::min<uint64_t>(space, n);
+      size_t off = (size_t)(head & (cap - 1));
+      size_t first = std::min(chunk, (size_t)(cap - off));
+      std::memcpy(tx_data_ + off, p, first);
+      if (chunk > first) std::memcpy(tx_data_, p + first, chunk - first);
+      tx_->head.store(head + chunk, std::memory_order_release);
+      p += chunk;
+      n -= chunk;
+    }
+    ring_doorbell();
+    return true;
+  }
+
+  bool read_all(void* buf, size_t n) {
+    if (!rx_) return fd_read_all(fd_, buf, n);
+    char* p = (char*)buf;
+    const uint64_t cap = cap_;
+    while (n > 0) {
+      uint64_t tail = rx_->tail.load(std::memory_order_relaxed);
+      uint64_t head = rx_->head.load(std::memory_order_acquire);
+      uint64_t avail = head - tail;
+      if (avail == 0) {
+        int w = wait_readable(-1);
+        if (w < 0) return false;
+        continue;
+      }
+      size_t chunk = (size_t)std::min<uint64_t>(avail, n);
+      size_t off = (size_t)(tail & (cap - 1));
+      size_t first = std::min(chunk, (size_t)(cap - off));
+      std::memcpy(p, rx_data_ + off, first);
+      if (chunk > first) std::memcpy(p + first, rx_data_, chunk - first);
+      rx_->tail.store(tail + chunk, std::memory_order_release);
+      p += chunk;
+      n -= chunk;
+    }
+    return true;
+  }
+
+  // 1: data available, 0: timeout, -1: connection closed / error.  timeout_ms < 0: no limit.
+  int wait_readable(int timeout_ms) {
+    if (!rx_) {
+      for (;;) {
+        pollfd p{fd_, POLLIN, 0};
+        int pr = ::poll(&p, 1, timeout_ms < 0 ? 100 : timeout_ms);
+        if (pr > 0) return 1;  // readable or hung up: the following read tells which
+        if (pr < 0 && errno != EINTR) return -1;
+        if (timeout_ms >= 0) return 0;
+        if (dead()) return -1;
+      }
+    }
+    auto ready = [&] { return rx_->head.load(std::memory_order_acquire) != rx_->tail.load(std::memory_order_relaxed); };
+    auto start = std::chrono::steady_clock::now();
+    for (;;) {
+      if (ready()) return 1;
+      if (dead()) return -1;
+      // bounded user-space spin (same budget as every other wait of the runtime)
+      const int budget = spin_budget_us();
+      if (budget > 0) {
+        auto t0 = std::chrono::steady_clock::now();
+        while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(budget)) {
+          for (int i = 0; i < 64; ++i) {
+            if (ready()) return 1;
+            cpu_relax();
+          }
+        }
+      }
+      // announce the sleep, re-check (Dekker), then block on the socket: the producer rings
+      // the doorbell (one byte) when it sees the announcement; EOF means the peer went away
+      rx_->consumer_asleep.store(1, std::memory_order_seq_cst);
+      if (ready()) {
+        rx_->consumer_asleep.store(0, std::memory_order_seq_cst);
+        return 1;
+      }
+      pollfd p{fd_, POLLIN, 0};
+      int slice = 100;
+      if (timeout_ms >= 0) {
+        auto spent = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - start).count();
+        if (spent >= timeout_ms) {
+          rx_->consumer_asleep.store(0, std::memory_order_seq_cst);
+          return ready() ? 1 : 0;
+        }
+        slice = (int)std::min<long long>(100, timeout_ms - spent);
+      }
+      int pr = ::poll(&p, 1, slice);
+      rx_->consumer_asleep.store(0, std::memory_order_seq_cst);
+      if (pr > 0) {
+        char sink[64];
+        ssize_t r = ::recv(fd_, sink, sizeof(sink), MSG_DONTWAIT);
+        if (r == 0) return ready() ? 1 : -1;  // EOF: drain what is already in the ring first
+        if (r < 0 && errno != EAGAIN && errno != EWOULDBLOCK && errno != EINTR) return ready() ? 1 : -1;
+      } else if (pr < 0 && errno != EINTR) {
+        return -1;
+      }
+    }
+  }
+
+ private:
+  void adopt(void* m, size_t len, bool is_client) {
+    map_ = m;
+    map_len_ = len;
+    auto* h = reinterpret_cast<ShmHeader*>(m);
+    cap_ = h->capacity;
+    char* base = reinterpret_cast<char*>(m) + kShmHeaderBytes;
+    if (is_client) {
+      tx_ = &h->c2s;
+      tx_data_ = base;
+      rx_ = &h->s2c;
+      rx_data_ = base + cap_;
+    } else {
+      tx_ = &h->s2c;
+      tx_data_ = base + cap_;
+      rx_ = &h->c2s;
+      rx_data_ = base;
+    }
+  }
+  void ring_doorbell() {
+    if (tx_->consumer_asleep.load(std::memory_order_seq_cst)) {
+      char b = 1;
+      (void)::send(fd_, &b, 1, MSG_NOSIGNAL | MSG_DONTWAIT);
+    }
+  }
+  bool peer_closed() {
+    pollfd p{fd_, POLLIN, 0};
+    if (::poll(&p, 1, 0) > 0 && (p.revents & (POLLHUP | POLLERR | POLLNVAL))) return true;
+    return false;
+  }
+
+  int fd_;
+  std::atomic<bool> dead_{false};
+  void* map_ = nullptr;
+  size_t map_len_ = 0;
+  uint64_t cap_ = 0;
+  ShmRing* tx_ = nullptr;
+  char* tx_data_ = nullptr;
+  ShmRing* rx_ = nullptr;
+  char* rx_data_ = nullptr;
+  void* pending_map_ = nullptr;
+  size_t pending_len_ = 0;
+  std::string pending_name_;
+};
+
+}  // namespace fedcore

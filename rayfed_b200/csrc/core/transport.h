@@ -35,11 +35,12 @@
 
 #include "mailbox.h"
 #include "ref.h"
+#include "shm_conn.h"
 
 namespace fedcore {
 
 static constexpr uint32_t kMagic = 0x42444546;  // "FEDB"
-enum : uint8_t { kFrameData = 1, kFrameAck = 2 };
+enum : uint8_t { kFrameData = 1, kFrameAck = 2, kFrameHello = 3 };  // Hello: shm upgrade offer (shm_conn.h)
 
 #pragma pack(push, 1)
 struct FrameHeader {
@@ -62,35 +63,6 @@ struct RetryPolicy {
   double max_backoff_s = 30.0;
   double multiplier = 2.0;
 };
-
-inline bool write_all(int fd, const void* buf, size_t n) {
-  const char* p = (const char*)buf;
-  while (n > 0) {
-    ssize_t w = ::send(fd, p, n, MSG_NOSIGNAL);
-    if (w < 0) {
-      if (errno == EINTR) continue;
-      return false;
-    }
-    p += w;
-    n -= (size_t)w;
-  }
-  return true;
-}
-
-inline bool read_all(int fd, void* buf, size_t n) {
-  char* p = (char*)buf;
-  while (n > 0) {
-    ssize_t r = ::recv(fd, p, n, 0);
-    if (r == 0) return false;
-    if (r < 0) {
-      if (errno == EINTR) continue;
-      return false;
-    }
-    p += r;
-    n -= (size_t)r;
-  }
-  return true;
-}
 
 struct ParsedAddr {
   bool is_unix = false;
@@ -132,6 +104,7 @@ struct TransportStats {
   std::atomic<uint64_t> bytes_sent{0};
   std::atomic<uint64_t> bytes_received{0};
   std::atomic<uint64_t> rejected{0};
+  std::atomic<uint64_t> shm_conns{0};  // connections whose data path is the shared-memory rings
 };
 
 // ---------------------------------------------------------------------------
@@ -262,9 +235,18 @@ class Peer {
     for (int attempt = 1; attempt <= retry_.max_attempts; ++attempt) {
       int fd = connect_once();
       if (fd >= 0) {
+        auto c = std::make_shared<Conn>(fd);
+        if (shm_enabled() && shm_ok_ && is_local_addr() && !offer_shm(*c)) {
+          // the handshake broke the stream: start over on a fresh socket, without the offer
+          shm_ok_ = false;
+          ::close(fd);
+          --attempt;
+          continue;
+        }
+        std::atomic_store(&conn_, c);
         reader_fd_ = fd;
         fd_.store(fd);
-        reader_ = std::thread([this, fd] { reader_loop(fd); });
+        reader_ = std::thread([this, c] { reader_loop(c); });
         return true;
       }
       if (attempt == retry_.max_attempts) break;
@@ -281,7 +263,42 @@ class Peer {
   // on a number that was closed — and possibly reused — under it.
   void close_conn() {
     int fd = fd_.exchange(-1);
+    if (auto c = std::atomic_load(&conn_)) c->mark_dead();
     if (fd >= 0) ::shutdown(fd, SHUT_RDWR);
+  }
+
+  bool is_local_addr() const {
+    ParsedAddr pa = parse_addr(addr_);
+    return pa.is_unix || pa.host == "127.0.0.1" || pa.host == "::1";
+  }
+
+  // Offer the server a shared-memory data path (see shm_conn.h).  Returns false only when the
+  // socket stream itself can no longer be trusted; a polite refusal keeps the socket path.
+  bool offer_shm(Conn& c) {
+    std::string name = c.create_segment();
+    if (name.empty()) return true;  // no /dev/shm: plain socket
+    FrameHeader h{};
+    h.magic = kMagic;
+    h.type = kFrameHello;
+    h.data_len = name.size();
+    std::string out((const char*)&h, sizeof(h));
+    out += name;
+    bool io_ok = fd_write_all(c.fd(), out.data(), out.size());
+    bool accepted = false;
+    if (io_ok) {
+      pollfd p{c.fd(), POLLIN, 0};
+      io_ok = ::poll(&p, 1, 3000) > 0;
+      FrameHeader a{};
+      if (io_ok) io_ok = fd_read_all(c.fd(), &a, sizeof(a)) && a.magic == kMagic && a.type == kFrameAck;
+      if (io_ok && a.data_len) {
+        std::string skip(a.data_len, '\0');
+        io_ok = a.data_len <= 4096 && fd_read_all(c.fd(), &skip[0], a.data_len);
+      }
+      accepted = io_ok && a.code == 200;
+    }
+    c.finish_create(accepted);
+    if (accepted) stats_->shm_conns.fetch_add(1, std::memory_order_relaxed);
+    return io_ok;
   }
 
   // Callers: the writer thread while it holds the `writing_` token, or stop() after
@@ -343,9 +360,9 @@ class Peer {
       std::lock_guard<std::mutex> lk(mu_);
       inflight_[id] = {ack, m->deadline};
     }
-    int fd = fd_.load();
-    bool ok = fd >= 0 && write_all(fd, head.data(), head.size()) &&
-              (nbytes <= 4096 || write_all(fd, m->data.data(), nbytes));
+    auto c = std::atomic_load(&conn_);
+    bool ok = c && fd_.load() == c->fd() && c->write_all(head.data(), head.size()) &&
+              (nbytes <= 4096 || c->write_all(m->data.data(), nbytes));
     if (!ok) {
       {
         std::lock_guard<std::mutex> lk(mu_);
@@ -359,20 +376,20 @@ class Peer {
     }
   }
 
-  void reader_loop(int fd) {
+  void reader_loop(std::shared_ptr<Conn> c) {
+    const int fd = c->fd();
     for (;;) {
-      pollfd p{fd, POLLIN, 0};
-      int pr = ::poll(&p, 1, 100);
-      if (pr < 0 && errno != EINTR) break;
+      int pr = c->wait_readable(100);
+      if (pr < 0) break;
       sweep_timeouts();
-      if (pr <= 0) {
+      if (pr == 0) {
         if (fd_.load() != fd) break;
         continue;
       }
       FrameHeader h{};
-      if (!read_all(fd, &h, sizeof(h)) || h.magic != kMagic || h.type != kFrameAck) break;
+      if (!c->read_all(&h, sizeof(h)) || h.magic != kMagic || h.type != kFrameAck) break;
       std::string result(h.data_len, '\0');
-      if (h.data_len && !read_all(fd, &result[0], h.data_len)) break;
+      if (h.data_len && !c->read_all(&result[0], h.data_len)) break;
       RefPtr ack;
       {
         std::lock_guard<std::mutex> lk(mu_);
@@ -388,6 +405,7 @@ class Peer {
       else
         ack->set_raw(std::move(result), true);
     }
+    c->mark_dead();
     if (fd_.load() == fd) close_conn();
     fail_inflight("connection to party '" + name_ + "' closed before the message was acknowledged");
   }
@@ -440,6 +458,8 @@ class Peer {
   bool stopping_ = false;
   bool writing_ = false;
   std::atomic<int> fd_{-1};
+  std::shared_ptr<Conn> conn_;  // byte channel of the live connection (atomic_load/atomic_store)
+  bool shm_ok_ = true;          // cleared when a shm offer broke a connection attempt
   int reader_fd_ = -1;  // descriptor the running reader_ was started on (see reap_reader)
   std::thread writer_, reader_;
 };
@@ -528,7 +548,7 @@ class SocketTransport {
     if (accept_thread_.joinable()) accept_thread_.join();
     if (lfd >= 0) ::close(lfd);
     std::map<std::string, std::unique_ptr<Peer>> peers;
-    std::vector<Conn> conns;
+    std::vector<ServerConn> conns;
     {
       std::lock_guard<std::mutex> lk(mu_);
       peers.swap(peers_);
@@ -580,7 +600,7 @@ class SocketTransport {
           ++it;
         }
       }
-      Conn c;
+      ServerConn c;
       c.fd = cfd;
       c.done = std::make_shared<std::atomic<bool>>(false);
       auto done = c.done;
@@ -593,16 +613,35 @@ class SocketTransport {
   }
 
   void serve(int fd) {
+    Conn c(fd);
     for (;;) {
       FrameHeader h{};
-      if (!read_all(fd, &h, sizeof(h))) return;
-      if (h.magic != kMagic || h.type != kFrameData) return;
+      if (!c.read_all(&h, sizeof(h))) return;
+      if (h.magic != kMagic) return;
+      if (h.type == kFrameHello) {
+        // shm upgrade offer: data = segment name.  Answered on the socket; afterwards both
+        // directions of this connection use the rings (or stay on the socket when refused).
+        if (h.data_len == 0 || h.data_len > 255 || c.uses_shm()) return;
+        std::string name(h.data_len, '\0');
+        if (!c.read_all(&name[0], h.data_len)) return;
+        FrameHeader a{};
+        a.magic = kMagic;
+        a.type = kFrameAck;
+        bool ok = shm_enabled();
+        // reply BEFORE switching the receive side (the client reads the answer on the socket)
+        ok = ok && c.attach_segment(name);
+        if (ok) stats_.shm_conns.fetch_add(1, std::memory_order_relaxed);
+        a.code = ok ? 200 : 501;
+        if (!fd_write_all(fd, &a, sizeof(a))) return;
+        continue;
+      }
+      if (h.type != kFrameData) return;
       std::string job(h.job_len, '\0'), up(h.up_len, '\0'), down(h.down_len, '\0');
-      if (h.job_len && !read_all(fd, &job[0], h.job_len)) return;
-      if (h.up_len && !read_all(fd, &up[0], h.up_len)) return;
-      if (h.down_len && !read_all(fd, &down[0], h.down_len)) return;
+      if (h.job_len && !c.read_all(&job[0], h.job_len)) return;
+      if (h.up_len && !c.read_all(&up[0], h.up_len)) return;
+      if (h.down_len && !c.read_all(&down[0], h.down_len)) return;
       std::string data(h.data_len, '\0');
-      if (h.data_len && !read_all(fd, &data[0], h.data_len)) return;
+      if (h.data_len && !c.read_all(&data[0], h.data_len)) return;
 
       FrameHeader a{};
       a.magic = kMagic;
@@ -624,7 +663,7 @@ class SocketTransport {
       a.data_len = result.size();
       std::string out((const char*)&a, sizeof(a));
       out += result;
-      if (!write_all(fd, out.data(), out.size())) return;
+      if (!c.write_all(out.data(), out.size())) return;
     }
   }
 
@@ -632,12 +671,12 @@ class SocketTransport {
   std::shared_ptr<Mailbox> mailbox_;
   std::mutex mu_;
   std::map<std::string, std::unique_ptr<Peer>> peers_;
-  struct Conn {
+  struct ServerConn {
     int fd = -1;
     std::thread th;
     std::shared_ptr<std::atomic<bool>> done;
   };
-  std::vector<Conn> conns_;
+  std::vector<ServerConn> conns_;
   std::atomic<int> listen_fd_{-1};
   std::atomic<bool> stopped_{false};
   std::thread accept_thread_;

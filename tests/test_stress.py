@@ -163,3 +163,67 @@ def test_sender_reconnects_after_the_receiver_restarts():
     for _ in range(3):  # stop() must be idempotent and must not hang with a retired descriptor
         tx.stop()
     rx2.stop()
+
+
+@pytest.mark.parametrize("ring_kb", [64, 1024])
+def test_shared_memory_data_path_is_negotiated_and_streams_large_messages(monkeypatch, ring_kb):
+    """RAYFED_B200_SHM=1: the socket only carries the handshake / doorbells / EOF, frames move
+    through the SPSC rings — including messages much larger than a ring (streamed while the
+    reader drains) and many small ones (wrap-around)."""
+    import hashlib
+    import os
+
+    from party_utils import free_ports
+    from rayfed_b200.core import native
+
+    monkeypatch.setenv("RAYFED_B200_SHM", "1")
+    monkeypatch.setenv("RAYFED_B200_SHM_RING_KB", str(ring_kb))
+    nat = native()
+    addr = f"127.0.0.1:{free_ports(1)[0]}"
+    mb = nat.Mailbox()
+    rx = nat.SocketTransport("bob", "job", mb)
+    assert not rx.listen(addr)
+    tx = nat.SocketTransport("alice", "job", nat.Mailbox())
+    tx.add_peer("bob", addr, 20, 0.05, 0.2, 1.5, 20.0)
+    big = os.urandom(3 * 1024 * 1024 + 17)  # > ring in both parametrisations
+    acks = [tx.send("bob", "big", "1", big, False, None)]
+    smalls = [os.urandom(1 + (i * 37) % 900) for i in range(3000)]
+    acks += [tx.send("bob", f"s{i}", "2", b, False, None) for i, b in enumerate(smalls)]
+    for a in acks:
+        assert a.result(20.0) == b"OK"
+    got = mb.claim("big", "1").result(5.0)
+    assert hashlib.sha256(got).digest() == hashlib.sha256(big).digest()
+    for i in (0, 1, 1499, 2999):
+        assert mb.claim(f"s{i}", "2").result(5.0) == smalls[i]
+    assert tx.stats()["shm_conns"] == 1 and rx.stats()["shm_conns"] == 1
+    # wrong job is still refused on this path
+    other = nat.SocketTransport("alice", "other-job", nat.Mailbox())
+    other.add_peer("bob", addr, 5, 0.05, 0.2, 1.5, 5.0)
+    with pytest.raises(Exception, match="JobName mis-match"):
+        other.send("bob", "x", "y", b"z", False, lambda data, is_error: (_ for _ in ()).throw(RuntimeError(data.decode()))
+                   if is_error else True).result(5.0)
+    other.stop()
+    tx.stop()
+    rx.stop()
+
+
+def test_shared_memory_offer_is_refused_politely_when_the_server_has_it_off(monkeypatch):
+    from party_utils import free_ports
+    from rayfed_b200.core import native
+
+    nat = native()
+    addr = f"127.0.0.1:{free_ports(1)[0]}"
+    monkeypatch.delenv("RAYFED_B200_SHM", raising=False)
+    mb = nat.Mailbox()
+    rx = nat.SocketTransport("bob", "job", mb)
+    assert not rx.listen(addr)
+    tx = nat.SocketTransport("alice", "job", nat.Mailbox())
+    tx.add_peer("bob", addr, 20, 0.05, 0.2, 1.5, 10.0)
+    monkeypatch.setenv("RAYFED_B200_SHM", "1")  # only the client offers ...
+    ack = tx.send("bob", "a", "b", b"payload", False, None)
+    # ... the serve thread reads the env when the offer arrives; make it see "off"
+    monkeypatch.delenv("RAYFED_B200_SHM", raising=False)
+    assert ack.result(10.0) == b"OK" and mb.claim("a", "b").result(5.0) == b"payload"
+    assert rx.stats()["shm_conns"] in (0, 1)  # env is process-wide: the race decides, both must work
+    tx.stop()
+    rx.stop()
