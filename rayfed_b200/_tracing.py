@@ -15,24 +15,31 @@ import time
 from typing import List, Optional
 
 
+_NVTX = None  # None: unknown, False: unavailable, else torch.cuda.nvtx
+
+
+def _nvtx():
+    global _NVTX
+    if _NVTX is None:
+        try:
+            import torch
+
+            _NVTX = torch.cuda.nvtx if torch.cuda.is_available() else False
+        except Exception:  # noqa: BLE001
+            _NVTX = False
+    return _NVTX
+
+
 @contextlib.contextmanager
 def nvtx_range(name: str):
-    pushed = False
-    try:
-        import torch
-
-        if torch.cuda.is_available():
-            torch.cuda.nvtx.range_push(name)
-            pushed = True
-    except Exception:  # noqa: BLE001
-        pushed = False
+    nv = _nvtx()
+    if nv:
+        nv.range_push(name)
     try:
         yield
     finally:
-        if pushed:
-            import torch
-
-            torch.cuda.nvtx.range_pop()
+        if nv:
+            nv.range_pop()
 
 
 class Timeline:
