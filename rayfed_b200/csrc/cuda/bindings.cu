@@ -484,7 +484,7 @@ PYBIND11_MODULE(_fedcuda, m) {
       [](const std::vector<uint64_t>& b, const std::vector<uint64_t>& at, uint64_t w_base, uint64_t w_base_scales,
          uint64_t out, uint64_t out_scales, uint64_t m_rows, uint64_t n_cols, int r, float scale,
          const std::vector<float>& weights, bool base_fp8, bool out_fp8, uint64_t stream, bool use_tma,
-         uint64_t bcat, uint64_t atcat, int kpad) {
+         uint64_t bcat, uint64_t atcat, int kpad, bool deep) {
         LoraMergeArgs a{};
         fill_peers(a.b, b);
         fill_peers(a.at, at);
@@ -517,7 +517,7 @@ PYBIND11_MODULE(_fedcuda, m) {
           int dev = 0, sms = 0;
           check(cudaGetDevice(&dev), "cudaGetDevice");
           check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "sm count");
-          check(fedk_launch_lora_merge_staged(&a, &maps, P<void>(bcat), P<void>(atcat), kpad, sms,
+          check(fedk_launch_lora_merge_staged(&a, &maps, P<void>(bcat), P<void>(atcat), kpad, sms, deep ? 1 : 0,
                                               (cudaStream_t)(uintptr_t)stream),
                 "fed_lora_merge_staged launch");
         } else if (use_tma && !base_fp8 && !out_fp8 && n_cols % 64 == 0 && (out % 16 == 0) && (w_base % 16 == 0)) {
@@ -535,7 +535,7 @@ PYBIND11_MODULE(_fedcuda, m) {
       py::arg("b"), py::arg("at"), py::arg("w_base"), py::arg("w_base_scales"), py::arg("out"),
       py::arg("out_scales"), py::arg("m"), py::arg("n"), py::arg("r"), py::arg("scale"), py::arg("weights"),
       py::arg("base_fp8"), py::arg("out_fp8"), py::arg("stream"), py::arg("use_tma") = true, py::arg("bcat") = 0,
-      py::arg("atcat") = 0, py::arg("kpad") = 0);
+      py::arg("atcat") = 0, py::arg("kpad") = 0, py::arg("deep") = false);
 
   m.def(
       "local_sgd",

@@ -93,7 +93,7 @@ extern "C" {
 cudaError_t fedk_launch_lora_merge(const LoraMergeArgs* a, cudaStream_t stream);
 cudaError_t fedk_launch_lora_merge_tma(const LoraMergeArgs* a, const void* tma_maps, cudaStream_t stream);
 cudaError_t fedk_launch_lora_merge_staged(const LoraMergeArgs* a, const void* staged_maps, void* bcat, void* atcat,
-                                          int kpad, int sm_count, cudaStream_t stream);
+                                          int kpad, int sm_count, int deep, cudaStream_t stream);
 cudaError_t fedk_launch_push(const PushArgs* a, int mode, int blocks, int use_bulk, cudaStream_t stream);
 cudaError_t fedk_launch_push_mc(const PushArgs* a, const PeerPtrs* flags, int n_flags, int blocks, cudaStream_t stream);
 cudaError_t fedk_launch_unpack(const PushArgs* a, int mode, int blocks, cudaStream_t stream);

@@ -654,8 +654,204 @@ fed_lora_gemm_kernel(const __grid_constant__ LoraMergeArgs a, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------
+// "staged3": same warp roles as fed_lora_gemm_kernel, but the W tiles and the operand tiles
+// live in SEPARATE rings with separate life times.  An operand stage is free the moment its
+// MMAs have retired (tcgen05.commit -> op_empty), long before the epilogue of that tile ran;
+// a W stage is free when its TMA store has finished reading it.  With 2 operand stages and 3 W
+// stages the producer runs two to three tiles ahead, so the per-tile critical path shrinks from
+// max(epilogue, load latency + MMA) towards the epilogue alone.  Shared memory at K = 128:
+// 3 x 32 KB (W) + 2 x 64 KB (A|B) = 224 KB of the 227 KB a CTA may have.
+// OPT-IN (impl="staged3"): written after this round's GPU budget was spent — not yet executed
+// on hardware; fed_lora_gemm_kernel above stays the default until this one has been measured.
+constexpr int kWStages3 = 3;
+constexpr int kOpStages3 = 2;
+
+__global__ void __launch_bounds__(kStgThreads, 1)
+fed_lora_gemm3_kernel(const __grid_constant__ LoraMergeArgs a, const __grid_constant__ LoraStagedMaps maps,
+                      int atoms, int tiles_n, int n_tiles) {
+  extern __shared__ unsigned char lm_smem[];
+  __shared__ __align__(8) uint64_t w_full[kWStages3];
+  __shared__ __align__(8) uint64_t w_empty[kWStages3];
+  __shared__ __align__(8) uint64_t op_full[kOpStages3];
+  __shared__ __align__(8) uint64_t op_empty[kOpStages3];
+  __shared__ __align__(8) uint64_t tmem_full_bar[kStgStages];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[kStgStages];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t raw = lm_smem_u32(lm_smem);
+  unsigned char* w_ring = lm_smem + (((raw + 1023u) & ~1023u) - raw);  // [kWStages3][2 atoms]
+  unsigned char* op_ring = w_ring + (size_t)kWStages3 * 2 * kAtomBytes;  // [kOpStages3][A: atoms | B: atoms]
+  const int op_stage_bytes = 2 * atoms * kAtomBytes;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool has_base = a.w_base != nullptr;
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kWStages3; ++s) {
+      lm_mbar_init(&w_full[s], 1);
+      lm_mbar_init(&w_empty[s], 1);
+    }
+#pragma unroll
+    for (int s = 0; s < kOpStages3; ++s) {
+      lm_mbar_init(&op_full[s], 1);
+      lm_mbar_init(&op_empty[s], 1);
+    }
+#pragma unroll
+    for (int s = 0; s < kStgStages; ++s) {
+      lm_mbar_init(&tmem_full_bar[s], 1);
+      lm_mbar_init(&tmem_empty_bar[s], kStgEpiThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     lm_smem_u32(&tmem_base_slot)),
+                 "n"(kStgStages * kLoraBN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ---------------- producer -----------------------------------------------------------------
+    if (lane == 0) {
+      const uint32_t op_tx = (uint32_t)(2 * atoms) * kAtomBytes;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int t = (int)blockIdx.x + it * (int)gridDim.x;
+        const int m0 = (t / tiles_n) * kLoraBM, n0 = (t % tiles_n) * kLoraBN;
+        // operands first: they gate the MMA, which is the head of the per-tile dependency chain
+        const int os = it % kOpStages3;
+        const uint32_t oph = (uint32_t)(it / kOpStages3) & 1u;
+        lm_mbar_wait(&op_empty[os], oph ^ 1u);
+        unsigned char* sA = op_ring + (size_t)os * op_stage_bytes;
+        unsigned char* sB = sA + (size_t)atoms * kAtomBytes;
+        lm_mbar_expect_tx(&op_full[os], op_tx);
+        for (int k = 0; k < atoms; ++k) {
+          lm_tma_load_2d(sA + (size_t)k * kAtomBytes, &maps.bcat, k * 64, m0, &op_full[os]);
+          lm_tma_load_2d(sB + (size_t)k * kAtomBytes, &maps.atcat, k * 64, n0, &op_full[os]);
+        }
+        const int ws = it % kWStages3;
+        const uint32_t wph = (uint32_t)(it / kWStages3) & 1u;
+        lm_mbar_wait(&w_empty[ws], wph ^ 1u);
+        unsigned char* sW = w_ring + (size_t)ws * 2 * kAtomBytes;
+        if (has_base) {
+          lm_mbar_expect_tx(&w_full[ws], 2u * kAtomBytes);
+          lm_tma_load_2d(sW, &maps.w, n0, m0, &w_full[ws]);
+          lm_tma_load_2d(sW + kAtomBytes, &maps.w, n0 + 64, m0, &w_full[ws]);
+        } else {
+          lm_mbar_arrive(&w_full[ws]);  // nothing to load: the stage is simply handed over
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer -----------------------------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = lm_instr_desc();
+      const int ksteps = (a.n_parties * a.r) >> 4;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int os = it % kOpStages3;
+        const uint32_t oph = (uint32_t)(it / kOpStages3) & 1u;
+        const int ts = it & 1;
+        const uint32_t tph = (uint32_t)(it >> 1) & 1u;
+        lm_mbar_wait(&op_full[os], oph);
+        lm_mbar_wait(&tmem_empty_bar[ts], tph ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_base = lm_smem_u32(op_ring + (size_t)os * op_stage_bytes);
+        const uint32_t b_base = a_base + (uint32_t)atoms * kAtomBytes;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(ts * kLoraBN);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2) * kAtomBytes + (uint32_t)(ks & 3) * 32;
+          lm_mma(tmem_d, lm_make_desc(a_base + off), lm_make_desc(b_base + off), idesc, ks > 0 ? 1u : 0u);
+        }
+        // both commits track every MMA issued above: accumulator ready / operand stage reusable
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         lm_smem_u32(&tmem_full_bar[ts]))
+                     : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         lm_smem_u32(&op_empty[os]))
+                     : "memory");
+      }
+    }
+  } else {
+    // ---------------- epilogue (identical tile math to fed_lora_gemm_kernel) -----------------------
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const float scale = a.scale;
+    const bool storer = threadIdx.x == 64;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int t = (int)blockIdx.x + it * (int)gridDim.x;
+      const int m0 = (t / tiles_n) * kLoraBM, n0 = (t % tiles_n) * kLoraBN;
+      const int ws = it % kWStages3;
+      const uint32_t wph = (uint32_t)(it / kWStages3) & 1u;
+      const int ts = it & 1;
+      const uint32_t tph = (uint32_t)(it >> 1) & 1u;
+      unsigned char* sW = w_ring + (size_t)ws * 2 * kAtomBytes;
+      lm_mbar_wait(&w_full[ws], wph);
+      lm_mbar_wait(&tmem_full_bar[ts], tph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      unsigned char* row = sW + (size_t)h * kAtomBytes + (size_t)r * 128;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        lm_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * kLoraBN + h * 64 + c * 32), v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int chunk = c * 4 + j;
+          uint4* slot = reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4));
+          float f[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[j * 8 + k]) * scale;
+          if (has_base) {
+            const uint4 x = *slot;
+            f[0] += bf16_lo(x.x); f[1] += bf16_hi(x.x); f[2] += bf16_lo(x.y); f[3] += bf16_hi(x.y);
+            f[4] += bf16_lo(x.z); f[5] += bf16_hi(x.z); f[6] += bf16_lo(x.w); f[7] += bf16_hi(x.w);
+          }
+          uint4 y;
+          y.x = pack_bf16x2(f[0], f[1]);
+          y.y = pack_bf16x2(f[2], f[3]);
+          y.z = pack_bf16x2(f[4], f[5]);
+          y.w = pack_bf16x2(f[6], f[7]);
+          *slot = y;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) lm_mbar_arrive(&tmem_empty_bar[ts]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("barrier.sync 1, %0;" ::"n"(kStgEpiThreads) : "memory");
+      if (storer) {
+        lm_tma_store_2d(&maps.out, n0, m0, sW);
+        lm_tma_store_2d(&maps.out, n0 + 64, m0, sW + kAtomBytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // release the stage as early as possible (the TMA only has to have READ it): the
+        // sooner W(i+3) can be issued, the more of epilogue(i+1), (i+2) its latency hides under
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        lm_mbar_arrive(&w_empty[ws]);
+      }
+    }
+    if (storer) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kStgStages * kLoraBN)
+                 : "memory");
+  }
+}
+
 extern "C" cudaError_t fedk_launch_lora_merge_staged(const LoraMergeArgs* a, const void* maps, void* bcat, void* atcat,
-                                                     int kpad, int sm_count, cudaStream_t stream) {
+                                                     int kpad, int sm_count, int deep, cudaStream_t stream) {
   const int K = a->n_parties * a->r;
   if (a->r % 16 != 0 || K > 128 || K < 16 || kpad % 64 != 0 || kpad < K || a->n % 8 != 0 || a->base_fp8 ||
       a->out_fp8)
@@ -673,6 +869,21 @@ extern "C" cudaError_t fedk_launch_lora_merge_staged(const LoraMergeArgs* a, con
     if (e != cudaSuccess) return e;
   }
   // phase 2: persistent GEMM + update
+  const int tiles_m = (int)((a->m + kLoraBM - 1) / kLoraBM), tiles_n = (int)((a->n + kLoraBN - 1) / kLoraBN);
+  const int n_tiles = tiles_m * tiles_n;
+  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
+  if (deep) {
+    const int smem3 = (kWStages3 * 2 + kOpStages3 * 2 * atoms) * kAtomBytes + 1024;
+    static int configured3 = 0;
+    if (configured3 < smem3) {
+      cudaError_t e = cudaFuncSetAttribute(fed_lora_gemm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3);
+      if (e != cudaSuccess) return e;
+      configured3 = smem3;
+    }
+    fed_lora_gemm3_kernel<<<grid, kStgThreads, smem3, stream>>>(*a, *reinterpret_cast<const LoraStagedMaps*>(maps),
+                                                                 atoms, tiles_n, n_tiles);
+    return cudaGetLastError();
+  }
   const int smem = kStgStages * (2 + 2 * atoms) * kAtomBytes + 1024;
   static int configured = 0;
   if (configured < smem) {
@@ -680,9 +891,6 @@ extern "C" cudaError_t fedk_launch_lora_merge_staged(const LoraMergeArgs* a, con
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  const int tiles_m = (int)((a->m + kLoraBM - 1) / kLoraBM), tiles_n = (int)((a->n + kLoraBN - 1) / kLoraBN);
-  const int n_tiles = tiles_m * tiles_n;
-  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
   fed_lora_gemm_kernel<<<grid, kStgThreads, smem, stream>>>(*a, *reinterpret_cast<const LoraStagedMaps*>(maps), atoms,
                                                             tiles_n, n_tiles);
   return cudaGetLastError();

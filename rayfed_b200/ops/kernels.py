@@ -217,7 +217,8 @@ def lora_merge(*, b_ptrs: Sequence[int], at_ptrs: Sequence[int], out_ptr: int, m
     """K3 GEMM (tcgen05/TMEM): ``out = W_base + scale * sum_i w_i * B_i @ A_i`` with the
     operands gathered from every party's adapter buffers. ``B_i``: [m, r]; ``A_i^T``: [n, r].
 
-    ``impl``: ``"staged"`` (gather once + persistent TMA/tcgen05 pipeline; default where it
+    ``impl``: ``"staged3"`` (as ``staged`` with separate 3-deep W / 2-deep operand rings; opt-in,
+    not yet validated on hardware), ``"staged"`` (gather once + persistent TMA/tcgen05 pipeline; default where it
     applies: bf16 base/out, parties*r <= 128), ``"tma"`` (per-tile gather, TMA epilogue),
     ``"direct"`` (per-tile gather, register epilogue; the only one for fp8 base/out).
     ``RAYFED_B200_LORA_IMPL`` overrides the default."""
@@ -232,10 +233,13 @@ def lora_merge(*, b_ptrs: Sequence[int], at_ptrs: Sequence[int], out_ptr: int, m
         raise ValueError("lora_merge needs n % 32 == 0")
     if impl is None:
         impl = os.environ.get("RAYFED_B200_LORA_IMPL", "staged") if use_tma else "direct"
-    if impl not in ("staged", "tma", "direct"):
+    if impl not in ("staged", "staged3", "tma", "direct"):
         raise ValueError(f"unknown lora_merge impl {impl!r}")
+    deep = impl == "staged3"  # decoupled W / operand rings (opt-in until measured on hardware)
+    if deep:
+        impl = "staged"
     if impl == "staged" and (base_fp8 or out_fp8 or p * r > 128):
-        impl = "tma"
+        impl, deep = "tma", False
     sh = _stream_handle(stream)
     bcat = atcat = kpad = 0
     if impl == "staged":
@@ -244,7 +248,7 @@ def lora_merge(*, b_ptrs: Sequence[int], at_ptrs: Sequence[int], out_ptr: int, m
         bcat, atcat = ws[0].data_ptr(), ws[1].data_ptr()
     cuda_ext().lora_merge(list(b_ptrs), list(at_ptrs), w_base_ptr, w_base_scales_ptr, out_ptr, out_scales_ptr, m, n,
                           r, float(scale), [float(w) for w in (weights or [1.0] * p)], bool(base_fp8),
-                          bool(out_fp8), sh, impl != "direct", bcat, atcat, kpad)
+                          bool(out_fp8), sh, impl != "direct", bcat, atcat, kpad, deep)
     if impl == "staged":
         launch_counter.add("fed_lora_gather")
         launch_counter.add("fed_lora_gemm")

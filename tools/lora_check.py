@@ -35,7 +35,7 @@ def main():
         Bc, Ac = torch.cat(Bs, 1), torch.cat(Ats, 1)
         ref = torch.addmm(W.float(), Bc.float(), Ac.float().t(), alpha=1.0 / P).to(torch.bfloat16)
         res = {}
-        for impl in ("staged", "tma", "direct"):
+        for impl in ("staged", "staged3", "tma", "direct"):
             try:
                 Wout.zero_()
                 call = lambda: K.lora_merge(b_ptrs=[b.data_ptr() for b in Bs], at_ptrs=[a.data_ptr() for a in Ats],  # noqa: E731
