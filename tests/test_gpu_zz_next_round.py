@@ -10,6 +10,9 @@ pytestmark = pytest.mark.gpu
 
 if not torch.cuda.is_available():
     pytest.skip("CUDA device required", allow_module_level=True)
+if os.environ.get("RAYFED_B200_NEXT_ROUND_TESTS") != "1":
+    pytest.skip("not yet executed on hardware: opt in with RAYFED_B200_NEXT_ROUND_TESTS=1 "
+                "(tools/round_first_call.sh and tools/round_multi_gpu_call.sh do)", allow_module_level=True)
 if torch.cuda.device_count() < 2 and os.environ.get("RAYFED_B200_TEST_SINGLE_GPU_PARTIES") != "1":
     pytest.skip("multi-party GPU tests need >= 2 GPUs", allow_module_level=True)
 

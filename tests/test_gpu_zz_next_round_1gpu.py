@@ -12,6 +12,9 @@ pytestmark = pytest.mark.gpu
 
 if not torch.cuda.is_available():
     pytest.skip("CUDA device required", allow_module_level=True)
+if os.environ.get("RAYFED_B200_NEXT_ROUND_TESTS") != "1":
+    pytest.skip("not yet executed on hardware: opt in with RAYFED_B200_NEXT_ROUND_TESTS=1 "
+                "(tools/round_first_call.sh and tools/round_multi_gpu_call.sh do)", allow_module_level=True)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

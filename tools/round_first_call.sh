@@ -4,6 +4,7 @@
 # Outputs land in gpurun_out/ (merged back by gpurun).
 set -u
 mkdir -p gpurun_out
+export RAYFED_B200_NEXT_ROUND_TESTS=1   # include the tests that have never run on hardware
 echo "== gpu tests"; timeout 300 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -5 | tee gpurun_out/gpu_tests.txt
 echo "== smoke";     timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/smoke.txt
 echo "== bench N=1"; timeout 300 python bench.py --gpus 1 --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_n1.json
