@@ -194,6 +194,21 @@ def run(rank, nproc, xdir, args):
     t = timed(agg_once, stream, iters=20)
     agg["avg_us"] = t * 1e6
     agg["elems"] = nel
+    # sensitivity to the number of CTAs (all parties use the same value each time): if halving
+    # the grid costs much less than 2x, the kernel is latency- not parallelism-bound
+    sweep = {}
+    for blocks in (37, 74, 111, 148):
+        group.barrier()
+
+        def agg_b():
+            nonlocal epoch
+            K.aggregate(inputs=wbuf.peer_ptrs, outputs=wbuf.peer_ptrs, my_rank=rank, shard_start=rank * shard,
+                        shard_len=shard, kind=K.AGG_AVG, sig_ptr=sig_ptr, sig_peers=sig_peers, epoch=epoch,
+                        status_ptr=status, timeout_ns=int(20e9), device_index=dev, blocks=blocks)
+            epoch += 2
+
+        sweep[str(blocks)] = timed(agg_b, stream, iters=10) * 1e6
+    agg["avg_us_by_blocks"] = sweep
     # bytes over my NVLink: read (N-1)/N * nel*2, write (N-1)/N * nel*2
     agg["link_GBps_per_dir"] = (N - 1) / N * nel * 2 / t / 1e9
     out["aggregate_p2p"] = agg
