@@ -13,6 +13,7 @@
 #pragma once
 #include <pybind11/pybind11.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -111,6 +112,31 @@ inline bool spin_until(Pred&& pred) {
   }
 }
 
+// Adaptive spinning for waits on a Ref (the driver in fed.get, an actor lane parked on its
+// inputs): when this thread's recent waits were short, spin about that long before falling back
+// to the futex — the kernel wake-up it avoids costs more than the wait itself in tiny-task
+// loops.  Long waits (GPU work, slow peers) push the average up and the spin falls back to the
+// base budget, so nothing burns a core while real work is pending.  OFF by default
+// (RAYFED_B200_ADAPTIVE_SPIN_US = cap in microseconds, 0 = off): to be tuned on the target host.
+inline int adaptive_spin_cap_us() {
+  static int v = [] {
+    const char* e = std::getenv("RAYFED_B200_ADAPTIVE_SPIN_US");
+    return e ? std::atoi(e) : 0;
+  }();
+  return v;
+}
+
+template <typename Pred>
+inline bool spin_for(Pred&& pred, int budget_us) {
+  if (budget_us <= 0) return pred();
+  auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    if (pred()) return true;
+    for (int i = 0; i < 32; ++i) cpu_relax();
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(budget_us)) return pred();
+  }
+}
+
 inline bool interpreter_alive() {
   if (!Py_IsInitialized()) return false;
 #if PY_VERSION_HEX >= 0x030D0000
@@ -167,7 +193,24 @@ class Ref : public std::enable_shared_from_this<Ref> {
   // hold the GIL (bindings release it).
   bool wait(double timeout_s) {
     if (done()) return true;
-    if (timeout_s != 0 && spin_until([&] { return done(); })) return true;
+    const int cap = adaptive_spin_cap_us();
+    if (cap <= 0) {
+      if (timeout_s != 0 && spin_until([&] { return done(); })) return true;
+      return block(timeout_s);
+    }
+    // adaptive: spin ~2x this thread's recent wait time, bounded by [base budget, cap]
+    static thread_local double ema_us = 1e12;
+    auto t0 = std::chrono::steady_clock::now();
+    int budget = spin_budget_us();
+    if (ema_us < (double)cap) budget = std::max(budget, std::min(cap, (int)(2.0 * ema_us) + 1));
+    bool ok = timeout_s != 0 && spin_for([&] { return done(); }, budget);
+    if (!ok) ok = block(timeout_s);
+    double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    ema_us = ema_us > 1e11 ? us : 0.75 * ema_us + 0.25 * us;
+    return ok;
+  }
+
+  bool block(double timeout_s) {
     std::unique_lock<std::mutex> lk(mu_);
     if (timeout_s < 0) {
       cv_.wait(lk, [&] { return done(); });
