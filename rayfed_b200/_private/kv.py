@@ -97,3 +97,26 @@ def raw_get(wrapped_key) -> Optional[bytes]:
 def raw_keys():
     with _STORE_LOCK:
         return list(_STORE.keys())
+
+
+# -- migration conveniences (the reference keeps these next to the KV in compatible_utils.py) ------
+def init_ray(address: str = None, **kwargs):
+    """The reference's scripts call ``compatible_utils.init_ray(address='local')`` before
+    ``fed.init`` (compatible_utils.py:51-57).  There is no Ray to start here: accepted, ignored."""
+    return None
+
+
+def _compare_version_strings(version1: str, version2: str) -> bool:
+    """True iff ``version1`` > ``version2`` (numeric, component-wise; missing components = 0)."""
+    def parts(v):
+        out = []
+        for p in str(v).split("."):
+            digits = "".join(ch for ch in p if ch.isdigit())
+            out.append(int(digits) if digits else 0)
+        return out
+
+    a, b = parts(version1), parts(version2)
+    n = max(len(a), len(b))
+    a += [0] * (n - len(a))
+    b += [0] * (n - len(b))
+    return a > b

@@ -181,3 +181,27 @@ def test_top_level_send_recv_exports():
     assert core.get(fed.send("alice", {"k": [1, 2]}, "u", "d"), timeout=10)
     assert core.get(fed.recv("alice", "alice", "u", "d"), timeout=10) == {"k": [1, 2]}
     fed.shutdown()
+
+
+def test_migration_shims_for_reference_style_scripts():
+    """`import rayfed_b200.compat.ray as ray` + `compatible_utils.init_ray(...)`: the Ray calls a
+    rayfed driver script makes keep working without Ray."""
+    import fed._private.compatible_utils as compatible_utils
+    import rayfed_b200.compat.ray as ray
+    from rayfed_b200.core import get_runtime
+
+    assert compatible_utils.init_ray(address="local", resources={"127.0.0.1": 2}) is None
+    assert compatible_utils._compare_version_strings("2.10.0", "2.9.3") is True
+    assert compatible_utils._compare_version_strings("2.0.0", "2.0.0") is False
+    assert compatible_utils._compare_version_strings("1.13.0", "2.0.0") is False
+    ray.init(address="local", num_cpus=2)
+    assert ray.is_initialized()
+    rt = get_runtime()
+    r = rt.submit(lambda x: x * 2, (21,))
+    assert ray.get(r) == 42
+    ready, rest = ray.wait([r], num_returns=1, timeout=1)
+    assert len(ready) == 1 and not rest
+    slow = rt.submit(__import__("time").sleep, (0.5,))
+    with pytest.raises(ray.exceptions.GetTimeoutError):
+        ray.get(slow, timeout=0.01)
+    ray.get(slow)
