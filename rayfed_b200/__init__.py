@@ -17,6 +17,12 @@ import os as _os
 # Streams are multiplexed onto a small number of GPU front-end queues (default 8);
 # kernels that wait for a peer must not sit in front of unrelated local work.
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# A receive parks a stream on a peer's flag (cuStreamWaitValue32).  With CUDA's default LAZY
+# module loading, the *first* launch of any kernel has to load its module, which synchronises
+# with the context — i.e. blocks the launching host thread for as long as a wait is parked
+# (measured on B200: profiles/README.md "stream memory operations").  Between two parties that is
+# a deadlock in the first round.  Load everything up front instead.
+_os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 from .api import get, init, kill, remote, shutdown  # noqa: E402,F401
 from .exceptions import FedRemoteError, FedTaskError  # noqa: E402,F401

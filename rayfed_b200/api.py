@@ -67,12 +67,17 @@ def _signal_handler(signum, frame):
         _shutdown(intended=False)
 
 
-def _pick_transport(cross_silo_comm_dict: Dict, tls_config: Dict) -> str:
+def _transport_choice(cross_silo_comm_dict: Dict) -> str:
     choice = (cross_silo_comm_dict.get("transport") or constants.TRANSPORT_AUTO).lower()
     if choice not in (
         constants.TRANSPORT_AUTO, constants.TRANSPORT_NATIVE, constants.TRANSPORT_GRPC, constants.TRANSPORT_NVLINK
     ):
         raise ValueError(f"Unknown cross_silo_comm.transport '{choice}'.")
+    return choice
+
+
+def _pick_transport(cross_silo_comm_dict: Dict, tls_config: Dict) -> str:
+    choice = _transport_choice(cross_silo_comm_dict)
     if choice == constants.TRANSPORT_AUTO:
         # TLS and L7-gateway style addresses are only spoken by the gRPC transport.
         return constants.TRANSPORT_GRPC if tls_config else constants.TRANSPORT_NATIVE
@@ -183,9 +188,7 @@ def init(
         if receiver_proxy_cls is None:
             if transport == constants.TRANSPORT_GRPC:
                 from .proxy.grpc.grpc_proxy import GrpcReceiverProxy as receiver_proxy_cls
-            elif transport == constants.TRANSPORT_NVLINK or (
-                transport == constants.TRANSPORT_NATIVE and _device_path_wanted(cross_silo_comm_dict, runtime)
-            ):
+            elif _device_path_wanted(cross_silo_comm_dict, tls_config, runtime):
                 from .proxy.nvlink.nvlink_proxy import NvlinkReceiverProxy as receiver_proxy_cls
             else:
                 from .proxy.native.socket_proxy import NativeReceiverProxy as receiver_proxy_cls
@@ -197,9 +200,7 @@ def init(
         if sender_proxy_cls is None:
             if transport == constants.TRANSPORT_GRPC:
                 from .proxy.grpc.grpc_proxy import GrpcSenderProxy as sender_proxy_cls
-            elif transport == constants.TRANSPORT_NVLINK or (
-                transport == constants.TRANSPORT_NATIVE and _device_path_wanted(cross_silo_comm_dict, runtime)
-            ):
+            elif _device_path_wanted(cross_silo_comm_dict, tls_config, runtime):
                 from .proxy.nvlink.nvlink_proxy import NvlinkSenderProxy as sender_proxy_cls
             else:
                 from .proxy.native.socket_proxy import NativeSenderProxy as sender_proxy_cls
@@ -208,48 +209,132 @@ def init(
             proxy_cls=sender_proxy_cls, proxy_config=cross_silo_comm_dict, ready_timeout_second=ready_timeout,
         )
 
-    _maybe_start_device_channel(addresses, party, cross_silo_comm_config, runtime)
+    if receiver_sender_proxy_cls is None and _device_path_negotiable(cross_silo_comm_dict, tls_config):
+        _maybe_start_device_channel(addresses, party, cross_silo_comm_config, runtime, job_name)
 
     if config.get("barrier_on_initializing", False):
         ping_others(addresses=addresses, self_party=party, max_retries=3600)
 
 
-def _maybe_start_device_channel(addresses, party, cfg: CrossSiloMessageConfig, runtime):
-    """Bring up the symmetric heap + DeviceChannel when the NVLink proxies are in
-    use.  Collective: every party reaches this point in ``init``; the handle
-    exchange rides the host transport that was just started (connect retries
-    cover parties that start late)."""
+def _host_identity() -> str:
+    """Same string in every process of one OS instance (containers on a box share the boot id)."""
+    import socket
+
+    boot = ""
+    try:
+        with open("/proc/sys/kernel/random/boot_id") as f:
+            boot = f.read().strip()
+    except OSError:
+        pass
+    return f"{boot}/{socket.gethostname()}" if not os.environ.get("RAYFED_B200_HOST_ID") else os.environ[
+        "RAYFED_B200_HOST_ID"]
+
+
+def _maybe_start_device_channel(addresses, party, cfg: CrossSiloMessageConfig, runtime, job_name: str):
+    """Negotiate, then bring up, the symmetric heap + DeviceChannel.
+
+    Collective: every party whose transport choice is ``auto``/``nvlink`` reaches this point in
+    ``init`` — whether or not it has a device — and all-gathers one capability record over the host
+    transport that was just started (connect retries cover parties that start late).  The device
+    path is used only if EVERY party advertises a CUDA device, the NVLink proxies and the same
+    host; otherwise all of them stay on the host path (a CPU-only or off-box peer cannot map a
+    CUDA IPC/VMM handle).  Reference behaviour being replaced: one gRPC channel per peer,
+    fed/proxy/grpc/grpc_proxy.py:116-141."""
+    import json
+
+    if len(addresses) < 2:
+        return
     rt = get_runtime()
     recv_host = rt.get_named(barriers.receiver_proxy_actor_name())
+    send_host = rt.get_named(barriers.sender_proxy_actor_name())
+    from .proxy.native.socket_proxy import NativeReceiverProxy, NativeSenderProxy
+
+    if not (isinstance(recv_host.proxy, NativeReceiverProxy) and isinstance(send_host.proxy, NativeSenderProxy)):
+        return  # user-supplied proxies: their transport, their rules
     start_unpackers = getattr(recv_host.proxy, "start_unpackers", None)
-    if start_unpackers is None or len(addresses) < 2:
+    has_device = runtime.device is not None and str(runtime.device).startswith("cuda")
+    from .parallel.group import FedExchange, PartyGroup
+
+    dev_index = 0
+    if has_device:
+        import torch
+
+        dev = torch.device(runtime.device)
+        dev_index = dev.index or 0
+    mine = {"device": bool(has_device and start_unpackers is not None), "host": _host_identity()}
+    blob = json.dumps(mine).encode()
+    # Publish my capabilities to every peer with plain proxy sends (not fed sends: the op counters
+    # and the send-checking queue stay untouched).  A party WITHOUT a device stops here — it never
+    # blocks in init for a negotiation it has no stake in; parties with a device wait for everyone.
+    for p in addresses:
+        if p != party:
+            try:
+                send_host.proxy.send(p, blob, f"__caps__/{party}", "__caps__")
+            except Exception as e:  # noqa: BLE001
+                logger.debug(f"capability publish to {p} failed: {e!r}")
+    if not mine["device"]:
+        return
+    wait_s = (cfg.timeout_in_ms or 60000) / 1000.0 * 2
+    caps = []
+    try:
+        for p in addresses:
+            if p == party:
+                caps.append(mine)
+            else:
+                raw = recv_host.proxy.get_data(p, f"__caps__/{p}", "__caps__").result(wait_s)
+                caps.append(json.loads(raw))
+    except Exception as e:  # noqa: BLE001  (a peer that was configured host-only never answers)
+        logger.warning(f"device-path negotiation failed ({e!r}); staying on the host transport.")
+        return
+    group = PartyGroup(list(addresses.keys()), party, FedExchange(), device_index=dev_index)
+    agreed = all(c.get("device") for c in caps) and len({c.get("host") for c in caps}) == 1
+    if not agreed:
+        if has_device:
+            logger.info("NVLink device path not used: "
+                        + ("a peer has no CUDA device" if not all(c.get("device") for c in caps)
+                           else "the parties are not on one host") + "; CUDA tensors ride the host transport.")
+        if _transport_choice({"transport": cfg.transport}) == constants.TRANSPORT_NVLINK:
+            raise RuntimeError("cross_silo_comm.transport='nvlink' needs every party on this box with a CUDA device")
         return
     import torch
 
-    from .parallel.group import FedExchange, PartyGroup
     from .proxy.nvlink import nvlink_proxy
     from .proxy.nvlink.channel import DeviceChannel
 
-    dev = torch.device(runtime.device)
-    torch.cuda.set_device(dev)
-    group = PartyGroup(list(addresses.keys()), party, FedExchange(), device_index=dev.index or 0)
+    torch.cuda.set_device(torch.device(runtime.device))
     channel = DeviceChannel(
         group,
         region_bytes=cfg.device_arena_bytes or (256 << 20),
         wire_dtype=cfg.device_wire_dtype,
         timeout_s=(cfg.timeout_in_ms or 60000) / 1000.0,
+        job_name=job_name,
+        zero_copy=True if cfg.device_zero_copy is None else bool(cfg.device_zero_copy),
+        zero_copy_min_bytes=cfg.device_zero_copy_min_bytes if cfg.device_zero_copy_min_bytes is not None else 64 << 10,
+        consumer_streams=runtime.device_streams,
+        wait_timeout_s=(cfg.device_wait_timeout_ms / 1000.0) if cfg.device_wait_timeout_ms else None,
     )
     nvlink_proxy.attach_channel(channel)
     start_unpackers(channel)
     logger.info(
         f"NVLink device channel up: {group.size} parties, {channel.region_bytes >> 20} MiB/region, "
-        f"backend={channel.buf.backend}"
+        f"backend={channel.buf.backend}, multicast={channel.can_multicast}"
     )
 
 
-def _device_path_wanted(cross_silo_comm_dict: Dict, runtime) -> bool:
-    """The NVLink device path is used when the party was given a CUDA device."""
-    return runtime.device is not None and str(runtime.device).startswith("cuda")
+def _device_path_negotiable(cross_silo_comm_dict: Dict, tls_config) -> bool:
+    """``auto`` (without TLS) and ``nvlink`` negotiate the device path; ``native`` and ``grpc`` are
+    host-only by definition."""
+    choice = _transport_choice(cross_silo_comm_dict)
+    if choice == constants.TRANSPORT_NVLINK:
+        return True
+    return choice == constants.TRANSPORT_AUTO and not tls_config
+
+
+def _device_path_wanted(cross_silo_comm_dict: Dict, tls_config, runtime) -> bool:
+    """Use the NVLink proxies (a superset of the native ones: without a channel they send plain
+    host frames) when this party has a CUDA device and the device path is negotiable."""
+    return (_device_path_negotiable(cross_silo_comm_dict, tls_config) and runtime.device is not None
+            and str(runtime.device).startswith("cuda"))
 
 
 def shutdown():

@@ -106,6 +106,12 @@ class CrossSiloMessageConfig:
         device_wire_dtype: optional on-the-wire cast fused into the push kernel
             (``None`` | ``bf16`` | ``fp8_e4m3``).
         device_min_bytes: CUDA tensors smaller than this ride the host frame.
+        device_zero_copy: hand received tensors out as views of the arena (default True);
+            ``False`` always copies them out with the unpack kernel.
+        device_zero_copy_min_bytes: blocks smaller than this are copied out (default 64 KiB).
+        device_wait_timeout_ms: patience of the watchdog behind a parked device receive
+            (default: 10 x ``timeout_in_ms``, at least 10 min — a receive legitimately lasts as
+            long as the producer's device work).
     """
 
     proxy_max_restarts: int = None
@@ -129,6 +135,9 @@ class CrossSiloMessageConfig:
     device_arena_bytes: Optional[int] = None
     device_wire_dtype: Optional[str] = None
     device_min_bytes: Optional[int] = None
+    device_zero_copy: Optional[bool] = None
+    device_zero_copy_min_bytes: Optional[int] = None
+    device_wait_timeout_ms: Optional[int] = None
 
     def __json__(self):
         return json.dumps(self.__dict__)

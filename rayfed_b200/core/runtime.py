@@ -15,11 +15,13 @@ actors, ordered mailbox,      :meth:`PartyRuntime.create_actor` → C++ ordered 
 named actors                  :meth:`PartyRuntime.register_named` / ``get_named``
 ===========================  =================================================
 
-CUDA semantics: a task that runs on a lane with a stream returns its value
-wrapped with the CUDA event recorded after the body; a consumer on another
-stream waits on that event *on the device* (``cudaStreamWaitEvent``) — the host
+CUDA semantics live in the C++ scheduler, not here: a worker
+thread of a device party owns a CUDA stream; the executor records a CUDA event
+after each task body and attaches it to the output `Ref`s; before a consumer's
+body runs — and before the GIL is taken — the executor makes the consumer's
+stream wait for the events of its inputs (``cudaStreamWaitEvent``).  The host
 never blocks for a device→device dependency, so local tasks overlap in-flight
-pushes.
+pushes (``csrc/core/executor.h``, ``csrc/core/device_hooks.h``).
 """
 from __future__ import annotations
 
@@ -95,46 +97,28 @@ def is_refs(objs) -> bool:
     return False
 
 
-class _Produced:
-    """A value plus the CUDA event that orders it after its producer stream."""
+def DeviceValue(value, event: int = 0, stream: int = 0, owner=None):
+    """``value`` + the CUDA event (raw handle) that orders it after its producer — what a
+    device-aware transport's decoder returns and what the sender hand-off receives.  A `Ref`
+    completed with one keeps the plain value and adopts the event (csrc/core/ref.h)."""
+    return native().DeviceValue(value, int(event), int(stream), owner)
 
-    __slots__ = ("value", "event", "stream")
 
-    def __init__(self, value, event, stream=None):
-        self.value = value
-        self.event = event
-        self.stream = stream  # the stream the producer ran on
+def is_device_value(obj) -> bool:
+    return type(obj) is native().DeviceValue
 
 
 def _wrap_task_error(exc: BaseException):
     return FedTaskError.from_exception(exc)
 
 
-class _StreamContext:
-    """Lazily creates a CUDA stream for a lane / pool thread."""
-
-    def __init__(self, device: Optional[str]):
-        self.device = device
-        self._stream = None
-
-    def stream(self):
-        if self.device is None:
-            return None
-        if self._stream is None:
-            import torch
-
-            self._stream = torch.cuda.Stream(device=self.device)
-        return self._stream
-
-
 class ActorHandle:
     """Local actor: an instance pinned to one ordered lane."""
 
-    def __init__(self, runtime: "PartyRuntime", lane_id: int, name: str, stream_ctx: _StreamContext):
+    def __init__(self, runtime: "PartyRuntime", lane_id: int, name: str):
         self._runtime = runtime
         self._lane_id = lane_id
         self._name = name
-        self._stream_ctx = stream_ctx
         self._instance = None
         self._dead = False
         self._ready_ref = None
@@ -152,7 +136,7 @@ class ActorHandle:
 
             call.__name__ = f"{self._name}.{method_name}"
             self._callers[method_name] = call
-        return self._runtime._submit(self._lane_id, call, args, kwargs, num_returns, self._stream_ctx)
+        return self._runtime._submit(self._lane_id, call, args, kwargs, num_returns)
 
     def submit_call(self, fn: Callable, args: tuple, kwargs: dict, num_returns: int = 1):
         """Run ``fn(instance, *args)`` in mailbox order (used by proxy hosts)."""
@@ -160,7 +144,7 @@ class ActorHandle:
         def call(*a, **kw):
             return fn(self._instance, *a, **kw)
 
-        return self._runtime._submit(self._lane_id, call, args, kwargs, num_returns, self._stream_ctx)
+        return self._runtime._submit(self._lane_id, call, args, kwargs, num_returns)
 
     def kill(self):
         if not self._dead:
@@ -186,7 +170,7 @@ class PartyRuntime:
         self._device = device
         self._named: Dict[str, Any] = {}
         self._named_lock = threading.Lock()
-        self._pool_tls = threading.local()
+        self._lane_streams = []
         self._actor_count = 0
         self._closed = False
 
@@ -196,26 +180,54 @@ class PartyRuntime:
         return self._device
 
     def set_device(self, device: Optional[str]):
+        """Bind this party to a CUDA device.  From here on every worker thread owns a CUDA
+        stream, every task result carries the event recorded after its body, and the C++
+        executor orders consumer streams after producer events (``cudaStreamWaitEvent``,
+        issued before the GIL is taken) — the host never blocks for a device->device edge."""
         self._device = device
+        if device is not None and str(device).startswith("cuda"):
+            from ..ops.kernels import cuda_ext
+
+            native().set_device_hooks(cuda_ext().device_hooks())
+            self._executor.set_lane_thread_init(0, self._thread_init())
+        else:
+            self._executor.set_lane_thread_init(0, None)
+
+    def _thread_init(self):
+        """Runs once on each worker thread: device + a stream of its own as the thread's current
+        stream; returns the raw stream handle to the executor."""
+        if self._device is None or not str(self._device).startswith("cuda"):
+            return None
+        device = self._device
+
+        def init():
+            import torch
+
+            dev = torch.device(device)
+            torch.cuda.set_device(dev)
+            stream = torch.cuda.Stream(device=dev)
+            torch.cuda.set_stream(stream)
+            with self._named_lock:
+                self._lane_streams.append(stream)
+            return stream.cuda_stream
+
+        return init
+
+    def device_streams(self) -> List[int]:
+        """Raw handles of every stream the runtime's workers run tasks on."""
+        with self._named_lock:
+            return [s.cuda_stream for s in self._lane_streams]
 
     # -- tasks -----------------------------------------------------------------
-    def _pool_stream_ctx(self) -> Optional[_StreamContext]:
-        if self._device is None:
-            return None
-        return _StreamContext(self._device)  # resolved per pool thread in the trampoline
-
-    def _submit(self, lane_id, fn, args, kwargs, num_returns, stream_ctx):
+    def _submit(self, lane_id, fn, args, kwargs, num_returns):
         if _tracing._TRACER is not None:
             fn = _tracing.traced_task(fn, getattr(fn, "__name__", "task"))
-        if stream_ctx is not None and stream_ctx.device is not None:
-            fn = _device_trampoline(fn, stream_ctx, self._pool_tls if lane_id == 0 else None)
         refs = self._executor.submit(lane_id, fn, tuple(args), kwargs or None, num_returns)
         return refs[0] if num_returns <= 1 else list(refs)
 
     def submit(self, fn: Callable, args: Sequence = (), kwargs: Optional[dict] = None, num_returns: int = 1):
         """Stateless task: runs on the shared pool once its `Ref` args resolve."""
-        ctx = _StreamContext(self._device) if self._device is not None else None
-        return self._submit(0, fn, args, kwargs, num_returns, ctx)
+        return self._submit(0, fn, args, kwargs, num_returns)
 
     # -- actors ----------------------------------------------------------------
     def create_actor(self, cls, args: Sequence = (), kwargs: Optional[dict] = None, *, name: str = "",
@@ -223,15 +235,15 @@ class PartyRuntime:
         self._actor_count += 1
         if not name:
             name = f"{getattr(cls, '__name__', 'actor')}#{self._actor_count}"
-        lane_id = self._executor.create_lane(name, max_concurrency or 1)
-        handle = ActorHandle(self, lane_id, name, _StreamContext(self._device))
+        lane_id = self._executor.create_lane(name, max_concurrency or 1, self._thread_init())
+        handle = ActorHandle(self, lane_id, name)
 
         def construct(*a, **kw):
             handle._instance = cls(*a, **kw)
             return True
 
         construct.__name__ = f"{name}.__init__"
-        handle._ready_ref = self._submit(lane_id, construct, args, kwargs, 1, handle._stream_ctx)
+        handle._ready_ref = self._submit(lane_id, construct, args, kwargs, 1)
         return handle
 
     # -- named registry (ray.get_actor analogue) -------------------------------
@@ -280,50 +292,6 @@ class PartyRuntime:
         self._executor.shutdown(wait, timeout)
 
 
-def _device_trampoline(fn, stream_ctx: _StreamContext, pool_tls):
-    """Run ``fn`` on the lane's CUDA stream; order device inputs/outputs by events."""
-
-    def run(*args, **kwargs):
-        import torch
-
-        if pool_tls is not None:
-            ctx = getattr(pool_tls, "ctx", None)
-            if ctx is None or ctx.device != stream_ctx.device:
-                ctx = _StreamContext(stream_ctx.device)
-                pool_tls.ctx = ctx
-        else:
-            ctx = stream_ctx
-        stream = ctx.stream()
-        with torch.cuda.device(stream.device), torch.cuda.stream(stream):
-            args = tuple(_consume(a, stream) for a in args)
-            if kwargs:
-                kwargs = {k: _consume(v, stream) for k, v in kwargs.items()}
-            out = fn(*args, **kwargs)
-            ev = torch.cuda.Event()
-            ev.record(stream)
-        return _Produced(out, ev, stream)
-
-    run.__name__ = getattr(fn, "__name__", "task")
-    return run
-
-
-def _consume(x, stream):
-    if type(x) is _Produced:
-        if x.event is not None:
-            stream.wait_event(x.event)
-        return x.value
-    return x
-
-
-def _unwrap_for_host(x):
-    """Host-side read of a task result: device work must be complete."""
-    if type(x) is _Produced:
-        if x.event is not None:
-            x.event.synchronize()
-        return x.value
-    return x
-
-
 # ---------------------------------------------------------------------------
 _runtime: Optional[PartyRuntime] = None
 _runtime_lock = threading.Lock()
@@ -358,13 +326,21 @@ def _atexit_shutdown():
 atexit.register(_atexit_shutdown)
 
 
+def _host_value(ref, t: float):
+    """Host-side read of a task result: its device work must be complete."""
+    v = ref.result(t)
+    if ref.cuda_event:
+        ref.device_sync()  # GIL released
+    return v
+
+
 def get(refs, timeout: Optional[float] = None):
     """``ray.get`` analogue for a Ref or a list of Refs."""
     t = -1.0 if timeout is None else float(timeout)
     try:
         if is_ref(refs):
-            return _unwrap_for_host(refs.result(t))
-        return [_unwrap_for_host(r.result(t)) for r in refs]
+            return _host_value(refs, t)
+        return [_host_value(r, t) for r in refs]
     except TimeoutError as e:
         raise FedGetTimeoutError(str(e)) from None
 

@@ -65,7 +65,16 @@ struct Lane : public std::enable_shared_from_this<Lane> {
   std::atomic<int> busy{0};
   std::atomic<int> qsize{0};     // mirrors q.size() for lock-free spinning
   std::atomic<bool> wake{false};  // set on stop/kill
-  ~Lane() { safe_release(kill_error); }
+  // Device lanes: `thread_init()` runs once per worker thread (GIL held) — it binds the thread to
+  // the party's CUDA device, makes a stream of its own the thread's current stream and returns the
+  // stream handle.  Bumping `init_gen` makes running workers re-initialise before their next task
+  // (fed.init sets the device after the pool threads exist).
+  py::object thread_init;
+  std::atomic<uint64_t> init_gen{0};
+  ~Lane() {
+    safe_release(kill_error);
+    safe_release(thread_init);
+  }
 };
 using LanePtr = std::shared_ptr<Lane>;
 
@@ -81,10 +90,14 @@ class Executor : public std::enable_shared_from_this<Executor> {
   }
   ~Executor() { safe_release(wrap_error_); }
 
-  int create_lane(const std::string& name, int concurrency) {
+  int create_lane(const std::string& name, int concurrency, py::object thread_init = py::none()) {
     auto lane = std::make_shared<Lane>();
     lane->name = name;
     lane->ordered = true;
+    if (!thread_init.is_none()) {
+      lane->thread_init = std::move(thread_init);
+      lane->init_gen.store(1);
+    }
     int id;
     {
       std::lock_guard<std::mutex> lk(mu_);
@@ -144,6 +157,14 @@ class Executor : public std::enable_shared_from_this<Executor> {
       }
     }
     return outs;
+  }
+
+  // GIL held. (Re)bind a lane's worker threads to a device stream; None detaches.
+  void set_lane_thread_init(int lane_id, py::object thread_init) {
+    LanePtr lane = get_lane(lane_id);
+    std::lock_guard<std::mutex> lk(lane->mu);
+    lane->thread_init = thread_init.is_none() ? py::object() : std::move(thread_init);
+    lane->init_gen.fetch_add(1);
   }
 
   // Drop an actor's mailbox: queued tasks fail with `error`; later submits too.
@@ -274,13 +295,65 @@ class Executor : public std::enable_shared_from_this<Executor> {
         for (auto& d : t->deps) d->wait(-1.0);
       }
       if (!interpreter_alive()) return;
+      if (lane->init_gen.load(std::memory_order_acquire) != tl_init_gen()) bind_thread(*lane);
       run(*t, *stats, wrap);
       lane->busy.fetch_sub(1);
       t.reset();
     }
   }
 
+  // ---- device ordering (device_hooks.h) ---------------------------------------------------
+  static uint64_t& tl_stream() {
+    static thread_local uint64_t s = 0;
+    return s;
+  }
+  static uint64_t& tl_init_gen() {
+    static thread_local uint64_t g = 0;
+    return g;
+  }
+
+  static void bind_thread(Lane& lane) {
+    py::gil_scoped_acquire gil;
+    py::object init;
+    uint64_t gen;
+    {
+      std::lock_guard<std::mutex> lk(lane.mu);
+      init = lane.thread_init;
+      gen = lane.init_gen.load();
+    }
+    uint64_t stream = 0;
+    if (init) {
+      try {
+        stream = init().cast<uint64_t>();
+      } catch (py::error_already_set& e) {
+        e.discard_as_unraisable("fedcore lane thread_init");
+      }
+    }
+    tl_stream() = stream;
+    tl_init_gen() = gen;
+  }
+
+  // Make this worker's stream wait for the device completion of every input that has one.
+  // `seen` remembers which inputs were handled so the post-decode pass only adds new ones.
+  static void wait_device_inputs(const std::vector<RefPtr>& deps, uint64_t stream, std::vector<const Ref*>& seen) {
+    const DeviceHooks* h = device_hooks();
+    if (!h || !stream) return;
+    for (auto& d : deps) {
+      if (std::find(seen.begin(), seen.end(), d.get()) != seen.end()) continue;
+      DeviceEventPtr e = d->device_event();
+      if (!e || !e->event) continue;
+      seen.push_back(d.get());
+      if (e->stream == stream) continue;  // same stream: already ordered
+      h->stream_wait_event(stream, e->event);
+    }
+  }
+
   static void run(Task& t, ExecStats& stats, py::object& wrap) {
+    // Device dependencies first, and without the GIL: the consumer stream is ordered after the
+    // producers' events by the scheduler itself (no Python trampoline, no host blocking).
+    const uint64_t stream = tl_stream();
+    std::vector<const Ref*> dev_seen;
+    if (stream) wait_device_inputs(t.deps, stream, dev_seen);
     pre_gil_spin();  // see ref.h: avoid sleeping on the GIL while the driver is mid-submit
     py::gil_scoped_acquire gil;
     py::object dep_err;
@@ -322,12 +395,29 @@ class Executor : public std::enable_shared_from_this<Executor> {
     // fall asleep on the GIL instead of running.
     std::vector<py::object> values;
     py::object error;
+    DeviceEventPtr produced;
     if (dep_err) {
       // An upstream task failed: the failure flows along the edge (Ray semantics).
       error = dep_err;
     } else {
+      // inputs that were still raw bytes above got their event from the decoder just now
+      if (stream) wait_device_inputs(t.deps, stream, dev_seen);
       try {
         py::object res = t.fn(*call_args, **call_kwargs);
+        if (stream) {
+          // one event after the body orders every output of this task on the device
+          if (const DeviceHooks* h = device_hooks()) {
+            uint64_t ev = EventPool::get().acquire(h);
+            if (ev && h->event_record(ev, stream) == 0) {
+              produced = std::make_shared<DeviceEvent>();
+              produced->event = ev;
+              produced->stream = stream;
+              produced->pooled = true;
+            } else if (ev) {
+              EventPool::get().release(ev);
+            }
+          }
+        }
         size_t n = t.outs.size();
         if (n == 1) {
           values.push_back(std::move(res));
@@ -374,7 +464,10 @@ class Executor : public std::enable_shared_from_this<Executor> {
       for (auto& o : t.outs) o->set_error(error);
     } else {
       stats.completed.fetch_add(1, std::memory_order_relaxed);
-      for (size_t i = 0; i < t.outs.size(); ++i) t.outs[i]->set_value(std::move(values[i]));
+      for (size_t i = 0; i < t.outs.size(); ++i) {
+        if (produced) t.outs[i]->set_device_event(produced);
+        t.outs[i]->set_value(std::move(values[i]));
+      }
     }
   }
 

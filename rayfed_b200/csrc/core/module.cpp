@@ -129,9 +129,79 @@ PYBIND11_MODULE(_fedcore, m) {
       .def(
           "set_raw", [](Ref& r, py::bytes b, bool is_error) { return r.set_raw(std::string(b), is_error); },
           py::arg("data"), py::arg("is_error") = false)
+      // ---- device ordering (device_hooks.h) ----
+      .def_property_readonly("cuda_event",
+                             [](Ref& r) {
+                               DeviceEventPtr e = r.device_event();
+                               return e ? e->event : (uint64_t)0;
+                             })
+      .def_property_readonly("cuda_stream",
+                             [](Ref& r) {
+                               DeviceEventPtr e = r.device_event();
+                               return e ? e->stream : (uint64_t)0;
+                             })
+      .def(
+          "set_cuda_event",
+          [](Ref& r, uint64_t event, uint64_t stream, py::object owner) {
+            auto e = std::make_shared<DeviceEvent>();
+            e->event = event;
+            e->stream = stream;
+            e->owner = owner.is_none() ? py::object() : owner;
+            r.set_device_event(std::move(e));
+          },
+          py::arg("event"), py::arg("stream") = 0, py::arg("owner") = py::none())
+      .def("device_sync",
+           [](RefPtr r) {
+             py::gil_scoped_release rel;
+             if (!r->device_sync()) throw std::runtime_error("cudaEventSynchronize failed on a fed Ref");
+           })
       .def("set_decoder", &Ref::set_decoder)
       .def("set_decoded_exc_is_error", &Ref::set_decoded_exc_is_error)
       .def("add_done_callback", &Ref::add_done_callback);
+
+  py::class_<DeviceValue>(m, "DeviceValue",
+                          "value + the CUDA event (and stream) that orders it; a Ref completed with one "
+                          "keeps the plain value and adopts the event")
+      .def(py::init([](py::object value, uint64_t event, uint64_t stream, py::object owner) {
+             DeviceValue dv;
+             dv.value = std::move(value);
+             dv.event = event;
+             dv.stream = stream;
+             dv.owner = owner.is_none() ? py::object() : owner;
+             return dv;
+           }),
+           py::arg("value"), py::arg("event") = 0, py::arg("stream") = 0, py::arg("owner") = py::none())
+      .def_readwrite("value", &DeviceValue::value)
+      .def_readwrite("event", &DeviceValue::event)
+      .def_readwrite("stream", &DeviceValue::stream)
+      .def_readwrite("owner", &DeviceValue::owner);
+
+  // The CUDA calls the scheduler needs, published by _fedcuda as a capsule (no link dependency).
+  m.def("set_device_hooks", [](py::object capsule) {
+    const DeviceHooks* old = device_hooks();
+    const DeviceHooks* h = nullptr;
+    if (!capsule.is_none()) {
+      h = static_cast<const DeviceHooks*>(PyCapsule_GetPointer(capsule.ptr(), "rayfed_b200.device_hooks"));
+      if (!h) throw py::error_already_set();
+    }
+    if (h == old) return;
+    EventPool::get().drop_all(old);
+    g_device_hooks.store(h, std::memory_order_release);
+  });
+  m.def("install_fake_device_hooks", [] {
+    const DeviceHooks* old = device_hooks();
+    if (old == fake_device_hooks()) return;
+    EventPool::get().drop_all(old);
+    g_device_hooks.store(fake_device_hooks(), std::memory_order_release);
+  });
+  m.def("has_device_hooks", [] { return device_hooks() != nullptr; });
+  m.def("fake_device_log", [](bool clear) {
+    FakeDeviceLog& l = fake_device_log();
+    std::lock_guard<std::mutex> lk(l.mu);
+    std::vector<std::string> out = l.lines;
+    if (clear) l.lines.clear();
+    return out;
+  }, py::arg("clear") = false);
 
   m.def("wait_refs", &wait_refs, py::arg("refs"), py::arg("num_ready") = 1, py::arg("timeout") = -1.0);
 
@@ -143,7 +213,9 @@ PYBIND11_MODULE(_fedcore, m) {
 
   py::class_<Executor, std::shared_ptr<Executor>>(m, "Executor")
       .def(py::init<int, py::object>(), py::arg("pool_threads") = 4, py::arg("wrap_error") = py::none())
-      .def("create_lane", &Executor::create_lane, py::arg("name"), py::arg("concurrency") = 1)
+      .def("create_lane", &Executor::create_lane, py::arg("name"), py::arg("concurrency") = 1,
+           py::arg("thread_init") = py::none())
+      .def("set_lane_thread_init", &Executor::set_lane_thread_init, py::arg("lane"), py::arg("thread_init"))
       .def("submit", &Executor::submit, py::arg("lane"), py::arg("fn"), py::arg("args"), py::arg("kwargs"),
            py::arg("num_returns") = 1)
       .def("kill_lane", &Executor::kill_lane)

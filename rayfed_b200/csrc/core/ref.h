@@ -25,6 +25,8 @@
 #include <string>
 #include <vector>
 
+#include "device_hooks.h"
+
 namespace py = pybind11;
 
 namespace fedcore {
@@ -158,6 +160,30 @@ inline void safe_release(py::object& o) {
   o = py::object();
 }
 
+// The device-side completion of a value: "everything the producer enqueued on `stream`
+// before `event` was recorded".  Shared by all outputs of one task.
+struct DeviceEvent {
+  uint64_t event = 0;
+  uint64_t stream = 0;  // the producer's stream (a consumer on the same stream needs no wait)
+  bool pooled = false;  // ours (goes back to the pool) vs borrowed (`owner` keeps it alive)
+  py::object owner;     // e.g. the torch.cuda.Event a transport recorded
+  ~DeviceEvent() {
+    if (pooled && event) EventPool::get().release(event);
+    safe_release(owner);
+  }
+};
+using DeviceEventPtr = std::shared_ptr<DeviceEvent>;
+
+// Python-visible carrier "value + the CUDA event that orders it": what a transport's decoder
+// returns for a payload that landed through the device channel, and what the sender hand-off
+// receives.  A Ref completed with one keeps the plain value and adopts the event.
+struct DeviceValue {
+  py::object value;
+  uint64_t event = 0;
+  uint64_t stream = 0;
+  py::object owner;
+};
+
 class Ref : public std::enable_shared_from_this<Ref> {
  public:
   Ref() = default;
@@ -178,7 +204,10 @@ class Ref : public std::enable_shared_from_this<Ref> {
 
   // ---- completion (callable from any thread) -------------------------------
   // GIL must be held by the caller for the py::object flavours.
-  bool set_value(py::object v) { return complete(RefState::kValue, std::move(v), std::string(), false); }
+  bool set_value(py::object v) {
+    adopt_device_value(v);
+    return complete(RefState::kValue, std::move(v), std::string(), false);
+  }
   bool set_error(py::object exc) { return complete(RefState::kError, std::move(exc), std::string(), true); }
   // No GIL needed: transport threads hand over bytes.
   bool set_raw(std::string bytes, bool is_error) {
@@ -267,6 +296,7 @@ class Ref : public std::enable_shared_from_this<Ref> {
     }
     // A decoder may itself hand back an exception instance for error frames.
     if (!err && PyExceptionInstance_Check(out.ptr()) && decoded_exc_is_error_) err = true;
+    if (!err) adopt_device_value(out);
     value_ = std::move(out);
     std::string().swap(raw_);
     state_.store(err ? (int)RefState::kError : (int)RefState::kValue, std::memory_order_release);
@@ -297,6 +327,18 @@ class Ref : public std::enable_shared_from_this<Ref> {
   }
 
   void set_decoded_exc_is_error(bool v) { decoded_exc_is_error_ = v; }
+
+  // ---- device ordering -------------------------------------------------------
+  // Attach BEFORE completing the Ref (the executor does) or from the decoder.
+  void set_device_event(DeviceEventPtr e) { std::atomic_store(&dev_event_, std::move(e)); }
+  DeviceEventPtr device_event() const { return std::atomic_load(&dev_event_); }
+  // Host-side read barrier: block until the producer's device work is complete. No GIL needed.
+  bool device_sync() {
+    DeviceEventPtr e = device_event();
+    const DeviceHooks* h = device_hooks();
+    if (!e || !e->event || !h) return true;
+    return h->event_synchronize(e->event) == 0;
+  }
 
  private:
   bool complete(RefState st, py::object v, std::string raw, bool is_err) {
@@ -329,7 +371,23 @@ class Ref : public std::enable_shared_from_this<Ref> {
     return true;
   }
 
+  // GIL held. `v` may be a DeviceValue: keep the plain value, adopt the event.
+  void adopt_device_value(py::object& v) {
+    if (!v || !py::isinstance<DeviceValue>(v)) return;
+    DeviceValue& dv = v.cast<DeviceValue&>();
+    if (dv.event) {
+      auto e = std::make_shared<DeviceEvent>();
+      e->event = dv.event;
+      e->stream = dv.stream;
+      e->owner = dv.owner;
+      set_device_event(std::move(e));
+    }
+    py::object inner = dv.value;
+    v = std::move(inner);
+  }
+
   std::atomic<int> state_{(int)RefState::kPending};
+  DeviceEventPtr dev_event_;
   std::mutex mu_;
   std::mutex decode_mu_;
   std::condition_variable cv_;

@@ -391,6 +391,30 @@ cudaError_t fedk_launch_aggregate(const AggArgs* a, int blocks, cudaStream_t str
   return cudaGetLastError();
 }
 
+
+#define FEDK_PRELOAD(fn)                                                        \
+  do {                                                                          \
+    cudaFuncAttributes at_;                                                     \
+    cudaError_t e_ = cudaFuncGetAttributes(&at_, fn);                           \
+    if (e_ != cudaSuccess) return e_;                                           \
+  } while (0)
+
+cudaError_t fedk_preload_aggregate() {
+  FEDK_PRELOAD((fed_aggregate_kernel<true, 1, 2, true>));
+  FEDK_PRELOAD((fed_aggregate_kernel<true, 1, 8, false>));
+  FEDK_PRELOAD((fed_aggregate_kernel<false, 1, 2, true>));
+  FEDK_PRELOAD((fed_aggregate_kernel<false, 1, 8, false>));
+  FEDK_PRELOAD((fed_aggregate_kernel<false, 2, 1, true>));
+  FEDK_PRELOAD((fed_aggregate_kernel<false, 2, 4, false>));
+  FEDK_PRELOAD((fed_aggregate_kernel<false, 4, 1, true>));
+  FEDK_PRELOAD((fed_aggregate_kernel<false, 4, 2, false>));
+  FEDK_PRELOAD((fed_aggregate_kernel<false, 8, 1, true>));
+  FEDK_PRELOAD((fed_aggregate_kernel<false, 8, 1, false>));
+  FEDK_PRELOAD(fed_barrier_kernel);
+  FEDK_PRELOAD(fed_local_sgd_kernel);
+  return cudaSuccess;
+}
+
 cudaError_t fedk_launch_barrier(const AggArgs* a, cudaStream_t stream) {
   fed_barrier_kernel<<<1, 32, 0, stream>>>(*a);
   return cudaGetLastError();

@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "../core/device_hooks.h"
 #include "kernels.h"
 
 namespace py = pybind11;
@@ -61,6 +62,43 @@ void cu_check(CUresult r, const char* what) {
 }
 
 size_t round_up(size_t x, size_t g) { return (x + g - 1) / g * g; }
+
+void fill_desc(PushArgs& a, uint64_t desc_dst, const std::string& desc) {
+  a.desc_dst = P<void>(desc_dst);
+  if (!desc.empty()) {
+    if (desc.size() != sizeof(PushDesc)) throw std::runtime_error("descriptor must be 64 bytes");
+    std::memcpy(&a.desc, desc.data(), sizeof(PushDesc));
+  }
+}
+
+// ---- the scheduler's CUDA calls (csrc/core/device_hooks.h) ---------------------------------
+const fedcore::DeviceHooks* cuda_device_hooks() {
+  static fedcore::DeviceHooks h = {
+      [](uint64_t* ev) -> int {
+        cudaEvent_t e = nullptr;
+        cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        *ev = (uint64_t)(uintptr_t)e;
+        return (int)r;
+      },
+      [](uint64_t ev) -> int { return (int)cudaEventDestroy((cudaEvent_t)(uintptr_t)ev); },
+      [](uint64_t ev, uint64_t stream) -> int {
+        return (int)cudaEventRecord((cudaEvent_t)(uintptr_t)ev, (cudaStream_t)(uintptr_t)stream);
+      },
+      [](uint64_t stream, uint64_t ev) -> int {
+        return (int)cudaStreamWaitEvent((cudaStream_t)(uintptr_t)stream, (cudaEvent_t)(uintptr_t)ev, 0);
+      },
+      [](uint64_t ev) -> int { return (int)cudaEventSynchronize((cudaEvent_t)(uintptr_t)ev); },
+      [](uint64_t ev) -> int {
+        cudaError_t r = cudaEventQuery((cudaEvent_t)(uintptr_t)ev);
+        if (r == cudaErrorNotReady) {
+          cudaGetLastError();
+          return 1;
+        }
+        return r == cudaSuccess ? 0 : (int)r;
+      },
+  };
+  return &h;
+}
 
 // [rows, cols] row-major bf16 matrix -> TMA descriptor with a {64 cols, 128 rows} box, SWIZZLE_128B.
 CUtensorMap make_bf16_tile_map(uint64_t ptr, uint64_t rows, uint64_t cols) {
@@ -155,6 +193,86 @@ PYBIND11_MODULE(_fedcuda, m) {
     check(cudaMemcpy(P<void>(p), &v, 4, cudaMemcpyHostToDevice), "cudaMemcpy");
   });
   m.def("memset", [](uint64_t p, int byte, size_t n) { check(cudaMemset(P<void>(p), byte, n), "cudaMemset"); });
+
+  // ---- streams, events, stream memory operations ---------------------------------
+  m.def("device_hooks", [] {
+    return py::capsule(const_cast<fedcore::DeviceHooks*>(cuda_device_hooks()), "rayfed_b200.device_hooks");
+  });
+  m.def("preload_kernels", [] {
+    check(fedk_preload_push(), "preload push kernels");
+    check(fedk_preload_aggregate(), "preload aggregate kernels");
+    check(fedk_preload_lora(), "preload lora kernels");
+  }, "Force the (lazy) load of every kernel of this module: a first launch must never happen "
+     "while a stream wait is parked (it would block the launching thread until the wait ends).");
+  m.def("stream_create", [](int priority) {
+    cudaStream_t s = nullptr;
+    check(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, priority), "cudaStreamCreateWithPriority");
+    return (uint64_t)(uintptr_t)s;
+  }, py::arg("priority") = 0);
+  m.def("stream_destroy", [](uint64_t s) { check(cudaStreamDestroy((cudaStream_t)(uintptr_t)s), "cudaStreamDestroy"); });
+  m.def("stream_synchronize", [](uint64_t s) {
+    py::gil_scoped_release rel;
+    check(cudaStreamSynchronize((cudaStream_t)(uintptr_t)s), "cudaStreamSynchronize");
+  });
+  m.def("event_create", [](bool timing) {
+    cudaEvent_t e = nullptr;
+    check(cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming), "cudaEventCreate");
+    return (uint64_t)(uintptr_t)e;
+  }, py::arg("timing") = false);
+  m.def("event_destroy", [](uint64_t e) { check(cudaEventDestroy((cudaEvent_t)(uintptr_t)e), "cudaEventDestroy"); });
+  m.def("event_record", [](uint64_t e, uint64_t s) {
+    check(cudaEventRecord((cudaEvent_t)(uintptr_t)e, (cudaStream_t)(uintptr_t)s), "cudaEventRecord");
+  });
+  m.def("event_synchronize", [](uint64_t e) {
+    py::gil_scoped_release rel;
+    check(cudaEventSynchronize((cudaEvent_t)(uintptr_t)e), "cudaEventSynchronize");
+  });
+  m.def("event_query", [](uint64_t e) {
+    cudaError_t r = cudaEventQuery((cudaEvent_t)(uintptr_t)e);
+    if (r == cudaErrorNotReady) {
+      cudaGetLastError();
+      return false;
+    }
+    check(r, "cudaEventQuery");
+    return true;
+  });
+  m.def("event_elapsed_ms", [](uint64_t a, uint64_t b) {
+    float ms = 0.f;
+    check(cudaEventElapsedTime(&ms, (cudaEvent_t)(uintptr_t)a, (cudaEvent_t)(uintptr_t)b), "cudaEventElapsedTime");
+    return ms;
+  });
+  m.def("stream_wait_event", [](uint64_t s, uint64_t e) {
+    check(cudaStreamWaitEvent((cudaStream_t)(uintptr_t)s, (cudaEvent_t)(uintptr_t)e, 0), "cudaStreamWaitEvent");
+  });
+  // K4: order a stream after a 32-bit word reaches `value` (cyclic >=) — a stream memory
+  // operation: no SM is occupied and no kernel spins while the producer is still pushing.
+  m.def("stream_wait_value32", [](uint64_t s, uint64_t addr, uint32_t value) {
+    using Fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    static Fn fn = drv<Fn>("cuStreamWaitValue32");
+    cu_check(fn((CUstream)(uintptr_t)s, (CUdeviceptr)addr, value, CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32");
+  });
+  m.def("stream_write_value32", [](uint64_t s, uint64_t addr, uint32_t value) {
+    using Fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    static Fn fn = drv<Fn>("cuStreamWriteValue32");
+    cu_check(fn((CUstream)(uintptr_t)s, (CUdeviceptr)addr, value, CU_STREAM_WRITE_VALUE_DEFAULT), "cuStreamWriteValue32");
+  });
+  // n u64 words, copied on `stream` (never the legacy default stream: that one serialises with
+  // whatever the user's main thread is doing)
+  m.def("read_u64s", [](uint64_t p, size_t n, uint64_t stream) {
+    std::vector<unsigned long long> v(n);
+    {
+      py::gil_scoped_release rel;
+      check(cudaMemcpyAsync(v.data(), P<void>(p), n * 8, cudaMemcpyDeviceToHost, (cudaStream_t)(uintptr_t)stream),
+            "cudaMemcpyAsync");
+      check(cudaStreamSynchronize((cudaStream_t)(uintptr_t)stream), "cudaStreamSynchronize");
+    }
+    return std::vector<uint64_t>(v.begin(), v.end());
+  });
+  m.def("read_bytes", [](uint64_t p, size_t n) {
+    std::string out(n, '\0');
+    check(cudaMemcpy(out.data(), P<void>(p), n, cudaMemcpyDeviceToHost), "cudaMemcpy");
+    return py::bytes(out);
+  });
 
   // ---- CUDA VMM + NVLS multicast (tier B) -------------------------------------
   m.def("vmm_info", [](int dev) {
@@ -294,7 +412,8 @@ PYBIND11_MODULE(_fedcuda, m) {
   m.def(
       "push",
       [](uint64_t src, uint64_t dst, uint64_t dst_scales, uint64_t n, float scale, uint64_t flag, uint32_t flag_value,
-         uint64_t done_counter, int mode, int blocks, bool use_bulk, uint64_t stream) {
+         uint64_t done_counter, int mode, int blocks, bool use_bulk, uint64_t stream, uint64_t desc_dst,
+         const std::string& desc) {
         PushArgs a{};
         a.src = P<const void>(src);
         a.dst = P<void>(dst);
@@ -304,15 +423,58 @@ PYBIND11_MODULE(_fedcuda, m) {
         a.flag = P<uint32_t>(flag);
         a.flag_value = flag_value;
         a.done_counter = P<uint32_t>(done_counter);
+        fill_desc(a, desc_dst, desc);
         check(fedk_launch_push(&a, mode, blocks, use_bulk ? 1 : 0, (cudaStream_t)(uintptr_t)stream), "fed_push launch");
       },
       py::arg("src"), py::arg("dst"), py::arg("dst_scales"), py::arg("n"), py::arg("scale"), py::arg("flag"),
       py::arg("flag_value"), py::arg("done_counter"), py::arg("mode"), py::arg("blocks"), py::arg("use_bulk"),
-      py::arg("stream"));
+      py::arg("stream"), py::arg("desc_dst") = 0, py::arg("desc") = py::bytes());
+  m.def(
+      "push_multi",
+      [](const std::vector<std::tuple<uint64_t, uint64_t, uint64_t>>& segs, uint64_t dst, uint64_t flag,
+         uint32_t flag_value, uint64_t done_counter, int blocks, uint64_t stream, uint64_t desc_dst,
+         const std::string& desc) {
+        if (segs.empty() || segs.size() > (size_t)kMaxSegs) throw std::runtime_error("push_multi: 1..48 segments");
+        PushSegs sg{};
+        sg.n = (int)segs.size();
+        for (int i = 0; i < sg.n; ++i) {
+          sg.s[i].src = P<const void>(std::get<0>(segs[i]));
+          sg.s[i].dst_off = std::get<1>(segs[i]);
+          sg.s[i].nbytes = std::get<2>(segs[i]);
+          if ((std::get<0>(segs[i]) | std::get<1>(segs[i])) & 15) throw std::runtime_error("push_multi: 16-byte alignment");
+        }
+        PushArgs a{};
+        a.dst = P<void>(dst);
+        a.flag = P<uint32_t>(flag);
+        a.flag_value = flag_value;
+        a.done_counter = P<uint32_t>(done_counter);
+        fill_desc(a, desc_dst, desc);
+        check(fedk_launch_push_multi(&a, &sg, blocks, (cudaStream_t)(uintptr_t)stream), "fed_push_multi launch");
+      },
+      py::arg("segs"), py::arg("dst"), py::arg("flag"), py::arg("flag_value"), py::arg("done_counter"),
+      py::arg("blocks"), py::arg("stream"), py::arg("desc_dst") = 0, py::arg("desc") = py::bytes());
+  m.def(
+      "desc_check",
+      [](uint64_t arena_desc, const std::string& want, uint64_t status, uint64_t stream) {
+        PushArgs a{};
+        a.src = P<const void>(arena_desc);
+        a.status = P<uint32_t>(status);
+        fill_desc(a, 0, want);
+        check(fedk_launch_desc_check(&a, (cudaStream_t)(uintptr_t)stream), "fed_desc_check launch");
+      },
+      py::arg("arena_desc"), py::arg("want"), py::arg("status"), py::arg("stream"));
+  m.def(
+      "credit",
+      [](uint64_t ring_slot, uint64_t value, uint64_t count_ptr, uint64_t count, uint64_t stream) {
+        check(fedk_launch_credit(P<unsigned long long>(ring_slot), value, P<unsigned long long>(count_ptr), count,
+                                 (cudaStream_t)(uintptr_t)stream),
+              "fed_credit launch");
+      },
+      py::arg("ring_slot"), py::arg("value"), py::arg("count_ptr"), py::arg("count"), py::arg("stream"));
   m.def(
       "push_mc",
       [](uint64_t src, uint64_t mc_dst, uint64_t nbytes, const std::vector<uint64_t>& flag_ptrs, uint32_t flag_value,
-         uint64_t done_counter, int blocks, uint64_t stream) {
+         uint64_t done_counter, int blocks, uint64_t stream, uint64_t desc_dst, const std::string& desc) {
         if (nbytes % 16) throw std::runtime_error("push_mc needs a multiple of 16 bytes");
         PushArgs a{};
         a.src = P<const void>(src);
@@ -320,13 +482,15 @@ PYBIND11_MODULE(_fedcuda, m) {
         a.n = nbytes;
         a.flag_value = flag_value;
         a.done_counter = P<uint32_t>(done_counter);
+        fill_desc(a, desc_dst, desc);
         PeerPtrs flags{};
         fill_peers(flags, flag_ptrs);
         check(fedk_launch_push_mc(&a, &flags, (int)flag_ptrs.size(), blocks, (cudaStream_t)(uintptr_t)stream),
               "fed_push_mc launch");
       },
       py::arg("src"), py::arg("mc_dst"), py::arg("nbytes"), py::arg("flag_ptrs"), py::arg("flag_value"),
-      py::arg("done_counter"), py::arg("blocks"), py::arg("stream"));
+      py::arg("done_counter"), py::arg("blocks"), py::arg("stream"), py::arg("desc_dst") = 0,
+      py::arg("desc") = py::bytes());
   m.def(
       "unpack",
       [](uint64_t src, uint64_t dst, uint64_t scales, uint64_t n, float scale, uint64_t flag, uint32_t flag_value,

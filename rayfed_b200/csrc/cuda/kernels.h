@@ -13,6 +13,29 @@ enum PushMode : int {
   kBF16ToF32 = 5,    // unpack of mode 1
 };
 
+// Fixed-layout 64-byte message descriptor, written by the push kernel into the first bytes of
+// the message's block in the *consumer's* arena, before the release flag (replaces
+// the protobuf SendDataRequest{data, upstream_seq_id, downstream_seq_id, job_name} of
+// fed/grpc/fed.proto:9-14 on the device path).  The consumer validates it on its own stream
+// (fed_desc_check / fed_unpack): a mismatch means diverged controllers or a foreign job and
+// raises a status word instead of handing out foreign bytes.
+struct alignas(16) PushDesc {
+  uint32_t magic;      // kDescMagic
+  uint32_t seq;        // k-th message of this (source -> destination) pair == release-flag value
+  uint32_t job_hash;   // fnv1a32(job name): the 417 "JobName mis-match" check of the gRPC path
+  uint32_t up_task;    // upstream fed task id   } the (upstream_seq_id, downstream_seq_id) key of
+  uint32_t up_idx;     // upstream output index  } the reference's event table
+  uint32_t down;       // downstream seq id      }
+  unsigned long long offset;  // block offset inside the source's region of the arena
+  unsigned long long nbytes;  // block bytes (header + payload, wire format)
+  unsigned char dtype, mode, ndim, status;  // status: 1 = DATA, 2 = ERROR
+  uint32_t n_tensors;  // tensors packed in this block
+  uint32_t shape[4];   // leading dims of the first tensor (the host frame has the full metadata)
+};
+static_assert(sizeof(PushDesc) == 64, "PushDesc must be 64 bytes");
+constexpr uint32_t kDescMagic = 0x46454450u;  // "FEDP"
+constexpr int kBlockHeaderBytes = 256;        // descriptor + padding: payload stays 256-byte aligned
+
 struct PushArgs {
   const void* src;
   void* dst;
@@ -26,6 +49,21 @@ struct PushArgs {
   unsigned long long credit_value;
   uint32_t* status;         // local error word (timeout)
   long long timeout_ns;
+  void* desc_dst;           // push: where the descriptor goes in peer memory (null: none)
+  PushDesc desc;            // push: written before the flag; unpack/check: the expected descriptor
+};
+
+// Multi-tensor push: one launch moves every tensor of an object (a state dict, a pytree) into
+// its block of the consumer's arena.  Segments ride in the kernel parameters (no table H2D).
+constexpr int kMaxSegs = 48;
+struct PushSegs {
+  int n;
+  int pad_;
+  struct Seg {
+    const void* src;
+    unsigned long long dst_off;  // relative to PushArgs::dst
+    unsigned long long nbytes;
+  } s[kMaxSegs];
 };
 
 enum AggKind : int {
@@ -97,6 +135,13 @@ cudaError_t fedk_launch_lora_merge_staged(const LoraMergeArgs* a, const void* st
 cudaError_t fedk_launch_push(const PushArgs* a, int mode, int blocks, int use_bulk, cudaStream_t stream);
 cudaError_t fedk_launch_push_mc(const PushArgs* a, const PeerPtrs* flags, int n_flags, int blocks, cudaStream_t stream);
 cudaError_t fedk_launch_unpack(const PushArgs* a, int mode, int blocks, cudaStream_t stream);
+cudaError_t fedk_launch_push_multi(const PushArgs* a, const PushSegs* segs, int blocks, cudaStream_t stream);
+cudaError_t fedk_launch_desc_check(const PushArgs* a, cudaStream_t stream);
+cudaError_t fedk_launch_credit(unsigned long long* ring_slot, unsigned long long value, unsigned long long* count_ptr,
+                               unsigned long long count, cudaStream_t stream);
+cudaError_t fedk_preload_push();       // force the (lazy) load of every kernel of a translation unit:
+cudaError_t fedk_preload_aggregate();  // a first launch must never happen while a stream wait is parked
+cudaError_t fedk_preload_lora();
 cudaError_t fedk_launch_aggregate(const AggArgs* a, int blocks, cudaStream_t stream);
 cudaError_t fedk_launch_barrier(const AggArgs* a, cudaStream_t stream);
 cudaError_t fedk_launch_local_sgd(const LocalSgdArgs* a, int blocks, cudaStream_t stream);

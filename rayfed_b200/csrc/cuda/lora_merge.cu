@@ -850,6 +850,23 @@ fed_lora_gemm3_kernel(const __grid_constant__ LoraMergeArgs a, const __grid_cons
   }
 }
 
+
+#define FEDK_PRELOAD(fn)                                                        \
+  do {                                                                          \
+    cudaFuncAttributes at_;                                                     \
+    cudaError_t e_ = cudaFuncGetAttributes(&at_, fn);                           \
+    if (e_ != cudaSuccess) return e_;                                           \
+  } while (0)
+
+extern "C" cudaError_t fedk_preload_lora() {
+  FEDK_PRELOAD(fed_lora_merge_kernel);
+  FEDK_PRELOAD(fed_lora_merge_tma_kernel);
+  FEDK_PRELOAD(fed_lora_gather_kernel);
+  FEDK_PRELOAD(fed_lora_gemm_kernel);
+  FEDK_PRELOAD(fed_lora_gemm3_kernel);
+  return cudaSuccess;
+}
+
 extern "C" cudaError_t fedk_launch_lora_merge_staged(const LoraMergeArgs* a, const void* maps, void* bcat, void* atcat,
                                                      int kpad, int sm_count, int deep, cudaStream_t stream) {
   const int K = a->n_parties * a->r;

@@ -18,6 +18,29 @@
 
 namespace fedk {
 
+// The 64-byte descriptor goes out as four 16-byte peer stores; the release store of the flag
+// that follows (same thread) orders them, and the payload, before the signal.
+__device__ __forceinline__ void publish_desc(const PushArgs& a) {
+  if (!a.desc_dst) return;
+  const uint4* d = reinterpret_cast<const uint4*>(&a.desc);
+  uint4* o = reinterpret_cast<uint4*>(a.desc_dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) st_v4(o + i, d[i]);
+}
+
+// Does the descriptor in the arena match what the host frame announced?
+__device__ __forceinline__ bool desc_matches(const PushDesc& want, const void* got_ptr) {
+  const uint4* g = reinterpret_cast<const uint4*>(got_ptr);
+  const uint4* w = reinterpret_cast<const uint4*>(&want);
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 x = ld_v4(g + i);
+    ok = ok && x.x == w[i].x && x.y == w[i].y && x.z == w[i].z && x.w == w[i].w;
+  }
+  return ok;
+}
+
 // Grid-wide "last CTA publishes" epilogue.
 __device__ __forceinline__ void publish_when_grid_done(const PushArgs& a, bool is_unpack) {
   fence_acq_rel_sys();  // my payload stores are visible before I count myself done
@@ -28,6 +51,7 @@ __device__ __forceinline__ void publish_when_grid_done(const PushArgs& a, bool i
       *a.done_counter = 0;  // re-arm for the next launch on this stream
       fence_acq_rel_sys();
       if (!is_unpack) {
+        publish_desc(a);
         if (a.flag) st_release_sys_u32(a.flag, a.flag_value);
       } else {
         if (a.credit) st_release_sys_u64(a.credit, a.credit_value);
@@ -70,7 +94,9 @@ __global__ void __launch_bounds__(512) fed_push_kernel(PushArgs a, int mode) {
     // K4: device-side receive barrier. Only one lane polls; the CTA parks on bar.sync.
     __shared__ int ok;
     if (threadIdx.x == 0) {
-      ok = spin_wait_ge(a.flag, a.flag_value, a.timeout_ns) ? 1 : 0;
+      // a.flag == nullptr: the stream was already ordered after the flag by a stream memory
+      // operation (cuStreamWaitValue32) — no SM spins
+      ok = (a.flag == nullptr || spin_wait_ge(a.flag, a.flag_value, a.timeout_ns)) ? 1 : 0;
       // status may live in pinned host memory (the host polls it without a CUDA call)
       if (!ok && a.status) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.status), "r"(1u) : "memory");
     }
@@ -240,6 +266,66 @@ __global__ void __launch_bounds__(512) fed_push_kernel(PushArgs a, int mode) {
 }
 
 // ---------------------------------------------------------------------------
+// Multi-tensor push.  Work items are 64 KiB slices of the concatenated segments; a CTA walks
+// items blockIdx.x, +gridDim.x, ... (segment lookup is a linear scan over <= kMaxSegs entries
+// in constant/param space, once per item).
+constexpr unsigned long long kSegItem = 64 * 1024;
+
+__global__ void __launch_bounds__(512) fed_push_multi_kernel(const __grid_constant__ PushArgs a,
+                                                             const __grid_constant__ PushSegs segs) {
+  unsigned long long total_items = 0;
+  for (int i = 0; i < segs.n; ++i) total_items += (segs.s[i].nbytes + kSegItem - 1) / kSegItem;
+  char* base = reinterpret_cast<char*>(a.dst);
+  for (unsigned long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+    unsigned long long rem = item;
+    int si = 0;
+    for (; si < segs.n; ++si) {
+      unsigned long long cnt = (segs.s[si].nbytes + kSegItem - 1) / kSegItem;
+      if (rem < cnt) break;
+      rem -= cnt;
+    }
+    const unsigned long long off = rem * kSegItem;
+    const unsigned long long left = segs.s[si].nbytes - off;
+    const unsigned long long nb = left < kSegItem ? left : kSegItem;
+    const char* s = reinterpret_cast<const char*>(segs.s[si].src) + off;
+    char* d = base + segs.s[si].dst_off + off;
+    const unsigned nvec = (unsigned)(nb >> 4);
+    const uint4* sv = reinterpret_cast<const uint4*>(s);
+    uint4* dv = reinterpret_cast<uint4*>(d);
+    unsigned i = threadIdx.x;
+    for (; i + 3 * 512 < nvec; i += 4 * 512) {
+      uint4 v0 = ld_stream_v4(sv + i), v1 = ld_stream_v4(sv + i + 512);
+      uint4 v2 = ld_stream_v4(sv + i + 1024), v3 = ld_stream_v4(sv + i + 1536);
+      st_v4(dv + i, v0);
+      st_v4(dv + i + 512, v1);
+      st_v4(dv + i + 1024, v2);
+      st_v4(dv + i + 1536, v3);
+    }
+    for (; i < nvec; i += 512) st_v4(dv + i, ld_stream_v4(sv + i));
+    if (threadIdx.x == 0)
+      for (unsigned long long b = (unsigned long long)nvec << 4; b < nb; ++b) d[b] = s[b];
+  }
+  publish_when_grid_done(a, false);
+}
+
+// One warp: compare the arena descriptor with the announced one; raise status 3 on mismatch.
+__global__ void fed_desc_check_kernel(const __grid_constant__ PushArgs a) {
+  if (threadIdx.x == 0 && !desc_matches(a.desc, a.src)) {
+    if (a.status) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.status), "r"(3u) : "memory");
+  }
+}
+
+// Flow control: "block <value> of my region in your arena is free again" — one entry of the
+// freed ring in the *producer's* control block, then the ring's count (release).
+__global__ void fed_credit_kernel(unsigned long long* ring_slot, unsigned long long value,
+                                  unsigned long long* count_ptr, unsigned long long count) {
+  if (threadIdx.x == 0) {
+    if (ring_slot) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(ring_slot), "l"(value) : "memory");
+    st_release_sys_u64(count_ptr, count);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // TMA-engine variant: cp.async.bulk global->shared (mbarrier complete_tx) then
 // cp.async.bulk shared->peer global (bulk_group). One elected thread per CTA
 // drives a kStages-deep ring; the SMs issue no per-byte instructions at all.
@@ -368,6 +454,14 @@ __global__ void __launch_bounds__(512) fed_push_mc_kernel(const __grid_constant_
     unsigned prev = atomicAdd(a.done_counter, 1u);
     if (prev == gridDim.x - 1) {
       *a.done_counter = 0;
+      if (a.desc_dst) {  // the block header, replicated by the switch like the payload
+        const uint4* dd = reinterpret_cast<const uint4*>(&a.desc);
+        char* o = reinterpret_cast<char*>(a.desc_dst);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o + 16 * k), "r"(dd[k].x),
+                       "r"(dd[k].y), "r"(dd[k].z), "r"(dd[k].w) : "memory");
+      }
       fence_acq_rel_sys();
       for (int p = 0; p < n_flags; ++p) st_release_sys_u32(reinterpret_cast<uint32_t*>(flags.p[p]), a.flag_value);
     }
@@ -396,6 +490,41 @@ cudaError_t fedk_launch_push(const PushArgs* a, int mode, int blocks, int use_bu
   } else {
     fed_push_kernel<false><<<blocks, 512, 0, stream>>>(*a, mode);
   }
+  return cudaGetLastError();
+}
+
+
+#define FEDK_PRELOAD(fn)                                                        \
+  do {                                                                          \
+    cudaFuncAttributes at_;                                                     \
+    cudaError_t e_ = cudaFuncGetAttributes(&at_, fn);                           \
+    if (e_ != cudaSuccess) return e_;                                           \
+  } while (0)
+
+cudaError_t fedk_preload_push() {
+  FEDK_PRELOAD(fed_push_kernel<false>);
+  FEDK_PRELOAD(fed_push_kernel<true>);
+  FEDK_PRELOAD(fed_push_bulk_kernel);
+  FEDK_PRELOAD(fed_push_mc_kernel);
+  FEDK_PRELOAD(fed_push_multi_kernel);
+  FEDK_PRELOAD(fed_desc_check_kernel);
+  FEDK_PRELOAD(fed_credit_kernel);
+  return cudaSuccess;
+}
+
+cudaError_t fedk_launch_push_multi(const PushArgs* a, const PushSegs* segs, int blocks, cudaStream_t stream) {
+  fed_push_multi_kernel<<<blocks, 512, 0, stream>>>(*a, *segs);
+  return cudaGetLastError();
+}
+
+cudaError_t fedk_launch_desc_check(const PushArgs* a, cudaStream_t stream) {
+  fed_desc_check_kernel<<<1, 32, 0, stream>>>(*a);
+  return cudaGetLastError();
+}
+
+cudaError_t fedk_launch_credit(unsigned long long* ring_slot, unsigned long long value, unsigned long long* count_ptr,
+                               unsigned long long count, cudaStream_t stream) {
+  fed_credit_kernel<<<1, 32, 0, stream>>>(ring_slot, value, count_ptr, count);
   return cudaGetLastError();
 }
 

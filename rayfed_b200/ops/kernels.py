@@ -82,8 +82,9 @@ def _blocks_for(nbytes: int, device_index: int, bytes_per_cta: int = 64 * 1024, 
 
 def push(src_ptr: int, dst_ptr: int, n: int, *, mode: int = MODE_COPY, scale: float = 1.0, dst_scales_ptr: int = 0,
          flag_ptr: int = 0, flag_value: int = 0, done_counter_ptr: int, stream=None, device_index: int = 0,
-         use_bulk: Optional[bool] = None, blocks: Optional[int] = None) -> None:
-    """K1. ``n`` is bytes for MODE_COPY, elements otherwise."""
+         use_bulk: Optional[bool] = None, blocks: Optional[int] = None, desc_dst: int = 0, desc: bytes = b"") -> None:
+    """K1. ``n`` is bytes for MODE_COPY, elements otherwise.  ``desc`` (64 bytes) is stored to
+    ``desc_dst`` in peer memory by the last CTA, before the release flag."""
     nbytes = n if mode == MODE_COPY else n * (4 if mode == MODE_F32_TO_BF16 else 2)
     if use_bulk is None:
         use_bulk = mode == MODE_COPY and nbytes >= (1 << 20) and nbytes % 16 == 0 and _bulk_default()
@@ -92,18 +93,32 @@ def push(src_ptr: int, dst_ptr: int, n: int, *, mode: int = MODE_COPY, scale: fl
         if use_bulk:
             blocks = int(min(blocks, max(1, (nbytes + 32 * 1024 - 1) // (32 * 1024))))
     cuda_ext().push(src_ptr, dst_ptr, dst_scales_ptr, n, float(scale), flag_ptr, flag_value, done_counter_ptr, mode,
-                    blocks, bool(use_bulk), _stream_handle(stream))
+                    blocks, bool(use_bulk), _stream_handle(stream), desc_dst, desc)
     launch_counter.add("fed_push_bulk" if use_bulk else "fed_push")
 
 
+def push_multi(segs: Sequence, dst_ptr: int, *, flag_ptr: int = 0, flag_value: int = 0, done_counter_ptr: int,
+               stream=None, device_index: int = 0, blocks: Optional[int] = None, desc_dst: int = 0,
+               desc: bytes = b"") -> None:
+    """K1 for a whole object: ``segs`` = [(src_ptr, dst_offset, nbytes)] (<= 48, 16-byte aligned)
+    land in one block at ``dst_ptr`` with one launch, one descriptor, one flag."""
+    total = sum(s[2] for s in segs)
+    if blocks is None:
+        blocks = _blocks_for(total, device_index)
+    cuda_ext().push_multi([tuple(int(x) for x in s) for s in segs], dst_ptr, flag_ptr, flag_value, done_counter_ptr,
+                          blocks, _stream_handle(stream), desc_dst, desc)
+    launch_counter.add("fed_push_multi")
+
+
 def push_mc(src_ptr: int, mc_dst_ptr: int, nbytes: int, *, flag_ptrs: Sequence[int], flag_value: int,
-            done_counter_ptr: int, stream=None, device_index: int = 0, blocks: Optional[int] = None) -> None:
+            done_counter_ptr: int, stream=None, device_index: int = 0, blocks: Optional[int] = None,
+            desc_dst: int = 0, desc: bytes = b"") -> None:
     """K1b: multicast push — one ``multimem.st`` stream lands in every party's copy of the
-    destination; then the release flag is stored to each listed peer."""
+    destination; then the descriptor (multicast too) and the release flag of each listed peer."""
     if blocks is None:
         blocks = _blocks_for(nbytes, device_index)
     cuda_ext().push_mc(src_ptr, mc_dst_ptr, nbytes, list(flag_ptrs), flag_value, done_counter_ptr, blocks,
-                       _stream_handle(stream))
+                       _stream_handle(stream), desc_dst, desc)
     launch_counter.add("fed_push_mc")
 
 

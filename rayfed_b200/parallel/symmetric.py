@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import logging
 import os
-import pickle
+import struct
 import socket
 import time
 from typing import List, Optional
@@ -111,13 +111,17 @@ class SymmetricHeap:
         g = self.group
         ptr, handle = self._ext.ipc_alloc(nbytes, True)
         self._ext.device_synchronize()
-        blobs = g.all_gather(g.next_tag(f"symm-ipc/{name}"), pickle.dumps((nbytes, handle, os.getpid())))
+        # fixed layout (never pickle: the blob comes from a peer): u64 nbytes | u64 pid | 64-byte handle
+        blobs = g.all_gather(g.next_tag(f"symm-ipc/{name}"), struct.pack("<QQ", nbytes, os.getpid()) + bytes(handle))
         peers = []
         for r, blob in enumerate(blobs):
             if r == g.rank:
                 peers.append(ptr)
                 continue
-            pn, ph, ppid = pickle.loads(blob)
+            if len(blob) != 16 + 64:
+                raise RuntimeError(f"malformed cudaIpc handle record from party #{r} ({len(blob)} bytes)")
+            pn, ppid = struct.unpack("<QQ", blob[:16])
+            ph = blob[16:]
             assert pn == nbytes, f"symmetric alloc size mismatch for {name}: {pn} vs {nbytes}"
             if ppid == os.getpid():
                 raise RuntimeError("cudaIpc handles cannot be opened in the exporting process")

@@ -33,7 +33,7 @@ from .. import config as fed_config
 from .._private import constants
 from .._private.global_context import get_global_context
 from ..core import get_runtime, is_ref, native
-from ..core.runtime import _Produced
+from ..core.runtime import DeviceValue, is_device_value
 from ..exceptions import FedRemoteError, FedTaskError
 from .. import _tracing
 from .base_proxy import ReceiverProxy, SenderProxy, SenderReceiverProxy  # noqa: F401  (re-exported)
@@ -237,10 +237,10 @@ class ProxyHost:
         proxies) — the CleanupManager treats both as a failed send."""
         self._send_seen = next(self._send_ops)
         try:
-            if type(data) is _Produced and not self._device_aware:
+            if is_device_value(data) and not self._device_aware:
                 # host-only transport: the value must be complete before pickling
-                if data.event is not None:
-                    data.event.synchronize()
+                if data.owner is not None:
+                    data.owner.device_sync()
                 data = data.value
             out = self._proxy_instance.send(dest_party, data, upstream_seq_id, downstream_seq_id)
         except KeyError:
@@ -440,6 +440,14 @@ def _copy_outcome(src, dst):
         dst.set_value(src.result())
 
 
+def _value_for_send(ref):
+    """The produced value, together with its device-completion event when it has one: a
+    device-aware transport orders its push stream after the event instead of blocking."""
+    v = ref.result()
+    ev = ref.cuda_event
+    return DeviceValue(v, ev, ref.cuda_stream, ref) if ev else v
+
+
 def send(dest_party, data, upstream_seq_id, downstream_seq_id, is_error=False, check_sending=True):
     """Push ``data`` (a value or the `Ref` of one) to ``dest_party``.
 
@@ -457,7 +465,7 @@ def send(dest_party, data, upstream_seq_id, downstream_seq_id, is_error=False, c
                 result = native().Ref()
                 result.set_error(e)
             else:
-                result = host.send(dest_party, data.result(), upstream_seq_id, downstream_seq_id, is_error)
+                result = host.send(dest_party, _value_for_send(data), upstream_seq_id, downstream_seq_id, is_error)
         else:
             result = native().Ref()
 
@@ -467,7 +475,7 @@ def send(dest_party, data, upstream_seq_id, downstream_seq_id, is_error=False, c
                     result.set_error(e)
                     return
                 try:
-                    inner = host.send(dest_party, r.result(), upstream_seq_id, downstream_seq_id, is_error)
+                    inner = host.send(dest_party, _value_for_send(r), upstream_seq_id, downstream_seq_id, is_error)
                 except BaseException as ex:  # noqa: BLE001
                     result.set_error(ex)
                     return
@@ -507,6 +515,10 @@ def send_broadcast(dest_parties, data, upstream_seq_id, downstream_seq_id):
 
     def issue(value):
         try:
+            if is_device_value(value) and not host._device_aware:
+                if value.owner is not None:
+                    value.owner.device_sync()
+                value = value.value
             for _ in dest_parties:
                 host._send_seen = next(host._send_ops)
             acks = proxy.broadcast(dest_parties, value, upstream_seq_id, downstream_seq_id)
@@ -524,7 +536,7 @@ def send_broadcast(dest_parties, data, upstream_seq_id, downstream_seq_id):
                 for r in results.values():
                     r.set_error(e)
             else:
-                issue(data.result())
+                issue(_value_for_send(data))
         else:
             def on_ready(r):
                 e = r.exception()
@@ -532,7 +544,7 @@ def send_broadcast(dest_parties, data, upstream_seq_id, downstream_seq_id):
                     for res in results.values():
                         res.set_error(e)
                 else:
-                    issue(r.result())
+                    issue(_value_for_send(r))
 
             data.add_done_callback(on_ready)
     else:
@@ -570,7 +582,7 @@ def pending_summary(limit: int = 16):
     if mailbox is None or not hasattr(mailbox, "snapshot"):
         return [], []
     waiting, unclaimed = mailbox.snapshot(limit)
-    unclaimed = [k for k in unclaimed if k != ("ping", "ping") and not k[0].startswith("__devq__")]
+    unclaimed = [k for k in unclaimed if k != ("ping", "ping") and not k[0].startswith("__")]
     return list(waiting), unclaimed
 
 

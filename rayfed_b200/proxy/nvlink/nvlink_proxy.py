@@ -1,39 +1,42 @@
-"""NVLink transport = native host frames for the object skeleton + the
-DeviceChannel (K1 push / K4 unpack) for every CUDA tensor leaf.
+"""NVLink transport = native host frames for the object skeleton + the DeviceChannel
+(K1 push / K4 stream wait / K1b multicast) for every CUDA tensor leaf.
 
-What crosses the host socket for ``send(dest, obj)`` is a pickle of ``obj`` in
-which each large CUDA tensor was replaced by a persistent id ``(k, idx)``; the
-tensor bytes themselves never touch the host: they are stored by the push
-kernel into the destination party's arena over NVLink.  Receive-side unpack
-kernels are launched by a per-source ordered thread as soon as the descriptor
-frame lands (arena regions are byte rings, so they must be consumed in FIFO
-order), i.e. usually *before* the consumer task asks for the value; the
-consumer just orders its CUDA stream after the unpack event.
+What crosses the host socket for ``send(dest, obj)`` is a pickle of ``obj`` in which each large
+CUDA tensor was replaced by a persistent id ``idx``, plus one small JSON *metadata* frame per
+arena block (block id, offsets, shapes).  The tensor bytes never touch the host: the push kernel
+stores them into the destination party's arena over NVLink.  Both frames leave at **launch**
+time — the sender's host does not wait for the push kernel, and the receiver's host does not
+wait for the data: a per-source thread orders that source's receive stream after the block's
+release flag with ``cuStreamWaitValue32`` and hands the consumer zero-copy views of the arena
+(or the output of an unpack kernel for wire formats / small / chunked tensors) together with
+the CUDA event the consumer's stream has to wait for.
 
-This is the B200-native replacement of the whole pickle→protobuf→HTTP/2 path
-for tensors (SURVEY §3.4 — ≥5 host copies, 3 process hops), while non-tensor
-objects keep the cheap host frame.
+This is the B200-native replacement of the whole pickle→protobuf→HTTP/2 path for tensors
+(SURVEY §3.4 — ≥5 host copies, 3 process hops); non-tensor objects keep the cheap host frame.
+
+Security parity (fed/_private/serialization_utils.py:24-83): the skeleton is decoded by the
+*same* restricted unpickler as any host payload when ``serializing_allowed_list`` is set; the
+metadata frames are JSON, never pickle.
 """
 from __future__ import annotations
 
 import io
+import json
 import logging
+import os as _os
 import pickle
-import queue
 import threading
 from typing import Dict
 
 import cloudpickle
 
-from ..._private.serialization import Deserializer
+from ..._private.serialization import Deserializer, _RestrictedUnpickler
 from ...config import CrossSiloMessageConfig
-from ...core.runtime import _Produced
+from ...core.runtime import DeviceValue, is_device_value
 from ...exceptions import FedRemoteError, FedTaskError
 from ..native.socket_proxy import NativeReceiverProxy, NativeSenderProxy, _ack_decoder
 
 logger = logging.getLogger(__name__)
-
-import os as _os
 
 # K1b multicast push for owner -> everyone broadcasts (fed.get).  On by default where the
 # channel got an NVLS mapping; RAYFED_B200_MC_PUSH=0 forces per-destination unicast pushes.
@@ -47,11 +50,10 @@ _DEFAULT_MIN_BYTES = 4096
 class _DevicePickler(cloudpickle.Pickler):
     """Pickles an object graph, diverting big CUDA tensors to ``sink``."""
 
-    def __init__(self, file, sink, min_bytes, before_host_copy=None, max_bytes=None):
+    def __init__(self, file, sink, min_bytes, before_host_copy=None):
         super().__init__(file, protocol=5)
         self._sink = sink
         self._min_bytes = min_bytes
-        self._max_bytes = max_bytes  # tensors that do not fit an arena region spill to the host frame
         self._before_host_copy = before_host_copy
         self.small_tensors = 0
 
@@ -60,9 +62,9 @@ class _DevicePickler(cloudpickle.Pickler):
 
         if isinstance(obj, torch.Tensor) and obj.is_cuda and obj.layout == torch.strided:
             nbytes = obj.numel() * obj.element_size()
-            if nbytes >= self._min_bytes and (self._max_bytes is None or nbytes + 4096 <= self._max_bytes):
+            if nbytes >= self._min_bytes:
                 return (_TAG, self._sink(obj.detach()))
-            # small (and oversize) tensors ride the host frame — as CPU data, re-homed on the *receiver's*
+            # small tensors ride the host frame — as CPU data, re-homed on the *receiver's*
             # device (a plain pickle would resurrect them on the sender's device index and
             # make every party open a CUDA context on every other party's GPU)
             if self._before_host_copy is not None and self.small_tensors == 0:
@@ -72,18 +74,19 @@ class _DevicePickler(cloudpickle.Pickler):
         return None
 
 
-class _DeviceUnpickler(pickle.Unpickler):
-    def __init__(self, file, resolve, rehome=None):
-        super().__init__(file)
-        self._resolve = resolve
-        self._rehome = rehome or (lambda t: t)
+def _make_unpickler(file, allowed, resolve, rehome):
+    """Skeleton unpickler: the restricted one whenever an allow-list is configured."""
+    base = pickle.Unpickler if allowed is None else _RestrictedUnpickler
 
-    def persistent_load(self, pid):
-        if isinstance(pid, tuple) and pid and pid[0] == _TAG:
-            return self._resolve(pid[1])
-        if isinstance(pid, tuple) and pid and pid[0] == _SMALL:
-            return self._rehome(pid[1])
-        raise pickle.UnpicklingError(f"unsupported persistent id {pid!r}")
+    class _DeviceUnpickler(base):
+        def persistent_load(self, pid):
+            if isinstance(pid, tuple) and len(pid) == 2 and pid[0] == _TAG and isinstance(pid[1], int):
+                return resolve(pid[1])
+            if isinstance(pid, tuple) and len(pid) == 2 and pid[0] == _SMALL:
+                return rehome(pid[1])
+            raise pickle.UnpicklingError(f"unsupported persistent id {pid!r}")
+
+    return _DeviceUnpickler(file) if allowed is None else _DeviceUnpickler(file, allowed)
 
 
 class _ChannelHolder:
@@ -98,11 +101,20 @@ def attach_channel(channel) -> None:
 
 
 def detach_channel() -> None:
-    _ChannelHolder.channel = None
+    ch, _ChannelHolder.channel = _ChannelHolder.channel, None
+    if ch is not None:
+        ch.close()
 
 
 def current_channel():
     return _ChannelHolder.channel
+
+
+def _split(data):
+    """(value, event handle, producer stream handle, event owner)."""
+    if is_device_value(data):
+        return data.value, data.event, data.stream, data.owner
+    return data, 0, 0, None
 
 
 class NvlinkSenderProxy(NativeSenderProxy):
@@ -113,45 +125,9 @@ class NvlinkSenderProxy(NativeSenderProxy):
         cfg: CrossSiloMessageConfig = self._proxy_config
         self._min_bytes = cfg.device_min_bytes if cfg.device_min_bytes is not None else _DEFAULT_MIN_BYTES
         self._order_lock = threading.Lock()
-        self._k = {}  # dest -> number of device messages sent
-        # Descriptor frames are released only once the push kernel has *finished*:
-        # the receiver then launches its unpack kernel against data that is already
-        # there.  (An eagerly launched unpack kernel that spins on the flag can
-        # deadlock: its GPU front-end queue may be shared with a later-submitted
-        # kernel the producer transitively waits for — measured on B200, see
-        # profiles/README.md.)
-        self._done_q = queue.SimpleQueue()
-        self._done_thread = threading.Thread(target=self._completion_loop, name="fed-push-done", daemon=True)
-        self._done_thread.start()
+        self._k = {}  # dest -> number of metadata frames sent (= the receiver's processing order)
 
-    def _completion_loop(self):
-        while True:
-            item = self._done_q.get()
-            if item is None:
-                return
-            ev, dest_party, k, blob = item
-            try:
-                ev.synchronize()  # releases the GIL
-                self._transport.send(dest_party, f"{_DEVQ}/{self._party}", str(k), blob, False, _ack_decoder)
-            except Exception:  # noqa: BLE001
-                logger.exception("failed to publish device descriptors")
-
-    def stop(self):
-        self._done_q.put(None)
-        self._done_thread.join(timeout=5)
-        super().stop()
-
-    def send(self, dest_party, data, upstream_seq_id, downstream_seq_id):
-        ready_event = None
-        producer_stream = None
-        if type(data) is _Produced:
-            ready_event, producer_stream, data = data.event, data.stream, data.value
-        channel = current_channel()
-        if channel is None or isinstance(data, FedRemoteError):
-            if ready_event is not None:
-                ready_event.synchronize()
-            return super().send(dest_party, data, upstream_seq_id, downstream_seq_id)
-
+    def _serialise(self, data, owner):
         tensors = []
 
         def sink(t):
@@ -159,27 +135,44 @@ class NvlinkSenderProxy(NativeSenderProxy):
             return len(tensors) - 1
 
         buf = io.BytesIO()
-        pickler = _DevicePickler(buf, sink, self._min_bytes,
-                                 ready_event.synchronize if ready_event is not None else None,
-                                 max_bytes=channel.region_bytes)
+        pickler = _DevicePickler(buf, sink, self._min_bytes, owner.device_sync if owner is not None else None)
         pickler.dump(data)
+        return buf.getvalue(), tensors, pickler.small_tensors
+
+    def _next_k(self, dest):
+        k = self._k.get(dest, 0) + 1
+        self._k[dest] = k
+        return k
+
+    def _meta_frame(self, dest, meta, last, n_tensors):
+        k = self._next_k(dest)
+        meta = dict(meta, last=bool(last), n=n_tensors)
+        self._transport.send(dest, f"{_DEVQ}/{self._party}", str(k), json.dumps(meta).encode(), False, _ack_decoder)
+        return k
+
+    def send(self, dest_party, data, upstream_seq_id, downstream_seq_id):
+        data, event, pstream, owner = _split(data)
+        channel = current_channel()
+        if channel is None or isinstance(data, FedRemoteError):
+            if owner is not None:
+                owner.device_sync()
+            return super().send(dest_party, data, upstream_seq_id, downstream_seq_id)
+
+        skeleton, tensors, small = self._serialise(data, owner)
+        up, down = str(upstream_seq_id), str(downstream_seq_id)
         if not tensors:
-            if pickler.small_tensors:
-                frame = pickle.dumps((_TAG, 0, buf.getvalue()), protocol=5)
-            else:
-                frame = buf.getvalue()  # plain host object: nothing to re-home
-            return self._transport.send(dest_party, str(upstream_seq_id), str(downstream_seq_id), frame,
-                                        False, _ack_decoder)
+            frame = pickle.dumps((_TAG, 0, skeleton), protocol=5) if small else skeleton
+            return self._transport.send(dest_party, up, down, frame, False, _ack_decoder)
         dest_rank = channel.group.parties.index(dest_party)
         with self._order_lock:
-            k = self._k.get(dest_party, 0) + 1
-            self._k[dest_party] = k
-            descs = [channel.push_tensor(dest_rank, t, ready_event, producer_stream=producer_stream) for t in tensors]
-            self._done_q.put((channel.record_push_event(), dest_party, k, pickle.dumps(descs)))
-        frame = pickle.dumps((_TAG, k, buf.getvalue()), protocol=5)
-        return self._transport.send(dest_party, str(upstream_seq_id), str(downstream_seq_id), frame, False,
-                                    _ack_decoder)
-
+            # one metadata frame per arena block, sent the moment its push kernel is *launched*
+            messages = channel.plan_messages(tensors)
+            k = 0
+            for i, parts in enumerate(messages):
+                meta = channel.push_message(dest_rank, parts, (up, down), event, pstream)
+                k = self._meta_frame(dest_party, meta, i == len(messages) - 1, len(tensors))
+        frame = pickle.dumps((_TAG, k, skeleton), protocol=5)
+        return self._transport.send(dest_party, up, down, frame, False, _ack_decoder)
 
     # -- K1b: owner -> all-parties broadcast (fed.get, weight redistribution) -------------------
     def can_broadcast(self) -> bool:
@@ -187,56 +180,32 @@ class NvlinkSenderProxy(NativeSenderProxy):
 
     def broadcast(self, dest_parties, data, upstream_seq_id, downstream_seq_id):
         """Send the same object to every party in ``dest_parties`` (all the others): each big
-        CUDA tensor is pushed ONCE with the multicast kernel; the skeleton + descriptors go
+        CUDA tensor is pushed ONCE with the multicast kernel; the skeleton + metadata go
         to each destination.  Returns {dest: ack Ref}."""
-        ready_event = None
-        if type(data) is _Produced:
-            ready_event, data = data.event, data.value
+        orig = data
+        data, event, pstream, owner = _split(data)
         channel = current_channel()
         if channel is None or isinstance(data, FedRemoteError):
-            if ready_event is not None:
-                ready_event.synchronize()
+            if owner is not None:
+                owner.device_sync()
             return super().broadcast(dest_parties, data, upstream_seq_id, downstream_seq_id)
-        tensors = []
-
-        def sink(t):
-            tensors.append(t)
-            return len(tensors) - 1
-
-        buf = io.BytesIO()
-        pickler = _DevicePickler(buf, sink, self._min_bytes,
-                                 ready_event.synchronize if ready_event is not None else None,
-                                 max_bytes=channel.region_bytes)
-        pickler.dump(data)
-        acks = {}
+        skeleton, tensors, small = self._serialise(data, owner)
+        up, down = str(upstream_seq_id), str(downstream_seq_id)
+        send = self._transport.send
         if not tensors:
-            frame = pickle.dumps((_TAG, 0, buf.getvalue()), protocol=5) if pickler.small_tensors else buf.getvalue()
-            for d in dest_parties:
-                acks[d] = self._transport.send(d, str(upstream_seq_id), str(downstream_seq_id), frame, False,
-                                               _ack_decoder)
-            return acks
+            frame = pickle.dumps((_TAG, 0, skeleton), protocol=5) if small else skeleton
+            return {d: send(d, up, down, frame, False, _ack_decoder) for d in dest_parties}
+        if not (_MC_PUSH_ENABLED and channel.can_bcast(tensors)):
+            return {d: self.send(d, orig, upstream_seq_id, downstream_seq_id) for d in dest_parties}
+        ks = {}
         with self._order_lock:
-            descs = None
-            if _MC_PUSH_ENABLED and all(channel.can_bcast_tensor(t) for t in tensors):  # all or nothing: no ring leaks
-                descs = [channel.push_tensor_bcast(t, ready_event) for t in tensors]
-                if any(d is None for d in descs):
-                    raise RuntimeError("multicast push refused a tensor it had accepted")
-            if descs is not None:
-                ev = channel.record_push_event()
-                blob = pickle.dumps(descs)
-                ks = {}
+            messages = channel.plan_messages(tensors)
+            for i, parts in enumerate(messages):
+                meta = channel.push_message(None, parts, (up, down), event, pstream)
                 for d in dest_parties:
-                    ks[d] = self._k.get(d, 0) + 1
-                    self._k[d] = ks[d]
-                    self._done_q.put((ev, d, ks[d], blob))
-        if descs is None:
-            data_again = _Produced(data, ready_event) if ready_event is not None else data
-            return {d: self.send(d, data_again, upstream_seq_id, downstream_seq_id) for d in dest_parties}
-        for d in dest_parties:
-            frame = pickle.dumps((_TAG, ks[d], buf.getvalue()), protocol=5)
-            acks[d] = self._transport.send(d, str(upstream_seq_id), str(downstream_seq_id), frame, False,
-                                           _ack_decoder)
-        return acks
+                    ks[d] = self._meta_frame(d, meta, i == len(messages) - 1, len(tensors))
+        return {d: send(d, up, down, pickle.dumps((_TAG, ks[d], skeleton), protocol=5), False, _ack_decoder)
+                for d in dest_parties}
 
 
 class NvlinkReceiverProxy(NativeReceiverProxy):
@@ -244,28 +213,32 @@ class NvlinkReceiverProxy(NativeReceiverProxy):
                  proxy_config: Dict = None):
         super().__init__(listening_address, party, job_name, tls_config, proxy_config)
         self._loads = Deserializer(self._proxy_config.serializing_allowed_list)
-        self._unpacked = {}  # (src, k) -> list[(tensor, event)]
+        self._ready = {}  # (src, k of the object's last block) -> (tensors, event, stream)
         self._cv = threading.Condition()
         self._threads = []
-        self._waiting = {}  # src -> k the unpacker is parked on
+        self._waiting = {}  # src -> k the receive thread is parked on
         self._stopping = False
+        self._timeout_s = (self._proxy_config.timeout_in_ms or 60000) / 1000.0
 
     # called by fed.init once the channel exists
     def start_unpackers(self, channel):
         for src in channel.group.parties:
             if src == self._party:
                 continue
-            t = threading.Thread(target=self._unpack_loop, args=(channel, src), name=f"fed-unpack-{src}",
+            t = threading.Thread(target=self._receive_loop, args=(channel, src), name=f"fed-recv-{src}",
                                  daemon=True)
             t.start()
             self._threads.append(t)
 
-    def _unpack_loop(self, channel, src: str):
+    def _receive_loop(self, channel, src: str):
+        """Metadata frames of one source, in order.  Per frame: a stream wait-value, a
+        descriptor check and (maybe) unpack kernels are *enqueued*; nothing here waits for the GPU."""
         import torch
 
         torch.cuda.set_device(channel.device_index)
         src_rank = channel.group.parties.index(src)
         k = 0
+        tensors, assembling = {}, {}
         while not self._stopping:
             k += 1
             self._waiting[src] = k
@@ -277,13 +250,21 @@ class NvlinkReceiverProxy(NativeReceiverProxy):
                 raw = ref.result()
                 if raw is None:
                     return
-                descs = pickle.loads(raw)
-                out = [channel.unpack_tensor(src_rank, d) for d in descs]
+                meta = json.loads(raw)
+                parts, ev, stream = channel.receive_message(src_rank, meta, assembling)
+                for ti, t in parts:
+                    if t is not None:
+                        tensors[ti] = t
+                if not meta["last"]:
+                    continue
+                out = ([tensors[i] for i in range(meta["n"])], ev, stream)
+                tensors, assembling = {}, {}
             except BaseException as e:  # noqa: BLE001
-                logger.exception("device unpack failed")
+                logger.exception("device receive failed")
                 out = e
+                tensors, assembling = {}, {}
             with self._cv:
-                self._unpacked[(src, k)] = out
+                self._ready[(src, k)] = out
                 self._cv.notify_all()
 
     def _rehome(self, cpu_tensor):
@@ -292,12 +273,12 @@ class NvlinkReceiverProxy(NativeReceiverProxy):
             return cpu_tensor
         return cpu_tensor.to(f"cuda:{ch.device_index}", non_blocking=False)
 
-    def _take(self, src: str, k: int, timeout: float = 120.0):
+    def _take(self, src: str, k: int):
         with self._cv:
-            ok = self._cv.wait_for(lambda: (src, k) in self._unpacked or self._stopping, timeout)
+            ok = self._cv.wait_for(lambda: (src, k) in self._ready or self._stopping, self._timeout_s)
             if not ok or self._stopping:
                 raise TimeoutError(f"device payload {k} from {src} never arrived")
-            out = self._unpacked.pop((src, k))
+            out = self._ready.pop((src, k))
         if isinstance(out, BaseException):
             raise out
         return out
@@ -311,14 +292,16 @@ class NvlinkReceiverProxy(NativeReceiverProxy):
             if isinstance(obj, tuple) and len(obj) == 3 and obj[0] == _TAG:
                 _, k, skeleton = obj
                 if k == 0:  # no device parts: only (possibly) small tensors to re-home
-                    value = _DeviceUnpickler(io.BytesIO(skeleton), None, self._rehome).load()
+                    value = _make_unpickler(io.BytesIO(skeleton), loads.allowed, None, self._rehome).load()
                     if isinstance(value, FedRemoteError):
                         raise FedTaskError(value, "", "recv")
                     return value
-                parts = self._take(src_party, k)
-                value = _DeviceUnpickler(io.BytesIO(skeleton), lambda idx: parts[idx][0], self._rehome).load()
-                # the receive stream is in-order: the last unpack's event covers them all
-                return _Produced(value, parts[-1][1])
+                parts, ev, stream = self._take(src_party, k)
+                value = _make_unpickler(io.BytesIO(skeleton), loads.allowed, lambda idx: parts[idx],
+                                        self._rehome).load()
+                # one event behind the source's receive stream orders every tensor of the object;
+                # the consumer's stream waits for it (C++ executor) — the host does not
+                return DeviceValue(value, ev.handle, stream, ev)
             if isinstance(obj, FedRemoteError):
                 raise FedTaskError(obj, "", "recv")
             return obj
@@ -328,7 +311,7 @@ class NvlinkReceiverProxy(NativeReceiverProxy):
 
     def stop(self):
         self._stopping = True
-        # unblock unpackers parked on their next descriptor frame
+        # unblock receive threads parked on their next metadata frame
         for src, k in list(self._waiting.items()):
             try:
                 self._mailbox.deliver_obj(f"{_DEVQ}/{src}", str(k), None, False)

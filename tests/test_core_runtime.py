@@ -124,3 +124,63 @@ def test_seq_counter():
     assert [c.next() for _ in range(3)] == [1, 2, 3]
     c.reset(0)
     assert c.next() == 1
+
+
+# -- device ordering in the C++ scheduler (csrc/core/device_hooks.h), with the recording fake ----
+def test_executor_orders_consumer_streams_after_producer_events():
+    from rayfed_b200.core import native
+
+    nat = native()
+    nat.install_fake_device_hooks()
+    nat.fake_device_log(True)
+    try:
+        ex = nat.Executor(2, None)
+        la = ex.create_lane("a", 1, lambda: 11)  # thread_init returns the lane's stream handle
+        lb = ex.create_lane("b", 1, lambda: 22)
+        r1 = ex.submit(la, lambda: 5, (), None, 1)[0]
+        r2 = ex.submit(lb, lambda x: x + 1, (r1,), None, 1)[0]
+        assert r2.result(5) == 6
+        log = nat.fake_device_log()
+        assert r1.cuda_event and r1.cuda_stream == 11 and r2.cuda_stream == 22
+        assert f"record e{r1.cuda_event} s11" in log
+        assert f"wait s22 e{r1.cuda_event}" in log  # the consumer's stream waits, not its thread
+        assert log.index(f"wait s22 e{r1.cuda_event}") < log.index(f"record e{r2.cuda_event} s22")
+        # same stream: already ordered, no wait is issued
+        r3 = ex.submit(lb, lambda x: x, (r2,), None, 1)[0]
+        assert r3.result(5) == 6
+        assert f"wait s22 e{r2.cuda_event}" not in nat.fake_device_log()
+        # num_returns > 1: every output carries the one event recorded after the body
+        a, b = ex.submit(la, lambda: (1, 2), (), None, 2)
+        assert (a.result(5), b.result(5)) == (1, 2) and a.cuda_event == b.cuda_event != 0
+        # pool tasks pick the stream up after set_lane_thread_init (fed.init sets the device late)
+        ex.set_lane_thread_init(0, lambda: 33)
+        r4 = ex.submit(0, lambda x, y: x + y, (a, b), None, 1)[0]
+        assert r4.result(5) == 3 and r4.cuda_stream == 33
+        assert f"wait s33 e{a.cuda_event}" in nat.fake_device_log()
+        # a host read synchronises the event (GIL released)
+        r4.device_sync()
+        assert f"sync e{r4.cuda_event}" in nat.fake_device_log()
+        ex.shutdown(True, 2.0)
+    finally:
+        nat.set_device_hooks(None)
+
+
+def test_ref_adopts_the_event_of_a_device_value():
+    from rayfed_b200.core import native
+    from rayfed_b200.core.runtime import DeviceValue, is_device_value
+
+    nat = native()
+    dv = DeviceValue({"k": 1}, 77, 5, None)
+    assert is_device_value(dv) and not is_device_value({"k": 1})
+    r = nat.Ref()
+    r.set_value(dv)
+    assert r.result(1) == {"k": 1} and r.cuda_event == 77 and r.cuda_stream == 5
+    # a decoder may return one too (the NVLink receiver does)
+    r2 = nat.Ref()
+    r2.set_decoder(lambda data, is_err: DeviceValue(data.decode(), 88, 6, None))
+    r2.set_raw(b"payload", False)
+    assert r2.result(1) == "payload" and r2.cuda_event == 88
+    plain = nat.Ref()
+    plain.set_value(3)
+    assert plain.cuda_event == 0
+    plain.device_sync()  # no event, no hooks: a no-op
