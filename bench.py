@@ -1,30 +1,35 @@
 #!/usr/bin/env python
 """bench.py — flagship benchmark of rayfed_b200 (driver contract).
 
-Flagship step = one **FedAvg round of ResNet-50 bf16** through the public fed
-API: every party (one per GPU) runs ``local_steps`` local SGD steps on its own
-synthetic 224x224 batches (H2D from pinned host memory each step; fwd/bwd via
-PyTorch/cuDNN; *our* fused local-SGD kernel), then all parties run *our* fused
-aggregate kernel (cross-party all-reduce + 1/N + all-gather over NVLink inside
-one kernel), and the round's losses are fetched with the collective ``fed.get``.
+Flagship step = one **FedAvg round of ResNet-50 bf16** through the public fed API: every party
+(one per GPU) runs ``local_steps`` local SGD steps on its own synthetic 224x224 batches (H2D from
+pinned host memory each step; fwd/bwd via PyTorch/cuDNN; *our* fused local-SGD kernel), then all
+parties run *our* fused aggregate kernel (cross-party all-reduce + 1/N + all-gather over NVLink
+inside one kernel), and the round's losses are fetched with the collective ``fed.get``.
 
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-Rank 0 prints ONE JSON line.  ``value`` = samples/s summed over all parties
-(device-timed with CUDA events, max over parties); ``e2e`` = the same through
-the public API with wall-clock around K rounds including the per-round
-``fed.get`` of the losses.  Secondary keys: ``rounds_per_sec``,
-``many_tiny_tasks`` (the reference's own benchmark, N-party generalisation),
-``push`` (K1 GB/s party0→party1) and ``aggregate`` (K2 µs + roofline fraction).
+Rank 0 prints ONE JSON line.  ``value`` = samples/s summed over all parties (device-timed with
+CUDA events, max over parties); ``e2e`` = the same through the public API with wall-clock around K
+rounds including the per-round ``fed.get`` of the losses.  Secondary keys:
 
-``--impl reference`` runs the unmodified reference from ``baseline/_ref`` if it
-is importable (it needs Ray, which is not in the offline wheelhouse) and
-otherwise prints ``{"impl": "reference", "unavailable": ...}``.
-``--impl reference-protocol`` measures the same FedAvg round with the
-aggregation done the reference way (weights pushed to one party over the
-wire-compatible gRPC transport, mean, pushed back).
+``aggregate``        K2 alone: µs, fraction of the NVLink/HBM roofline (NVLS byte count when the
+                     multicast path is in use; link peak measured in-run by the push sweep)
+``agg_check``        N>1: after an aggregate every party's weights are bit-identical and equal the
+                     fp32 oracle ``stack(weights).float().mean(0)`` computed over the DAG at p0
+``push``             N>1: the cross-party tensor push *through the API*
+                     (``sink.party(b).remote(make.party(a).remote(n))``), 1 KiB … 1 GiB: wall-clock
+                     per call, pipelined GB/s, and the device-timed push kernel
+``many_tiny_tasks``  the reference's own benchmark (N-party generalisation)
+``comm_bound``       rounds/s with ONE local step per round and aggregate-only rounds/s
+
+``--impl reference`` runs the unmodified reference from ``baseline/_ref`` through its own public API
+(``baseline/ref_arm.py``; Ray if importable, otherwise the ``baseline/ray_shim`` stand-in, labelled).
+``--impl reference-protocol`` measures the same FedAvg round with the aggregation done the
+reference way on OUR runtime over the wire-compatible gRPC transport.
+``--config llama-lora`` runs BASELINE config #4 (Llama-3-8B-shaped federated LoRA, fused Adam).
 """
 from __future__ import annotations
 
@@ -44,6 +49,7 @@ BATCH = 32
 LOCAL_STEPS = 4
 IMG = 224
 NUM_CLASSES = 1000
+NVLINK_REF_GBPS = 770.0  # peer-copy reference of the profiling recipe (900 nominal)
 
 
 def env_int(name, default):
@@ -51,6 +57,14 @@ def env_int(name, default):
         return int(os.environ.get(name, default))
     except ValueError:
         return default
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:  # noqa: BLE001
+        return {}
 
 
 class ClockSampler:
@@ -194,6 +208,17 @@ def make_worker_cls():
             self.bucket.flat_w.copy_(w.to(self.bucket.flat_w.device))
             return True
 
+        # -- agg_check: perturb (so the parties really differ), snapshot, aggregate, snapshot ----
+        def perturb_and_snapshot(self, rank):
+            g = torch.Generator(device=self.bucket.flat_w.device).manual_seed(77 + rank)
+            noise = torch.randn(self.bucket.numel, device=self.bucket.flat_w.device, generator=g) * 1e-2
+            self.bucket.flat_w.add_(noise.to(self.bucket.flat_w.dtype))
+            return self.bucket.flat_w.clone()
+
+        def aggregate_and_snapshot(self):
+            self.agg.aggregate()
+            return self.bucket.flat_w.clone()
+
     return BenchWorker
 
 
@@ -201,11 +226,132 @@ def addresses_for(n, base_port):
     return {f"p{i}": f"127.0.0.1:{base_port + i}" for i in range(n)}
 
 
+def _median(xs):
+    return statistics.median(xs) if xs else None
+
+
+def push_block(fed, parties, rank, quick=False):
+    """BASELINE config #5 through the public API: p0 produces a CUDA tensor, p1 consumes it."""
+    import torch
+
+    from rayfed_b200.proxy.nvlink import nvlink_proxy
+
+    a, b = parties[0], parties[1]
+    ch = nvlink_proxy.current_channel()
+
+    @fed.remote
+    class Peer:
+        def __init__(self):
+            self._cache = {}
+
+        def make(self, nbytes):
+            t = self._cache.get(nbytes)
+            if t is None:
+                t = self._cache[nbytes] = torch.randint(0, 255, (nbytes,), dtype=torch.uint8, device="cuda")
+            return t
+
+        def none(self):
+            return None
+
+        def sink(self, t):
+            # touches both ends on the device and reads 2 bytes back: the data really arrived
+            return 0 if t is None else int(t[0]) + int(t[-1])
+
+        def start_timing(self):
+            c = nvlink_proxy.current_channel()
+            if c is not None:
+                c.push_times = []
+            return True
+
+        def stop_timing(self):
+            c = nvlink_proxy.current_channel()
+            if c is None or c.push_times is None:
+                return []
+            torch.cuda.synchronize()
+            out = [(nb, e0.elapsed_time(e1) * 1e3) for nb, e0, e1 in c.push_times]
+            c.push_times = None
+            return out
+
+        def stats(self):
+            c = nvlink_proxy.current_channel()
+            return dict(c.stats) if c is not None else {}
+
+    pa = Peer.party(a).remote()
+    pb = Peer.party(b).remote()
+
+    def one(n):
+        src = pa.make.remote(n) if n else pa.none.remote()
+        return fed.get(pb.sink.remote(src))
+
+    sizes = [1 << 10, 1 << 16, 1 << 20, 1 << 24, 1 << 26, 1 << 28, 1 << 30]
+    if quick:
+        sizes = [1 << 10, 1 << 20, 1 << 26]
+    for _ in range(5):
+        one(0)
+    base_us = []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        one(0)
+        base_us.append((time.perf_counter() - t0) * 1e6)
+    base = _median(base_us)
+    rows = []
+    for n in sizes:
+        it = 20 if n <= (1 << 24) else (8 if n <= (1 << 28) else 4)
+        for _ in range(3):
+            one(n)
+        fed.get(pa.start_timing.remote())
+        lat = []
+        for _ in range(it):
+            t0 = time.perf_counter()
+            one(n)
+            lat.append((time.perf_counter() - t0) * 1e6)
+        # pipelined: M pushes in flight, one fed.get at the end
+        m = it
+        t0 = time.perf_counter()
+        outs = [pb.sink.remote(pa.make.remote(n)) for _ in range(m)]
+        fed.get(outs)
+        piped_s = time.perf_counter() - t0
+        ktimes = fed.get(pa.stop_timing.remote())
+        kus = _median([us for nb, us in ktimes if nb >= n]) if ktimes else None
+        # chunked tensors: several messages per tensor; sum the kernel time per tensor instead
+        if ktimes and kus is None:
+            per_tensor = sum(us for _, us in ktimes) / max(1, (it + m))
+            kus = per_tensor
+        rows.append({"bytes": n, "api_us": _median(lat), "api_us_minus_empty_call": _median(lat) - base,
+                     "pipelined_GBps": n * m / piped_s / 1e9,
+                     "kernel_us": kus, "kernel_GBps": (n / (kus * 1e-6) / 1e9) if kus else None,
+                     "messages_per_tensor": max(1, len(ktimes) // max(1, it + m)) if ktimes else None})
+    # K1b: fed.get broadcast (owner -> all) with and without the multicast push
+    bcast = []
+    if ch is not None:
+        for n in ([1 << 20, 1 << 26] if not quick else [1 << 20]):
+            row = {"bytes": n, "n_receivers": len(parties) - 1}
+            for mode in ("multicast", "unicast"):
+                nvlink_proxy._MC_PUSH_ENABLED = mode == "multicast"
+                for _ in range(2):
+                    fed.get(pa.make.remote(n))
+                t0 = time.perf_counter()
+                k = 6
+                for _ in range(k):
+                    fed.get(pa.make.remote(n))
+                row[mode + "_us"] = (time.perf_counter() - t0) / k * 1e6
+            nvlink_proxy._MC_PUSH_ENABLED = True
+            row["multicast_available"] = bool(ch.can_multicast)
+            bcast.append(row)
+    stats = fed.get([pa.stats.remote(), pb.stats.remote()])
+    peak = max([r["kernel_GBps"] for r in rows if r["kernel_GBps"]] or [0.0])
+    return {"path": f"{a}->{b} through fed.remote/fed.get (sink(make(n)))", "empty_call_us": base, "sizes": rows,
+            "broadcast": bcast, "kernel_peak_GBps": peak,
+            "zero_copy_tensors": stats[1].get("zero_copy_tensors"), "copied_tensors": stats[1].get("copied_tensors"),
+            "note": "api_us: wall clock of one produce->push->consume->fed.get chain; kernel_*: CUDA events around "
+                    "the push kernel on the sender's push stream; tensors > arena/4 are chunked (messages_per_tensor)"}
+
+
 def run_ours(args):
     import torch
 
     import rayfed_b200 as fed
-    from rayfed_b200.ops import kernels as K
+    from rayfed_b200.ops import kernels as K  # noqa: F401
 
     rank = env_int("RANK", 0)
     world = env_int("WORLD_SIZE", 1)
@@ -219,7 +365,7 @@ def run_ours(args):
     transport = "nvlink" if args.impl == "ours" else "grpc"
     comm = {"transport": transport, "retry_max_attempts": 200, "retry_initial_backoff_s": 0.05,
             "retry_max_backoff_s": 0.5, "retry_backoff_multiplier": 1.5, "timeout_in_ms": 120000,
-            "device_arena_bytes": 128 << 20,
+            "device_arena_bytes": args.arena_mib << 20,
             "messages_max_size_in_bytes": 1 << 30}
     fed.init(addresses=addresses_for(n, base), party=me, logging_level="warning",
              config={"cross_silo_comm": comm, "device": f"cuda:{local_rank}", "barrier_on_initializing": True},
@@ -235,13 +381,14 @@ def run_ours(args):
     def mean_weights(*ws):
         return torch.stack([w.float() for w in ws]).mean(0).to(ws[0].dtype)
 
-    def submit_round():
+    def submit_round(steps=None):
         """Issue one FedAvg round on every party; returns the FedObjects of the losses."""
+        steps = L if steps is None else steps
         if args.impl == "ours":
-            return [workers[p].round.remote(L) for p in parties]
+            return [workers[p].round.remote(steps) for p in parties]
         # reference-style aggregation through the DAG API over the gRPC transport:
         # local steps, weights -> p0, mean, -> every party
-        losses = [workers[p].local_round.remote(L) for p in parties]
+        losses = [workers[p].local_round.remote(steps) for p in parties]
         ws = [workers[p].flat_weights_host.remote() for p in parties]
         m = mean_weights.party(parties[0]).remote(*ws)
         for p in parties:
@@ -292,6 +439,7 @@ def run_ours(args):
     last = [float(x) for x in fed.get(prev)]
     fed.get([workers[p].sync.remote() for p in parties])
     e2e_s = time.perf_counter() - t0
+
     # max over parties of the wall-clock (every party ran the same loop; exchange the numbers)
     @fed.remote
     def _ident(x):
@@ -302,11 +450,6 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- secondary metrics -------------------------------------------------------
-    agg_us = None
-    if args.impl == "ours":
-        agg_us = max(fed.get([workers[p].time_aggregate.remote(20) for p in parties]))
-    tiny = many_tiny_tasks(fed, parties, iters=args.tiny_iters)
-
     samples_per_round = n * L * BATCH
     value = samples_per_round / (dev_ms_per_round * 1e-3)
     e2e_value = samples_per_round * K_steps / e2e_s
@@ -321,6 +464,8 @@ def run_ours(args):
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
+        "vs_baseline_note": "BASELINE.md publishes no number; the driver's --impl reference arm (unmodified "
+                            "reference over baseline/ray_shim) and --impl reference-protocol are the comparisons",
         "dtype": "bf16",
         "data": "synthetic (random 224x224 images in pinned host memory, random-init ResNet-50)",
         "impl": args.impl,
@@ -351,17 +496,86 @@ def run_ours(args):
         "gpu_launches": gpu_launches,
         "gpu_launches_by_kernel": launches[0][0],
         "clocks": clocks,
-        "many_tiny_tasks": tiny,
     }
-    if agg_us is not None:
-        nbytes = info["bucket_numel"] * 2
-        # bytes that must leave each GPU: serve (N-1)/N of my buffer to readers + write (N-1)/N to peers
-        link_bytes = 2 * (n - 1) / n * nbytes if n > 1 else 0
-        hbm_bytes = 2 * nbytes / max(n, 1) * (n if n > 1 else 1) + 2 * nbytes / max(n, 1)
-        roof_s = max(link_bytes / 770e9, (2 * nbytes / n) / 6485e9)
-        out["aggregate"] = {"us": agg_us, "bytes": nbytes, "roofline_us": roof_s * 1e6,
-                            "fraction_of_roofline": (roof_s * 1e6) / agg_us if agg_us else None,
-                            "roofline": "max(2*(N-1)/N*bytes / 770 GB/s measured NVLink, local shard r+w / 6485 GB/s measured HBM)"}
+
+    def guarded(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as e:  # noqa: BLE001  (a secondary metric must never cost the headline)
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    if args.impl == "ours":
+        # comm-bound variants of the headline: 1 local step per round, and the aggregate alone
+        def comm_bound():
+            for _ in range(2):
+                fed.get(submit_round(1))
+            fed.get([workers[p].sync.remote() for p in parties])
+            for p in parties:
+                workers[p].mark.remote("c0")
+            k = max(5, K_steps)
+            for _ in range(k):
+                submit_round(1)
+            for p in parties:
+                workers[p].mark.remote("c1")
+            ms1 = max(fed.get([workers[p].elapsed_ms.remote("c0", "c1") for p in parties])) / k
+            return {"local_steps_1_rounds_per_sec": 1e3 / ms1, "local_steps_1_ms_per_round": ms1}
+
+        guarded("comm_bound", comm_bound)
+
+        def aggregate_block():
+            agg_us = max(fed.get([workers[p].time_aggregate.remote(20) for p in parties]))
+            nbytes = info["bucket_numel"] * 2
+            peaks = measured_peaks()
+            hbm = float(peaks.get("hbm_gbs", 6485.0)) * 1e9
+            link = NVLINK_REF_GBPS * 1e9
+            push = out.get("push") if isinstance(out.get("push"), dict) else None
+            link_src = f"{NVLINK_REF_GBPS:.0f} GB/s/direction peer-copy reference (profiling recipe)"
+            if info["multicast"]:
+                # NVLS: the switch reduces/replicates; per direction a GPU moves its whole buffer once:
+                # serve (N-1)/N*S to the reducers + S/N multimem.st out; receive S/N reduced + (N-1)/N*S
+                link_bytes = float(nbytes) if n > 1 else 0.0
+                link_desc = "NVLS: ~S bytes per direction per GPU"
+            else:
+                link_bytes = 2.0 * (n - 1) / n * nbytes if n > 1 else 0.0
+                link_desc = "P2P two-shot: 2(N-1)/N*S bytes per direction per GPU"
+            # local HBM: every byte of my buffer is read once (by me or a peer) and written once
+            roof_s = max(link_bytes / link, 2.0 * nbytes / hbm)
+            d = {"us": agg_us, "bytes": nbytes, "roofline_us": roof_s * 1e6,
+                 "fraction_of_roofline": (roof_s * 1e6) / agg_us if agg_us else None,
+                 "aggregate_only_rounds_per_sec": 1e6 / agg_us if agg_us else None,
+                 "multicast": bool(info["multicast"]),
+                 "roofline": f"max({link_desc} / {link_src}, 2S / {hbm / 1e9:.0f} GB/s measured HBM)"}
+            if push and push.get("kernel_peak_GBps"):
+                d["nvlink_peer_GBps_measured_in_run"] = push["kernel_peak_GBps"]
+                d["fraction_of_roofline_vs_in_run_link_peak"] = (
+                    max(link_bytes / (push["kernel_peak_GBps"] * 1e9), 0.0) * 1e6 / agg_us if agg_us and n > 1 else None)
+            return d
+
+        if n > 1 and not args.no_push:
+            guarded("push", lambda: push_block(fed, parties, rank, quick=args.quick))
+        guarded("aggregate", aggregate_block)
+
+        if n > 1:
+            def agg_check():
+                before = [workers[p].perturb_and_snapshot.remote(i) for i, p in enumerate(parties)]
+                after = [workers[p].aggregate_and_snapshot.remote() for p in parties]
+
+                @fed.remote
+                def oracle(nb, *snaps):
+                    bs, as_ = snaps[:nb], snaps[nb:]
+                    exp = torch.stack([b.float() for b in bs]).mean(0)
+                    a0 = as_[0].float()
+                    max_err = float((a0 - exp).abs().max())
+                    # one bf16 ulp of the result is the resolution of the stored weights
+                    ulp = float((exp.abs().max() * 2.0 ** -8))
+                    equal = all(bool(torch.equal(as_[0], x)) for x in as_[1:])
+                    return {"parties_equal": equal, "max_err": max_err, "bf16_ulp_at_max": ulp,
+                            "within_1ulp": max_err <= ulp, "n_params": int(exp.numel())}
+
+                return fed.get(oracle.party(parties[0]).remote(len(parties), *before, *after))
+
+            guarded("agg_check", agg_check)
+    guarded("many_tiny_tasks", lambda: many_tiny_tasks(fed, parties, iters=args.tiny_iters))
     fed.shutdown()
     if rank == 0:
         print(json.dumps(out), flush=True)
@@ -398,27 +612,16 @@ def many_tiny_tasks(fed, parties, iters=2000):
 
 
 def run_reference(args):
-    """The unmodified reference needs Ray; say so if it is not importable."""
-    ref_dir = os.path.join(ROOT, "baseline", "_ref")
-    why = None
-    if not os.path.isdir(os.path.join(ref_dir, "fed")):
-        why = "reference not installed under baseline/_ref"
-    else:
-        try:
-            import ray  # noqa: F401
-        except Exception as e:  # noqa: BLE001
-            why = (f"reference is installed (pip --no-deps) but cannot import: it requires Ray "
-                   f"(fed/api.py:23 `import ray`) and no ray wheel exists in /opt/wheelhouse: {e!r}")
-    if why is None:
-        sys.path.insert(0, ref_dir)
-        try:
-            import fed  # noqa: F401
-
-            why = "reference import succeeded but no GPU FedAvg entry point exists in the reference to run"
-        except Exception as e:  # noqa: BLE001
-            why = f"reference import failed: {e!r}"
-    if env_int("RANK", 0) == 0:
-        print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
+    """The unmodified reference through its own public API (baseline/ref_arm.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import ref_arm
+    except Exception as e:  # noqa: BLE001
+        if env_int("RANK", 0) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": f"baseline/ref_arm.py failed to import: {e!r}"}),
+                  flush=True)
+        return
+    ref_arm.run(args, clock_sampler_cls=ClockSampler)
 
 
 def main():
@@ -427,10 +630,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-protocol"])
+    ap.add_argument("--config", default="resnet50", choices=["resnet50", "llama-lora"])
     ap.add_argument("--local-steps", type=int, default=LOCAL_STEPS)
     ap.add_argument("--tiny-iters", type=int, default=2000)
+    ap.add_argument("--arena-mib", type=int, default=1024, help="device arena region per (src,dst) pair")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-push", action="store_true", help="skip the API-level push sweep")
+    ap.add_argument("--quick", action="store_true", help="shorter secondary sweeps")
     args = ap.parse_args()
+    if args.config == "llama-lora":
+        sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+        import fedavg_llama_lora
+
+        return fedavg_llama_lora.bench_main(args)
     if args.impl == "reference":
         return run_reference(args)
     run_ours(args)

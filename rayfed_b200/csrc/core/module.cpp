@@ -276,8 +276,9 @@ PYBIND11_MODULE(_fedcore, m) {
       .def(
           "add_peer",
           [](SocketTransport& t, const std::string& name, const std::string& addr, int max_attempts,
-             double initial_backoff_s, double max_backoff_s, double multiplier, double timeout_s) {
+             double initial_backoff_s, double max_backoff_s, double multiplier, double timeout_s, int max_resends) {
             RetryPolicy rp;
+            rp.max_resends = max_resends < 0 ? 0 : max_resends;
             rp.max_attempts = max_attempts;
             rp.initial_backoff_s = initial_backoff_s;
             rp.max_backoff_s = max_backoff_s;
@@ -285,7 +286,8 @@ PYBIND11_MODULE(_fedcore, m) {
             t.add_peer(name, addr, rp, timeout_s);
           },
           py::arg("name"), py::arg("addr"), py::arg("max_attempts") = 5, py::arg("initial_backoff_s") = 5.0,
-          py::arg("max_backoff_s") = 30.0, py::arg("multiplier") = 2.0, py::arg("timeout_s") = 60.0)
+          py::arg("max_backoff_s") = 30.0, py::arg("multiplier") = 2.0, py::arg("timeout_s") = 60.0,
+          py::arg("max_resends") = 0)
       .def(
           "send",
           [](SocketTransport& t, const std::string& dest, const std::string& up, const std::string& down,
@@ -303,6 +305,8 @@ PYBIND11_MODULE(_fedcore, m) {
           },
           py::arg("dest"), py::arg("up"), py::arg("down"), py::arg("data"), py::arg("is_error") = false,
           py::arg("decoder") = py::none())
+      .def("set_max_message_bytes", &SocketTransport::set_max_message_bytes)
+      .def("max_message_bytes", &SocketTransport::max_message_bytes)
       .def(
           "drain",
           [](SocketTransport& t, double timeout) {

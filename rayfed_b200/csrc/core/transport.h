@@ -58,6 +58,11 @@ struct FrameHeader {
 #pragma pack(pop)
 
 struct RetryPolicy {
+  // `proxy_max_restarts` of the reference (fed/proxy/barriers.py:301-307: the sender proxy actor is
+  // restarted once and its in-flight sends are retried N times): a message that was written but
+  // not yet acknowledged when the connection died is re-queued up to this many times on the
+  // re-established connection instead of failing its send.  At-least-once, like Ray's task retry.
+  int max_resends = 0;
   int max_attempts = 5;
   double initial_backoff_s = 5.0;
   double max_backoff_s = 30.0;
@@ -116,18 +121,24 @@ class Peer {
     bool is_error;
     RefPtr ack;
     std::chrono::steady_clock::time_point deadline;
+    int resends = 0;  // times this message was re-queued after a lost connection
   };
 
   Peer(std::string name, std::string addr, std::string job, RetryPolicy retry, double timeout_s,
        TransportStats* stats)
       : name_(std::move(name)), addr_(std::move(addr)), job_(std::move(job)), retry_(retry),
         timeout_s_(timeout_s), stats_(stats) {
-    writer_ = std::thread([this] { writer_loop(); });
+    writer_ = std::thread([this] {
+      try {
+        writer_loop();
+      } catch (...) {  // nothing may escape a std::thread
+      }
+    });
   }
   ~Peer() { stop(); }
 
   void push(std::string up, std::string down, std::string data, bool is_error, RefPtr ack) {
-    auto m = std::make_unique<Outgoing>();
+    auto m = std::make_shared<Outgoing>();
     m->up = std::move(up);
     m->down = std::move(down);
     m->data = std::move(data);
@@ -246,7 +257,12 @@ class Peer {
         std::atomic_store(&conn_, c);
         reader_fd_ = fd;
         fd_.store(fd);
-        reader_ = std::thread([this, c] { reader_loop(c); });
+        reader_ = std::thread([this, c] {
+          try {
+            reader_loop(c);
+          } catch (...) {
+          }
+        });
         return true;
       }
       if (attempt == retry_.max_attempts) break;
@@ -313,7 +329,7 @@ class Peer {
 
   void writer_loop() {
     for (;;) {
-      std::unique_ptr<Outgoing> m;
+      std::shared_ptr<Outgoing> m;
       {
         std::unique_lock<std::mutex> lk(mu_);
         cv_.wait(lk, [&] { return stopping_ || (!q_.empty() && !writing_); });
@@ -338,7 +354,7 @@ class Peer {
   }
 
   // Writes one frame on the live connection. Caller owns the `writing_` token.
-  void transmit(std::unique_ptr<Outgoing> m) {
+  void transmit(std::shared_ptr<Outgoing> m) {
     FrameHeader h{};
     h.magic = kMagic;
     h.type = kFrameData;
@@ -358,18 +374,24 @@ class Peer {
     uint64_t id = m->id;
     {
       std::lock_guard<std::mutex> lk(mu_);
-      inflight_[id] = {ack, m->deadline};
+      inflight_[id] = InFlight{ack, m->deadline, retry_.max_resends > 0 ? m : nullptr};
     }
     auto c = std::atomic_load(&conn_);
     bool ok = c && fd_.load() == c->fd() && c->write_all(head.data(), head.size()) &&
               (nbytes <= 4096 || c->write_all(m->data.data(), nbytes));
     if (!ok) {
+      bool requeued = false;
       {
         std::lock_guard<std::mutex> lk(mu_);
         inflight_.erase(id);
+        if (m->resends < retry_.max_resends && !stopping_) {
+          m->resends++;
+          q_.push_front(m);
+          requeued = true;
+        }
       }
       close_conn();
-      ack->set_raw("connection to party '" + name_ + "' lost while sending", true);
+      if (!requeued) ack->set_raw("connection to party '" + name_ + "' lost while sending", true);
     } else {
       stats_->send_op_count.fetch_add(1, std::memory_order_relaxed);
       stats_->bytes_sent.fetch_add(nbytes, std::memory_order_relaxed);
@@ -388,6 +410,7 @@ class Peer {
       }
       FrameHeader h{};
       if (!c->read_all(&h, sizeof(h)) || h.magic != kMagic || h.type != kFrameAck) break;
+      if (h.data_len > (1u << 20)) break;  // an ack carries a short status string, never a payload
       std::string result(h.data_len, '\0');
       if (h.data_len && !c->read_all(&result[0], h.data_len)) break;
       RefPtr ack;
@@ -427,18 +450,34 @@ class Peer {
     for (auto& r : dead) r->set_raw("timed out waiting for party '" + name_ + "' to acknowledge", true);
   }
 
-  void fail_inflight(const std::string& why) {
-    std::map<uint64_t, std::pair<RefPtr, std::chrono::steady_clock::time_point>> dead;
+  void fail_inflight(const std::string& why, bool allow_resend = true) {
+    std::map<uint64_t, InFlight> dead;
+    bool requeued = false;
     {
       std::lock_guard<std::mutex> lk(mu_);
       dead.swap(inflight_);
+      if (allow_resend && !stopping_) {
+        // un-acknowledged messages go back to the head of the queue in their original order
+        for (auto it = dead.rbegin(); it != dead.rend();) {
+          auto& f = it->second;
+          if (f.msg && f.msg->resends < retry_.max_resends) {
+            f.msg->resends++;
+            q_.push_front(f.msg);
+            requeued = true;
+            it = decltype(it)(dead.erase(std::next(it).base()));
+          } else {
+            ++it;
+          }
+        }
+      }
     }
+    if (requeued) cv_.notify_all();
     for (auto& kv : dead) kv.second.first->set_raw(why, true);
   }
 
   void fail_all(const std::string& why) {
-    fail_inflight(why);
-    std::deque<std::unique_ptr<Outgoing>> dead;
+    fail_inflight(why, false);
+    std::deque<std::shared_ptr<Outgoing>> dead;
     {
       std::lock_guard<std::mutex> lk(mu_);
       dead.swap(q_);
@@ -452,8 +491,13 @@ class Peer {
   TransportStats* stats_;
   std::mutex mu_;
   std::condition_variable cv_;
-  std::deque<std::unique_ptr<Outgoing>> q_;
-  std::map<uint64_t, std::pair<RefPtr, std::chrono::steady_clock::time_point>> inflight_;
+  std::deque<std::shared_ptr<Outgoing>> q_;
+  struct InFlight {
+    RefPtr first;                                   // the ack future
+    std::chrono::steady_clock::time_point second;   // deadline
+    std::shared_ptr<Outgoing> msg;                  // kept only when resends are enabled
+  };
+  std::map<uint64_t, InFlight> inflight_;
   uint64_t next_id_ = 1;
   bool stopping_ = false;
   bool writing_ = false;
@@ -470,6 +514,10 @@ class SocketTransport {
   SocketTransport(std::string party, std::string job, std::shared_ptr<Mailbox> mailbox)
       : party_(std::move(party)), job_(std::move(job)), mailbox_(std::move(mailbox)) {}
   ~SocketTransport() { stop(); }
+
+  // Receive-side payload cap (bytes); frames announcing more are refused with code 413.
+  void set_max_message_bytes(uint64_t n) { max_message_bytes_.store(n ? n : kDefaultMaxMessageBytes); }
+  uint64_t max_message_bytes() const { return max_message_bytes_.load(); }
 
   // Returns "" on success, else an error description (port in use, ...).
   std::string listen(const std::string& addr) {
@@ -507,7 +555,12 @@ class SocketTransport {
       return e;
     }
     listen_fd_.store(fd);
-    accept_thread_ = std::thread([this, fd] { accept_loop(fd); });
+    accept_thread_ = std::thread([this, fd] {
+      try {
+        accept_loop(fd);
+      } catch (...) {
+      }
+    });
     return "";
   }
 
@@ -605,7 +658,11 @@ class SocketTransport {
       c.done = std::make_shared<std::atomic<bool>>(false);
       auto done = c.done;
       c.th = std::thread([this, cfd, done] {
-        serve(cfd);
+        try {
+          serve(cfd);
+        } catch (...) {  // nothing may escape a std::thread (std::terminate): drop the connection
+          stats_.rejected.fetch_add(1, std::memory_order_relaxed);
+        }
         done->store(true, std::memory_order_release);
       });
       conns_.push_back(std::move(c));
@@ -636,6 +693,24 @@ class SocketTransport {
         continue;
       }
       if (h.type != kFrameData) return;
+      // Every length comes from the peer: bound them BEFORE allocating (an unauthenticated
+      // 40-byte header must not be able to abort or exhaust the party).  The payload cap is
+      // messages_max_size_in_bytes (default 500 MiB, fed/proxy/grpc/grpc_options.py:28-29).
+      if (h.job_len > kMaxKeyLen || h.up_len > kMaxKeyLen || h.down_len > kMaxKeyLen ||
+          h.data_len > max_message_bytes_.load(std::memory_order_relaxed)) {
+        stats_.rejected.fetch_add(1, std::memory_order_relaxed);
+        FrameHeader a{};
+        a.magic = kMagic;
+        a.type = kFrameAck;
+        a.msg_id = h.msg_id;
+        a.code = 413;
+        std::string why = "message exceeds the receiver's limits (messages_max_size_in_bytes)";
+        a.data_len = why.size();
+        std::string out((const char*)&a, sizeof(a));
+        out += why;
+        c.write_all(out.data(), out.size());
+        return;  // the stream cannot be resynchronised past an oversize frame: drop the connection
+      }
       std::string job(h.job_len, '\0'), up(h.up_len, '\0'), down(h.down_len, '\0');
       if (h.job_len && !c.read_all(&job[0], h.job_len)) return;
       if (h.up_len && !c.read_all(&up[0], h.up_len)) return;
@@ -667,6 +742,9 @@ class SocketTransport {
     }
   }
 
+  static constexpr uint32_t kMaxKeyLen = 4096;                       // job name / seq-id strings
+  static constexpr uint64_t kDefaultMaxMessageBytes = 500ull << 20;  // the reference's gRPC default
+  std::atomic<uint64_t> max_message_bytes_{kDefaultMaxMessageBytes};
   std::string party_, job_;
   std::shared_ptr<Mailbox> mailbox_;
   std::mutex mu_;

@@ -263,7 +263,7 @@ class FedAvgWorker:
                     self._train_step(*self._static)
             torch.cuda.current_stream().wait_stream(s)
             self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
+            with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):  # other runtime threads keep issuing CUDA calls
                 self._static_loss = self._train_step(*self._static)
         self._static[0].copy_(x, non_blocking=True)
         self._static[1].copy_(y, non_blocking=True)

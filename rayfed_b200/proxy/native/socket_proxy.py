@@ -75,6 +75,9 @@ class NativeSenderProxy(SenderProxy):
             self._transport.add_peer(
                 name, addr, retry["max_attempts"], retry["initial_backoff_s"], retry["max_backoff_s"],
                 retry["multiplier"], timeout_s,
+                # proxy_max_restarts (fed/proxy/barriers.py:301-307): un-acknowledged sends are
+                # retried N times on a re-established connection instead of failing
+                int(cfg.proxy_max_restarts or 0),
             )
         self._max_bytes = cfg.messages_max_size_in_bytes
 
@@ -131,6 +134,9 @@ class NativeReceiverProxy(ReceiverProxy):
         nat = native()
         self._mailbox = nat.Mailbox()
         self._transport = nat.SocketTransport(party, job_name, self._mailbox)
+        if cfg.messages_max_size_in_bytes:
+            # enforced on RECEIVE, before any allocation (the reference: grpc.max_receive_message_length)
+            self._transport.set_max_message_bytes(int(cfg.messages_max_size_in_bytes))
         self._decoder = _PayloadDecoder(Deserializer(cfg.serializing_allowed_list))
         self._state = None
 

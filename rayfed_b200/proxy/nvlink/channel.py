@@ -312,6 +312,7 @@ class DeviceChannel:
         # error word in pinned host memory (UVA: same pointer on the device): kernels
         # store to it on a wait timeout / descriptor mismatch, the host reads it with a plain load
         self._status_host = torch.zeros(16, dtype=torch.int32).pin_memory()
+        self.push_times = None  # bench: list of (bytes, ev0, ev1) CUDA-event pairs around each push message
         self.stats = {"tensors_sent": 0, "bytes_sent": 0, "messages_sent": 0, "tensors_received": 0,
                       "bytes_received": 0, "messages_received": 0, "zero_copy_tensors": 0, "copied_tensors": 0,
                       "credit_stalls": 0, "bcast_tensors_sent": 0, "bcast_bytes_sent": 0, "blocks_released": 0,
@@ -511,7 +512,8 @@ class DeviceChannel:
             else:
                 stream.wait_stream(torch.cuda.current_stream(self._dev))
             tl = _tracing._TRACER
-            if tl is not None:
+            timed = tl is not None or self.push_times is not None
+            if timed:
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev0.record(stream)
             done = self._local(OFF_PUSH_DONE)
@@ -545,11 +547,14 @@ class DeviceChannel:
                            flag_ptr=flag if last else 0, flag_value=seq, done_counter_ptr=done, stream=stream,
                            device_index=self.device_index, desc_dst=base if last else 0, desc=desc if last else b"")
                     nbytes_all += p["pay"] + p["scales"]
-            if tl is not None:
+            if timed:
                 ev1 = torch.cuda.Event(enable_timing=True)
                 ev1.record(stream)
-                tl.device_span("fed_push_mc" if bcast else "fed_push", ev0, ev1, dest=dest_rank, seq=seq,
-                               bytes=nbytes_all)
+                if tl is not None:
+                    tl.device_span("fed_push_mc" if bcast else "fed_push", ev0, ev1, dest=dest_rank, seq=seq,
+                                   bytes=nbytes_all)
+                if self.push_times is not None:
+                    self.push_times.append((nbytes_all, ev0, ev1))
             for p in parts:
                 p["tensor"].record_stream(stream)
         st = self.stats
@@ -602,7 +607,7 @@ class DeviceChannel:
         with self._recv_lock:
             # K4: the stream — not a thread, not an SM — waits for the producer's release flag
             ext.stream_wait_value32(sh, flag, seq & 0xFFFFFFFF)
-            K.launch_counter.add("stream_wait_value32")
+            self.stats["stream_waits"] = self.stats.get("stream_waits", 0) + 1
             ext.desc_check(block, bytes.fromhex(meta["desc"]), self._status_host.data_ptr(), sh)
             K.launch_counter.add("fed_desc_check")
             zero_copy = (self.zero_copy and total >= self.zero_copy_min_bytes

@@ -251,3 +251,133 @@ def test_combined_sender_receiver_proxy():
     stats = get_runtime().get_named("SenderReceiverProxyActor")._get_stats()
     assert stats["send_op_count"] == 1 and stats["receive_op_count"] == 1
     fed.shutdown()
+
+
+def test_native_receiver_bounds_attacker_controlled_lengths():
+    """a 40-byte header announcing a huge payload must neither abort the party
+    (std::length_error escaping a std::thread) nor make it allocate; the connection is dropped
+    and the receiver keeps serving."""
+    import socket
+    import struct
+
+    from rayfed_b200.core import native
+
+    MAGIC, FRAME_DATA = 0x42444546, 1
+    nat = native()
+    port = free_ports(1)[0]
+    mb = nat.Mailbox()
+    srv = nat.SocketTransport("bob", "job", mb)
+    assert srv.listen(f"127.0.0.1:{port}") == ""
+    srv.set_max_message_bytes(1 << 20)
+    assert srv.max_message_bytes() == 1 << 20
+    try:
+        # FrameHeader {u32 magic, u16 type, u16 flags, u32 code, u32 job_len, u32 up_len, u32 down_len,
+        #              u64 msg_id, u64 data_len}: the magic is what a real client sends
+        cli = nat.SocketTransport("alice", "job", nat.Mailbox())
+        cli.add_peer("bob", f"127.0.0.1:{port}", 3, 0.05, 0.2, 1.5, 5.0)
+        ok = cli.send("bob", "1", "2", b"x" * 100, False, None)
+        assert ok.result(5) is not None
+        big = cli.send("bob", "3", "4", b"y" * (2 << 20), False, None)  # over the receiver's cap
+        with pytest.raises(Exception):
+            big.result(5)
+        # a raw, well-formed header (magic, type=data) with absurd lengths: the exact reproducer of the finding
+        s = socket.create_connection(("127.0.0.1", port))
+        s.sendall(struct.pack("<IBBHQIIIiQ", MAGIC, FRAME_DATA, 0, 0, 1, 3, 1, 1, 0, 0xFFFFFFFFFFFFFFF0))
+        s.settimeout(2)
+        try:
+            s.recv(4096)  # a 413 ack, then the server closes
+        except OSError:
+            pass
+        s.close()
+        # the server is still alive and serving
+        again = cli.send("bob", "5", "6", b"z", False, None)
+        assert again.result(5) is not None
+        assert mb.claim("5", "6").result(2) == b"z"
+        assert srv.stats()["rejected"] >= 1
+        cli.stop()
+    finally:
+        srv.stop()
+
+
+class _Evil:
+    def __reduce__(self):
+        import os
+
+        return (os.system, ("echo pwned > /tmp/rayfed_b200_pwned",))
+
+
+def test_nvlink_receiver_applies_the_allow_list_to_the_skeleton():
+    """the skeleton inside a ('fedcuda', k, skeleton) frame must go through the same
+    restricted unpickler as any other payload (fed/_private/serialization_utils.py:24-63)."""
+    import os
+
+    from rayfed_b200.exceptions import FedTaskError
+    from rayfed_b200.proxy.nvlink.nvlink_proxy import NvlinkReceiverProxy
+
+    marker = "/tmp/rayfed_b200_pwned"
+    if os.path.exists(marker):
+        os.unlink(marker)
+    port = free_ports(1)[0]
+    cfg = comm_config("native", serializing_allowed_list={"numpy": None})
+    rx = NvlinkReceiverProxy(f"127.0.0.1:{port}", "bob", "job", {}, cfg)
+    rx.start()
+    try:
+        evil = pickle.dumps(("fedcuda", 0, pickle.dumps(_Evil())))
+        rx.mailbox.deliver_raw("1", "2", evil, False)
+        ref = rx.get_data("alice", "1", "2")
+        with pytest.raises((pickle.UnpicklingError, FedTaskError, Exception)) as ei:
+            ref.result(5)
+        assert "not allowed" in str(ei.value) or "Unpickling" in type(ei.value).__name__
+        assert not os.path.exists(marker), "the allow-list was bypassed: code ran on the receiver"
+        # an allowed payload in the same envelope still decodes
+        ok = pickle.dumps(("fedcuda", 0, pickle.dumps({"a": 1})))
+        rx.mailbox.deliver_raw("3", "4", ok, False)
+        assert rx.get_data("alice", "3", "4").result(5) == {"a": 1}
+    finally:
+        rx.stop()
+
+
+@pytest.mark.parametrize("max_resends", [0, 2])
+def test_proxy_max_restarts_resends_unacknowledged_messages(max_resends):
+    """`proxy_max_restarts` (fed/proxy/barriers.py:301-307: the sender proxy is restarted and its
+    in-flight sends retried N times).  Here: a message written on a connection that dies before
+    the acknowledgement is re-sent on the re-established connection — or fails the send when the
+    option is off."""
+    import socket
+    import threading
+
+    from rayfed_b200.core import native
+
+    nat = native()
+    port = free_ports(1)[0]
+    swallowed = threading.Event()
+    lst = socket.socket()
+    lst.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+    lst.bind(("127.0.0.1", port))
+    lst.listen(1)
+
+    def black_hole():
+        c, _ = lst.accept()
+        c.recv(65536)  # take the frame, never acknowledge, die
+        c.close()
+        lst.close()
+        swallowed.set()
+
+    threading.Thread(target=black_hole, daemon=True).start()
+    cli = nat.SocketTransport("alice", "job", nat.Mailbox())
+    cli.add_peer("bob", f"127.0.0.1:{port}", 40, 0.05, 0.2, 1.5, 10.0, max_resends)
+    ack = cli.send("bob", "1", "2", b"payload", False, None)
+    assert swallowed.wait(5)
+    mb = nat.Mailbox()
+    srv = nat.SocketTransport("bob", "job", mb)  # the "restarted" receiver on the same address
+    assert srv.listen(f"127.0.0.1:{port}") == ""
+    try:
+        if max_resends:
+            assert ack.result(10) is not None
+            assert mb.claim("1", "2").result(5) == b"payload"
+        else:
+            with pytest.raises(Exception):
+                ack.result(10)
+    finally:
+        cli.stop()
+        srv.stop()
