@@ -274,22 +274,34 @@ class ActorHandle:
                 t.start()
                 self._threads.append(t)
 
-        def construct(a, k):
-            def body():
-                try:
-                    self._instance = cls(*a, **k)
-                    self._ready._set(True)
-                except BaseException as e:  # noqa: BLE001
-                    self._dead = RayActorError(f"The actor died because of an error raised in its creation task: {e!r}")
-                    self._ready._set(error=self._dead)
-
-            self._enqueue(body, is_ctor=True)
+        def finish_ctor(a, k):
+            try:
+                self._instance = cls(*a, **k)
+                self._ready._set(True)
+            except BaseException as e:  # noqa: BLE001
+                self._dead = RayActorError(f"The actor died because of an error raised in its creation task: {e!r}")
+                self._ready._set(error=self._dead)
 
         def fail(err):
             self._dead = RayActorError(f"actor creation failed: {err!r}")
             self._ready._set(error=self._dead)
 
-        _resolve_then(args, kwargs, construct, fail)
+        if not self._is_async and self._concurrency == 1:
+            # sequential actor: the constructor is the first entry of the mailbox; it waits there
+            # for its own arguments, and every method call queues up behind it
+            def ctor_body():
+                deps = [x for x in args if isinstance(x, ObjectRef)] + \
+                       [v for v in kwargs.values() if isinstance(v, ObjectRef)]
+                for d in deps:
+                    d._ev.wait()
+                    if d._error is not None:
+                        return fail(d._error)
+                finish_ctor(tuple(x._value if isinstance(x, ObjectRef) else x for x in args),
+                            {key: (v._value if isinstance(v, ObjectRef) else v) for key, v in kwargs.items()})
+
+            self._q.put(ctor_body)
+        else:
+            _resolve_then(args, kwargs, lambda a, k: self._enqueue(lambda: finish_ctor(a, k), is_ctor=True), fail)
 
     # -- execution -------------------------------------------------------------------
     def _enqueue(self, fn, is_ctor=False):
@@ -332,9 +344,36 @@ class ActorHandle:
             for r in refs:
                 r._set(error=err)
 
+        if not self._is_async and self._concurrency == 1:
+            # A plain (sequential) actor executes its tasks in SUBMISSION order, like Ray does per
+            # caller: a task whose arguments are still pending holds the ones behind it back.
+            def body():
+                self._ready._ev.wait()
+                if self._ready._error is not None:
+                    return fail(self._ready._error)
+                deps = [a for a in args if isinstance(a, ObjectRef)] + \
+                       [v for v in kwargs.values() if isinstance(v, ObjectRef)]
+                for d in deps:
+                    d._ev.wait()
+                    if d._error is not None:
+                        return fail(d._error)
+                if self._dead is not None:
+                    return fail(self._dead)
+                a = tuple(x._value if isinstance(x, ObjectRef) else x for x in args)
+                k = {key: (v._value if isinstance(v, ObjectRef) else v) for key, v in kwargs.items()}
+                try:
+                    _deliver(refs, num_returns, getattr(self._instance, method)(*a, **k))
+                except BaseException as e:  # noqa: BLE001
+                    fail(_wrap_error(e, what))
+
+            if self._dead is not None:
+                fail(self._dead)
+            else:
+                self._q.put(body)
+            return refs[0] if num_returns == 1 else refs
+
         def run(a, k):
-            # calls issued before the constructor has run (its arguments may still be pending)
-            # keep their order: they chain on the actor's ready future
+            # async / threaded actors: a call starts once its arguments and the constructor are done
             def after_ready(_):
                 if self._ready._error is not None:
                     return fail(self._ready._error)
@@ -372,8 +411,39 @@ class ActorHandle:
         if self._dead is None:
             self._dead = RayActorError(f"The actor is dead: {why}")
         if self._is_async:
-            if self._loop is not None and self._loop.is_running():
-                self._loop.call_soon_threadsafe(self._loop.stop)
+            loop = self._loop
+            if loop is not None and loop.is_running():
+                # A real actor is a process: when it dies the kernel closes its sockets.  Emulate
+                # that for what lives on this actor's event loop — gRPC aio servers are shut down,
+                # pending tasks cancelled — then stop the loop.
+                async def die():
+                    import gc
+
+                    for obj in gc.get_objects():
+                        try:
+                            if type(obj).__module__.startswith("grpc.aio") and type(obj).__name__ == "Server" \
+                                    and getattr(obj, "_loop", None) is loop:
+                                await obj.stop(0)
+                        except Exception:  # noqa: BLE001
+                            pass
+                    me = asyncio.current_task()
+                    for t in asyncio.all_tasks(loop):
+                        if t is not me:
+                            t.cancel()
+                    await asyncio.sleep(0)
+                    done.set_result(True)
+                    loop.stop()
+
+                done = concurrent.futures.Future()
+                loop.call_soon_threadsafe(lambda: asyncio.ensure_future(die()))
+                try:
+                    done.result(timeout=5)
+                except Exception:  # noqa: BLE001
+                    try:
+                        loop.call_soon_threadsafe(loop.stop)
+                    except RuntimeError:
+                        pass
+            self._instance = None
         else:
             # fail what is queued, then release the workers
             try:
@@ -383,6 +453,7 @@ class ActorHandle:
                 pass
             for _ in self._threads:
                 self._q.put(None)
+            self._instance = None
 
     def __repr__(self):
         return f"Actor({self._cls.__name__}, name={self._name!r})"

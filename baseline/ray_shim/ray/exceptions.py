@@ -4,7 +4,9 @@ class RayError(Exception):
 
 class RayTaskError(RayError):
     def __init__(self, function_name="", traceback_str="", cause=None):
-        super().__init__(f"{function_name}: {cause!r}")
+        # not super(): the dual-inheritance subclasses made by make_task_error() put the cause's own
+        # type (arbitrary __init__ signature) next in the MRO
+        Exception.__init__(self, f"{function_name}: {cause!r}")
         self.function_name = function_name
         self.traceback_str = traceback_str
         self.cause = cause

@@ -15,7 +15,12 @@ def _internal_kv_initialized():
     return _initialized
 
 
+def _b(x):
+    return x.encode() if isinstance(x, str) else x
+
+
 def _internal_kv_put(key, value, overwrite=True, namespace=None):
+    key, value = _b(key), _b(value)
     with _lock:
         existed = key in _store
         if overwrite or not existed:
@@ -24,16 +29,19 @@ def _internal_kv_put(key, value, overwrite=True, namespace=None):
 
 
 def _internal_kv_get(key, namespace=None):
+    key = _b(key)
     with _lock:
         return _store.get(key)
 
 
 def _internal_kv_del(key, namespace=None):
+    key = _b(key)
     with _lock:
         return 1 if _store.pop(key, None) is not None else 0
 
 
 def _internal_kv_exists(key, namespace=None):
+    key = _b(key)
     with _lock:
         return key in _store
 

@@ -206,6 +206,12 @@ def run(args, clock_sampler_cls=None):
     assert world == n, f"--gpus {n} but WORLD_SIZE={world}; launch with torchrun --nproc-per-node {n}"
     import torch
 
+    if not torch.cuda.is_available():
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "no CUDA device on this machine (the reference "
+                              "itself imports fine)", "reference_importable": True, "substrate": substrate}),
+                  flush=True)
+        return
     torch.cuda.set_device(local_rank)
     base = _env_int("MASTER_PORT", 29500) + 300
     parties = [f"p{i}" for i in range(n)]

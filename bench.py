@@ -201,6 +201,9 @@ def make_worker_cls():
             b.synchronize()
             return a.elapsed_time(b) / iters * 1e3  # µs
 
+        def agg_phases(self):
+            return self.agg.phase_breakdown(5)
+
         def flat_weights_host(self):
             return self.bucket.flat_w.cpu()
 
@@ -545,6 +548,13 @@ def run_ours(args):
                  "aggregate_only_rounds_per_sec": 1e6 / agg_us if agg_us else None,
                  "multicast": bool(info["multicast"]),
                  "roofline": f"max({link_desc} / {link_src}, 2S / {hbm / 1e9:.0f} GB/s measured HBM)"}
+            try:
+                ph = fed.get([workers[p].agg_phases.remote() for p in parties])
+                d["phases_us_party0"] = ph[0]
+                if all(ph):
+                    d["phases_us_max_over_parties"] = {k: max(x[k] for x in ph) for k in ph[0] if k != "ctas"}
+            except Exception as e:  # noqa: BLE001
+                d["phases_error"] = repr(e)[:200]
             if push and push.get("kernel_peak_GBps"):
                 d["nvlink_peer_GBps_measured_in_run"] = push["kernel_peak_GBps"]
                 d["fraction_of_roofline_vs_in_run_link_peak"] = (

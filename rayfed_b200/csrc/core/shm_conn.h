@@ -46,9 +46,13 @@ static constexpr size_t kShmHeaderBytes = 4096;
 static_assert(sizeof(ShmHeader) <= kShmHeaderBytes, "header must fit its page");
 
 // Read per connection attempt (not cached): cheap, and lets one process hold both kinds.
+// Default ON for same-host peers (the sender only offers it to loopback / unix addresses, and
+// either side may refuse): a tiny fed message costs a ring memcpy + a futex wake instead of a
+// TCP loopback round trip, which is what lets the N-1 sends of a fed.get broadcast and the N-1
+// receives of a fan-in overlap instead of queueing behind syscalls.  RAYFED_B200_SHM=0 disables.
 inline bool shm_enabled() {
   const char* e = std::getenv("RAYFED_B200_SHM");
-  return e && e[0] == '1';
+  return !(e && e[0] == '0');
 }
 inline uint32_t shm_ring_bytes() {
   const char* e = std::getenv("RAYFED_B200_SHM_RING_KB");
@@ -313,8 +317,10 @@ class Conn {
     }
   }
   bool peer_closed() {
-    pollfd p{fd_, POLLIN, 0};
-    if (::poll(&p, 1, 0) > 0 && (p.revents & (POLLHUP | POLLERR | POLLNVAL))) return true;
+    // POLLRDHUP: the peer shut its side down (FIN) — a server that refused a frame and left, a
+    // process that died — while our descriptor is still open; POLLHUP alone needs both directions.
+    pollfd p{fd_, (short)(POLLIN | POLLRDHUP), 0};
+    if (::poll(&p, 1, 0) > 0 && (p.revents & (POLLHUP | POLLRDHUP | POLLERR | POLLNVAL))) return true;
     return false;
   }
 

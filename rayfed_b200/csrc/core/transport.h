@@ -663,6 +663,9 @@ class SocketTransport {
         } catch (...) {  // nothing may escape a std::thread (std::terminate): drop the connection
           stats_.rejected.fetch_add(1, std::memory_order_relaxed);
         }
+        // tell the peer now (its writer may be parked on a full shared-memory ring); the descriptor
+        // itself is closed by the accept loop's reaper
+        ::shutdown(cfd, SHUT_RDWR);
         done->store(true, std::memory_order_release);
       });
       conns_.push_back(std::move(c));

@@ -18,6 +18,8 @@
 // with the cross-GPU synchronisation done inside the kernel on a signal pad
 // (per-CTA flags, st.release.sys / ld.acquire.sys), so there is no host hop and
 // no separate NCCL call or optimizer launch.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace fedk {
@@ -327,6 +329,99 @@ __global__ void __launch_bounds__(512) fed_aggregate_kernel(const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------
+// Plain FedAvg of bf16 weights (the flagship path): a lean, software-pipelined version of the
+// kernel above.  The generic kernel issues ALL of a thread's loads, then all of its stores — with
+// a 6 MB shard per party that is one trip, so on every GPU the reduce phase (egress-heavy: the
+// peers/switch pull my buffer) and the gather phase (ingress-heavy) run one after the other and
+// each NVLink direction idles half of the time.  Here every thread keeps kD vectors in flight and
+// re-issues the load of vector i+kD right before it reduces/stores vector i, with 2-3 CTAs per SM
+// (40 registers): loads and stores of different trips overlap, both directions stay busy.
+template <bool kUseMc, int kNP, int kD>
+__global__ void __launch_bounds__(512, 2) fed_allreduce_avg_kernel(const __grid_constant__ AggArgs a) {
+  const uint32_t epoch = a.epoch_dev ? ld_relaxed_sys_u32(a.epoch_dev) : a.epoch;
+  unsigned long long* ts = a.phase_ts ? a.phase_ts + (size_t)blockIdx.x * 4 : nullptr;
+  if (ts && threadIdx.x == 0) ts[0] = global_ns();
+  cta_party_barrier(a, epoch + 1);
+  if (ts && threadIdx.x == 0) ts[1] = global_ns();
+
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t nvec = a.shard_len >> 3;
+  const int N = a.n_parties;
+  const char* in_mc = reinterpret_cast<const char*>(a.mc_in) + a.shard_start * 2;
+  char* out_mc = reinterpret_cast<char*>(a.mc_out) + a.shard_start * 2;
+
+  uint4 x[kD][kNP];
+  auto issue = [&](int d, size_t v) {
+    if (kUseMc) {
+      x[d][0] = multimem_ld_reduce_bf16x8(in_mc + (v << 4));
+    } else {
+#pragma unroll
+      for (int j = 0; j < kNP; ++j)
+        if (j < N)
+          x[d][j] = ld_v4(reinterpret_cast<const char*>(a.in.p[(a.my_rank + j) % N]) + ((a.shard_start + (v << 3)) << 1));
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < kD; ++d) {
+    const size_t v = tid + (size_t)d * stride;
+    if (v < nvec) issue(d, v);
+  }
+  for (size_t v0 = tid; v0 < nvec; v0 += stride * kD) {
+#pragma unroll
+    for (int d = 0; d < kD; ++d) {
+      const size_t v = v0 + (size_t)d * stride;
+      if (v >= nvec) continue;
+      float acc[8];
+      if (kUseMc) {
+        float f[8];
+        unpack_bf16x8(x[d][0], f);
+        const float w0 = a.w[0];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = w0 * f[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < kNP; ++j) {
+          if (j < N) {
+            float f[8];
+            unpack_bf16x8(x[d][j], f);
+            const float wj = a.w[(a.my_rank + j) % N];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += wj * f[k];
+          }
+        }
+      }
+      // the slot is consumed: put the next trip's request on the wire before storing
+      const size_t vn = v + stride * kD;
+      if (vn < nvec) issue(d, vn);
+      uint4 o;
+      o.x = pack_bf16x2(acc[0], acc[1]);
+      o.y = pack_bf16x2(acc[2], acc[3]);
+      o.z = pack_bf16x2(acc[4], acc[5]);
+      o.w = pack_bf16x2(acc[6], acc[7]);
+      if (kUseMc) {
+        multimem_st_v4(out_mc + (v << 4), o);
+      } else {
+        const size_t off = (a.shard_start + (v << 3)) << 1;
+        for (int j = 0; j < N; ++j) st_v4(reinterpret_cast<char*>(a.out.p[(a.my_rank + j) % N]) + off, o);
+      }
+    }
+  }
+  if (ts && threadIdx.x == 0) ts[2] = global_ns();
+  cta_party_barrier(a, epoch + 2);
+  if (ts && threadIdx.x == 0) ts[3] = global_ns();
+  if (a.epoch_dev && threadIdx.x == 0) {
+    unsigned prev = atomicAdd(a.agg_done, 1u);
+    if (prev == gridDim.x - 1) {
+      *a.agg_done = 0;
+      *a.epoch_dev = epoch + 2;
+    }
+  }
+}
+
 // K5: N-party device barrier (replaces the reference's ping loop,
 // fed/proxy/barriers.py:497-523, once the symmetric heap is up).
 __global__ void fed_barrier_kernel(const __grid_constant__ AggArgs a) { cta_party_barrier(a, a.epoch + 1); }
@@ -366,10 +461,42 @@ __global__ void __launch_bounds__(512) fed_local_sgd_kernel(LocalSgdArgs a) {
 
 extern "C" {
 
+// Grid of the pipelined FedAvg kernel: every CTA of an SM resident at once (2 per SM with 512
+// threads at <= 64 registers), never more CTAs than 16-byte vectors / 512, and never more than the
+// signal pad has per-CTA barrier slots for (64 KiB / (kMaxParties * 4 B) = 1024).
+static int lean_grid(const AggArgs* a) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const unsigned long long nvec = a->shard_len >> 3;
+  long long want = (long long)((nvec + 511) / 512);
+  long long cap = (long long)sms * 2;
+  if (const char* e = getenv("RAYFED_B200_AGG_CTAS_PER_SM")) cap = (long long)sms * atoi(e);
+  long long g = want < cap ? want : cap;
+  if (g > 1024) g = 1024;
+  return (int)(g < 1 ? 1 : g);
+}
+
 cudaError_t fedk_launch_aggregate(const AggArgs* a, int blocks, cudaStream_t stream) {
   const bool mc = a->mc_in != nullptr && a->mc_out != nullptr && !a->out_fp8;
   const int n = a->n_parties;
   const bool state = a->kind != kAvg;
+  static const bool lean_off = [] {
+    const char* e = getenv("RAYFED_B200_AGG_LEAN");
+    return e && e[0] == '0';
+  }();
+  if (!state && !a->in_fp32 && !a->out_fp8 && !lean_off && n <= 8) {
+    const int g = lean_grid(a);
+    if (mc)          fed_allreduce_avg_kernel<true, 1, 4><<<g, 512, 0, stream>>>(*a);
+    else if (n == 1) fed_allreduce_avg_kernel<false, 1, 4><<<g, 512, 0, stream>>>(*a);
+    else if (n <= 2) fed_allreduce_avg_kernel<false, 2, 4><<<g, 512, 0, stream>>>(*a);
+    else if (n <= 4) fed_allreduce_avg_kernel<false, 4, 2><<<g, 512, 0, stream>>>(*a);
+    else             fed_allreduce_avg_kernel<false, 8, 1><<<g, 512, 0, stream>>>(*a);
+    return cudaGetLastError();
+  }
   // <multicast, preloaded parties per vector, vectors per trip>: kNP*kU 16-byte
   // requests (+ the optimizer state of kU vectors) are in flight per thread.
   if (mc) {
@@ -410,6 +537,11 @@ cudaError_t fedk_preload_aggregate() {
   FEDK_PRELOAD((fed_aggregate_kernel<false, 4, 2, false>));
   FEDK_PRELOAD((fed_aggregate_kernel<false, 8, 1, true>));
   FEDK_PRELOAD((fed_aggregate_kernel<false, 8, 1, false>));
+  FEDK_PRELOAD((fed_allreduce_avg_kernel<true, 1, 4>));
+  FEDK_PRELOAD((fed_allreduce_avg_kernel<false, 1, 4>));
+  FEDK_PRELOAD((fed_allreduce_avg_kernel<false, 2, 4>));
+  FEDK_PRELOAD((fed_allreduce_avg_kernel<false, 4, 2>));
+  FEDK_PRELOAD((fed_allreduce_avg_kernel<false, 8, 1>));
   FEDK_PRELOAD(fed_barrier_kernel);
   FEDK_PRELOAD(fed_local_sgd_kernel);
   return cudaSuccess;

@@ -204,6 +204,12 @@ PYBIND11_MODULE(_fedcuda, m) {
     check(fedk_preload_lora(), "preload lora kernels");
   }, "Force the (lazy) load of every kernel of this module: a first launch must never happen "
      "while a stream wait is parked (it would block the launching thread until the wait ends).");
+  m.def("module_loading_mode", [] {
+    using Fn = CUresult (*)(CUmoduleLoadingMode*);
+    CUmoduleLoadingMode mode;
+    cu_check(drv<Fn>("cuModuleGetLoadingMode")(&mode), "cuModuleGetLoadingMode");
+    return std::string(mode == CU_MODULE_EAGER_LOADING ? "eager" : "lazy");
+  });
   m.def("stream_create", [](int priority) {
     cudaStream_t s = nullptr;
     check(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, priority), "cudaStreamCreateWithPriority");
@@ -616,6 +622,9 @@ PYBIND11_MODULE(_fedcuda, m) {
            py::arg("lr"), py::arg("momentum"), py::arg("weight_decay"), py::arg("beta1"), py::arg("beta2"),
            py::arg("eps"), py::arg("sig"), py::arg("sig_peers"), py::arg("epoch_dev"), py::arg("agg_done"),
            py::arg("status"), py::arg("timeout_ns"), py::arg("blocks"))
+      .def("set_phase_ts", [](AggPlan& p, uint64_t ptr) { p.a.phase_ts = P<unsigned long long>(ptr); },
+           "debug: device buffer of 4 x u64 per CTA receiving %globaltimer stamps {start, entry barrier "
+           "done, loop done, exit barrier done}; 0 turns it off")
       .def("launch",
            [](AggPlan& p, uint32_t epoch, float lr, float bias_c1, float bias_c2, uint64_t stream) {
              p.a.epoch = epoch;

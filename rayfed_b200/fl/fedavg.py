@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import logging
+import os
 from typing import Callable, List, Optional, Sequence
 
 import torch
@@ -125,6 +126,9 @@ class FedAggregator:
             # faster than NVLS (N=4: 148 vs 161 us for 51 MB); NVLS halves the egress
             # bytes only asymptotically, so it is enabled from 8 parties.
             use_multicast = n >= 8
+            env = os.environ.get("RAYFED_B200_AGG_MC")  # experiments: force NVLS on (1) / off (0)
+            if env in ("0", "1"):
+                use_multicast = env == "1"
         if use_multicast is False or n == 1:
             mc = mc_out = 0
         uniform = all(abs(w - self.weights[0]) < 1e-12 for w in self.weights)
@@ -162,6 +166,33 @@ class FedAggregator:
         self._plan.launch(0, self.step_count, lr, stream)
         ev1.record(s)
         tl.device_span("fed_aggregate", ev0, ev1, round=self.step_count, shard_elems=self.shard_len)
+
+    def phase_breakdown(self, iters: int = 5):
+        """Per-phase device time of the pipelined FedAvg kernel (collective; plain ``fedavg`` of bf16
+        weights only): median over ``iters`` launches of the max over CTAs of {entry barrier, reduce +
+        gather loop, exit barrier} and the span first-start .. last-exit, in microseconds."""
+        ts = torch.zeros(4 * 1024, dtype=torch.int64, device=self.dev)
+        self._plan.set_phase_ts(ts.data_ptr())
+        rows = []
+        try:
+            for _ in range(iters):
+                ts.zero_()
+                self.aggregate()
+                torch.cuda.current_stream().synchronize()
+                t = ts.view(-1, 4)
+                t = t[t[:, 3] > 0].double()
+                if t.numel() == 0:
+                    return None
+                rows.append({"ctas": int(t.shape[0]),
+                             "entry_barrier_us": float((t[:, 1] - t[:, 0]).max()) / 1e3,
+                             "loop_us": float((t[:, 2] - t[:, 1]).max()) / 1e3,
+                             "loop_us_median_cta": float((t[:, 2] - t[:, 1]).median()) / 1e3,
+                             "exit_barrier_us": float((t[:, 3] - t[:, 2]).max()) / 1e3,
+                             "span_us": float(t[:, 3].max() - t[:, 0].min()) / 1e3})
+        finally:
+            self._plan.set_phase_ts(0)
+        rows.sort(key=lambda r: r["span_us"])
+        return rows[len(rows) // 2]
 
     def status(self) -> int:
         """0 = healthy; 2 = an in-kernel party barrier timed out."""

@@ -41,6 +41,31 @@ def run(device: str = "cuda:0"):
     K.unpack(buf.local_ptr, dst.data_ptr(), src.numel() * 4, flag_ptr=ctrl.data_ptr(), flag_value=1,
              done_counter_ptr=ctrl.data_ptr() + 12, status_ptr=ctrl.data_ptr() + 16, timeout_ns=int(5e9),
              device_index=dev.index or 0)
+    # the host-free receive path, loopback: multi-tensor push with a device descriptor, the
+    # consumer stream ordered by cuStreamWaitValue32, descriptor check, zero-copy view, credit kernel
+    from ..proxy.nvlink import channel as C
+
+    ext = K.cuda_ext()
+    ext.preload_kernels()
+    status = torch.zeros(4, dtype=torch.int32).pin_memory()
+    t1 = torch.arange(4096, dtype=torch.float32, device=dev)
+    t2 = torch.arange(1024, dtype=torch.float32, device=dev) * 2
+    desc = C.pack_desc(seq=1, job_hash=C.fnv1a32("smoke"), key=(1, 0, 2), offset=0, nbytes=C.HEADER + 16384 + 4096,
+                       dtype="float32", ndim=1, n_tensors=2, shape=(4096,))
+    block = buf.local_ptr + 65536 * 4
+    recv = ext.stream_create(0)
+    credit_words = torch.zeros(8, dtype=torch.int64, device=dev)
+    ext.stream_wait_value32(recv, ctrl.data_ptr() + 32, 1)  # parked BEFORE the push is launched
+    ext.desc_check(block, desc, status.data_ptr(), recv)
+    ev = ext.event_create(False)
+    ext.event_record(ev, recv)
+    K.push_multi([(t1.data_ptr(), C.HEADER, 16384), (t2.data_ptr(), C.HEADER + 16384, 4096)], block,
+                 flag_ptr=ctrl.data_ptr() + 32, flag_value=1, done_counter_ptr=ctrl.data_ptr() + 8,
+                 device_index=dev.index or 0, desc_dst=block, desc=desc)
+    ext.stream_wait_event(torch.cuda.current_stream().cuda_stream, ev)
+    view = buf.tensor(torch.float32, 4096, 65536 * 4 + C.HEADER)
+    got1 = view.clone()
+    ext.credit(credit_words.data_ptr(), 7, credit_words.data_ptr() + 8, 1, torch.cuda.current_stream().cuda_stream)
     # exact LoRA merge on the tensor cores (tcgen05/TMEM, TMA-fed persistent pipeline)
     m = n = 256
     r = 64
@@ -55,6 +80,10 @@ def run(device: str = "cuda:0"):
     assert (Wm.float() - ref.float()).abs().max().item() <= 2 ** -5 * max(1.0, ref.float().abs().max().item()), \
         "tcgen05 LoRA merge mismatch"
     assert torch.equal(src, dst), "push/unpack loopback mismatch"
+    assert torch.equal(got1, t1) and int(status[0]) == 0, "descriptor / stream-wait receive path mismatch"
+    assert credit_words.tolist()[:2] == [7, 1], "credit kernel mismatch"
+    ext.event_destroy(ev)
+    ext.stream_destroy(recv)
     assert torch.isfinite(loss).item()
     assert not torch.equal(w0, bucket.flat_w), "weights did not change"
     print(f"smoke ok: loss={loss.item():.4f} launches={K.launch_counter.by_kernel}")

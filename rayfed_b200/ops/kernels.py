@@ -192,6 +192,10 @@ class AggregatePlan:
                                         list(sig_peers), epoch_dev_ptr, agg_done_ptr, status_ptr, timeout_ns,
                                         blocks)
 
+    def set_phase_ts(self, ptr: int):
+        """Debug: per-CTA %globaltimer stamps of the pipelined FedAvg kernel (see aggregate.cu)."""
+        self._plan.set_phase_ts(int(ptr))
+
     def launch(self, epoch: int = 0, step: int = 1, lr: Optional[float] = None, stream=None):
         b1, b2 = self.beta1, self.beta2
         c1 = 1.0 / (1.0 - b1 ** step) if b1 < 1.0 else 1.0

@@ -273,6 +273,15 @@ class DeviceChannel:
         self._ext = K.cuda_ext()
         with torch.cuda.device(self.device_index):
             self._ext.preload_kernels()  # no first launch (= lazy module load) under a parked wait
+            try:
+                if self._ext.module_loading_mode() != "eager":
+                    logger.warning(
+                        "CUDA module loading is LAZY (the driver was initialised before `import rayfed_b200` could "
+                        "set CUDA_MODULE_LOADING=EAGER): the first launch of any kernel blocks its host thread "
+                        "while a device receive is parked on a peer's flag, which can deadlock the first round "
+                        "between parties. Export CUDA_MODULE_LOADING=EAGER for this process.")
+            except Exception:  # noqa: BLE001  (old driver without the query)
+                pass
         self._timeout_s = float(timeout_s)
         self._timeout_ns = int(timeout_s * 1e9)  # device waits use %globaltimer (ns)
         # A parked receive legitimately lasts as long as the producer's device work (the metadata

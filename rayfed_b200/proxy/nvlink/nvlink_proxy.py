@@ -43,7 +43,13 @@ logger = logging.getLogger(__name__)
 _MC_PUSH_ENABLED = _os.environ.get("RAYFED_B200_MC_PUSH", "1") != "0"
 _DEVQ = "__devq__"
 _TAG = "fedcuda"
+_TAG1 = "fedcuda1"  # single-block object: metadata rides inside the data frame (no receive-thread hop)
 _SMALL = "fedcuda-small"
+# Objects that fit one arena block of at most this size are announced inside their own data frame and
+# materialised by the consuming thread itself — two thread hand-overs less on the latency path.
+# Bigger / multi-block objects keep the eager, in-order receive thread (chunk assembly, prompt
+# copy-out and credit return).
+_INLINE_MAX_BYTES = int(_os.environ.get("RAYFED_B200_INLINE_META_BYTES", str(4 << 20)))
 _DEFAULT_MIN_BYTES = 4096
 
 
@@ -167,6 +173,11 @@ class NvlinkSenderProxy(NativeSenderProxy):
         with self._order_lock:
             # one metadata frame per arena block, sent the moment its push kernel is *launched*
             messages = channel.plan_messages(tensors)
+            if len(messages) == 1 and sum(p["pay"] + p["scales"] for p in messages[0]) <= _INLINE_MAX_BYTES:
+                meta = channel.push_message(dest_rank, messages[0], (up, down), event, pstream)
+                meta.update(last=True, n=len(tensors))
+                frame = pickle.dumps((_TAG1, json.dumps(meta).encode(), skeleton), protocol=5)
+                return self._transport.send(dest_party, up, down, frame, False, _ack_decoder)
             k = 0
             for i, parts in enumerate(messages):
                 meta = channel.push_message(dest_rank, parts, (up, down), event, pstream)
@@ -200,6 +211,11 @@ class NvlinkSenderProxy(NativeSenderProxy):
         ks = {}
         with self._order_lock:
             messages = channel.plan_messages(tensors)
+            if len(messages) == 1 and sum(p["pay"] + p["scales"] for p in messages[0]) <= _INLINE_MAX_BYTES:
+                meta = channel.push_message(None, messages[0], (up, down), event, pstream)
+                meta.update(last=True, n=len(tensors))
+                frame = pickle.dumps((_TAG1, json.dumps(meta).encode(), skeleton), protocol=5)
+                return {d: send(d, up, down, frame, False, _ack_decoder) for d in dest_parties}
             for i, parts in enumerate(messages):
                 meta = channel.push_message(None, parts, (up, down), event, pstream)
                 for d in dest_parties:
@@ -289,6 +305,17 @@ class NvlinkReceiverProxy(NativeReceiverProxy):
 
         def decode(data: bytes, is_error: bool):
             obj = loads(data)
+            if isinstance(obj, tuple) and len(obj) == 3 and obj[0] == _TAG1:
+                # single-block object: this (consuming) thread enqueues the stream wait itself
+                channel = current_channel()
+                if channel is None:
+                    raise RuntimeError("received a device-channel message but this party has no device channel")
+                meta = json.loads(obj[1])
+                got, ev, stream = channel.receive_message(channel.group.parties.index(src_party), meta, {})
+                tensors = dict(got)
+                value = _make_unpickler(io.BytesIO(obj[2]), loads.allowed, lambda idx: tensors[idx],
+                                        self._rehome).load()
+                return DeviceValue(value, ev.handle, stream, ev)
             if isinstance(obj, tuple) and len(obj) == 3 and obj[0] == _TAG:
                 _, k, skeleton = obj
                 if k == 0:  # no device parts: only (possibly) small tensors to re-home

@@ -8,6 +8,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
+# Before anything initialises the CUDA driver (torch.cuda.is_available() does): see rayfed_b200/__init__.py
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 # keep the adaptive spin short on small CI machines
 os.environ.setdefault("RAYFED_B200_SPIN_US", "20")
 

@@ -237,13 +237,23 @@ def test_flat_bucket_grads_accumulate_in_place_cpu():
     assert all(p.grad.abs().sum() == 0 for p in model.parameters())
 
 
-def test_reference_arm_reports_unavailable_without_ray():
+def test_reference_arm_runs_the_unmodified_reference():
+    """`bench.py --impl reference` must RUN the reference (baseline/_ref over Ray or the
+    baseline/ray_shim stand-in) — not declare it impossible.  Without a GPU the arm still has to
+    import the reference, say which substrate it would use, and exit 0 with the reason."""
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(root, "baseline", "_ref", "fed")):
+        pytest.skip("reference not installed under baseline/_ref")
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"],
-                         capture_output=True, text=True, timeout=120)
-    assert out.returncode == 0
+                         capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
-    assert line["impl"] == "reference" and ("unavailable" in line or "value" in line)
+    assert line["impl"] == "reference"
+    if "unavailable" in line:  # no CUDA device here: the only accepted reason on this box
+        assert "CUDA" in line["unavailable"], line
+        assert line.get("reference_importable") is True and line.get("substrate") in ("ray", "ray-shim"), line
+    else:
+        assert line["metric"] == "fedavg_resnet50_bf16_samples_per_sec" and line["value"] > 0

@@ -338,7 +338,7 @@ def test_nvlink_receiver_applies_the_allow_list_to_the_skeleton():
 
 
 @pytest.mark.parametrize("max_resends", [0, 2])
-def test_proxy_max_restarts_resends_unacknowledged_messages(max_resends):
+def test_proxy_max_restarts_resends_unacknowledged_messages(max_resends, monkeypatch):
     """`proxy_max_restarts` (fed/proxy/barriers.py:301-307: the sender proxy is restarted and its
     in-flight sends retried N times).  Here: a message written on a connection that dies before
     the acknowledgement is re-sent on the re-established connection — or fails the send when the
@@ -348,6 +348,9 @@ def test_proxy_max_restarts_resends_unacknowledged_messages(max_resends):
 
     from rayfed_b200.core import native
 
+    # plain socket data path: with the shared-memory offer the first frame on the wire would be the
+    # handshake, not the message this test wants to lose
+    monkeypatch.setenv("RAYFED_B200_SHM", "0")
     nat = native()
     port = free_ports(1)[0]
     swallowed = threading.Event()
