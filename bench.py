@@ -204,6 +204,47 @@ def make_worker_cls():
         def agg_phases(self):
             return self.agg.phase_breakdown(5)
 
+        def time_aggregate_variants(self, iters=20):
+            """The same aggregate with the other kernel / the other link path (collective)."""
+            from rayfed_b200.fl.fedavg import FedAggregator
+
+            def timed(agg):
+                s = torch.cuda.current_stream()
+                for _ in range(3):
+                    agg.aggregate()
+                a = torch.cuda.Event(enable_timing=True)
+                b = torch.cuda.Event(enable_timing=True)
+                a.record(s)
+                for _ in range(iters):
+                    agg.aggregate()
+                b.record(s)
+                b.synchronize()
+                return a.elapsed_time(b) / iters * 1e3
+
+            out = {}
+            mc_now = self.agg.uses_multicast
+            self.agg._plan.set_force_generic(True)
+            out["generic_kernel_" + ("nvls" if mc_now else "p2p")] = timed(self.agg)
+            self.agg._plan.set_force_generic(False)
+            if self.group.size > 1:
+                other = FedAggregator(self.bucket, self.group, self.channel, kind="fedavg", heap=self.heap,
+                                      use_multicast=not mc_now)
+                if other.uses_multicast != mc_now:
+                    tag = "nvls" if other.uses_multicast else "p2p"
+                    out["pipelined_kernel_" + tag] = timed(other)
+                    other._plan.set_force_generic(True)
+                    out["generic_kernel_" + tag] = timed(other)
+                    other._plan.set_force_generic(False)
+                # grid sweep of the pipelined kernel on both link paths (same cap in every party)
+                for agg, tag in ((self.agg, "nvls" if mc_now else "p2p"), (other, "p2p" if mc_now else "nvls")):
+                    if (tag == "nvls") != agg.uses_multicast:
+                        continue
+                    for cap in (16, 32, 64, 148):
+                        agg._plan.set_grid_cap(cap)
+                        out[f"pipelined_kernel_{tag}_grid{cap}"] = timed(agg, ) if True else None
+                    agg._plan.set_grid_cap(0)
+            return out
+
         def flat_weights_host(self):
             return self.bucket.flat_w.cpu()
 
@@ -548,6 +589,12 @@ def run_ours(args):
                  "aggregate_only_rounds_per_sec": 1e6 / agg_us if agg_us else None,
                  "multicast": bool(info["multicast"]),
                  "roofline": f"max({link_desc} / {link_src}, 2S / {hbm / 1e9:.0f} GB/s measured HBM)"}
+            try:
+                var = fed.get([workers[p].time_aggregate_variants.remote() for p in parties])
+                d["variants_us"] = {k: max(v[k] for v in var) for k in var[0]}
+                d["variants_us"]["pipelined_kernel_" + ("nvls" if info["multicast"] else "p2p")] = agg_us
+            except Exception as e:  # noqa: BLE001
+                d["variants_error"] = repr(e)[:200]
             try:
                 ph = fed.get([workers[p].agg_phases.remote() for p in parties])
                 d["phases_us_party0"] = ph[0]

@@ -395,7 +395,7 @@ def _teardown_runtime(wait_for_sending: bool):
     """What ``ray.shutdown()`` did for the reference: stop proxies, then the
     scheduler.  Pending acks were already drained by the CleanupManager."""
     try:
-        barriers._stop_proxies()
+        barriers._stop_proxies(drain=wait_for_sending)
         try:
             from .proxy.nvlink import nvlink_proxy
 

@@ -475,6 +475,7 @@ static int lean_grid(const AggArgs* a) {
   long long want = (long long)((nvec + 511) / 512);
   long long cap = (long long)sms * 2;
   if (const char* e = getenv("RAYFED_B200_AGG_CTAS_PER_SM")) cap = (long long)sms * atoi(e);
+  if (a->grid_cap > 0 && a->grid_cap < cap) cap = a->grid_cap;
   long long g = want < cap ? want : cap;
   if (g > 1024) g = 1024;
   return (int)(g < 1 ? 1 : g);
@@ -488,7 +489,7 @@ cudaError_t fedk_launch_aggregate(const AggArgs* a, int blocks, cudaStream_t str
     const char* e = getenv("RAYFED_B200_AGG_LEAN");
     return e && e[0] == '0';
   }();
-  if (!state && !a->in_fp32 && !a->out_fp8 && !lean_off && n <= 8) {
+  if (!state && !a->in_fp32 && !a->out_fp8 && !lean_off && !a->force_generic && n <= 8) {
     const int g = lean_grid(a);
     if (mc)          fed_allreduce_avg_kernel<true, 1, 4><<<g, 512, 0, stream>>>(*a);
     else if (n == 1) fed_allreduce_avg_kernel<false, 1, 4><<<g, 512, 0, stream>>>(*a);

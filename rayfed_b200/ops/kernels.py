@@ -192,6 +192,14 @@ class AggregatePlan:
                                         list(sig_peers), epoch_dev_ptr, agg_done_ptr, status_ptr, timeout_ns,
                                         blocks)
 
+    def set_force_generic(self, on: bool):
+        """Experiments: route plain FedAvg through the generic aggregate kernel."""
+        self._plan.set_force_generic(bool(on))
+
+    def set_grid_cap(self, n: int):
+        """Experiments: cap the pipelined FedAvg kernel's grid (0 = default, 2 CTAs per SM)."""
+        self._plan.set_grid_cap(int(n))
+
     def set_phase_ts(self, ptr: int):
         """Debug: per-CTA %globaltimer stamps of the pipelined FedAvg kernel (see aggregate.cu)."""
         self._plan.set_phase_ts(int(ptr))

@@ -418,7 +418,10 @@ def _start_sender_receiver_proxy(addresses: Dict, party: str, logging_level: str
     return host
 
 
-def _stop_proxies():
+def _stop_proxies(drain: bool = False, drain_timeout: float = 30.0):
+    """Stop both proxy hosts.  ``drain``: first let the sender flush what is still queued towards the
+    peers (frames whose acknowledgement nobody waits for — device metadata, capability records —
+    would otherwise be dropped by ``transport.stop()``)."""
     _HOSTS["sender"] = _HOSTS["receiver"] = None
     rt = get_runtime(create=False)
     if rt is None:
@@ -428,6 +431,13 @@ def _stop_proxies():
         host = rt.unregister_named(n)
         if host is not None and id(host) not in seen:
             seen.add(id(host))
+            if drain:
+                fn = getattr(host.proxy, "drain", None)
+                if callable(fn):
+                    try:
+                        fn(drain_timeout)
+                    except Exception:  # noqa: BLE001
+                        logger.debug("proxy drain failed", exc_info=True)
             host.stop()
 
 
