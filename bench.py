@@ -567,6 +567,9 @@ def run_ours(args):
         guarded("comm_bound", comm_bound)
 
         def aggregate_block():
+            # every party's earlier device work (the push sweep's last transfers) is complete before the
+            # collective is timed
+            fed.get([workers[p].sync.remote() for p in parties])
             agg_us = max(fed.get([workers[p].time_aggregate.remote(20) for p in parties]))
             nbytes = info["bucket_numel"] * 2
             peaks = measured_peaks()

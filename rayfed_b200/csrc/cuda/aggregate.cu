@@ -422,6 +422,19 @@ __global__ void __launch_bounds__(512, 2) fed_allreduce_avg_kernel(const __grid_
   }
 }
 
+// "I have reached the collective": one st.release.sys per peer, into word [my_rank] of the peers'
+// arrival arrays.  The launching stream then parks on its own arrival words with stream memory
+// operations (cuStreamWaitValue32) — see FedAggregator.aggregate: the compute kernel, which spins in
+// its barriers and fills the GPU, is not even launched before every party is there, so it can
+// never starve a local kernel (a queued push) that a late party is still waiting for.
+__global__ void fed_signal_kernel(const __grid_constant__ PeerPtrs arrive, int n_parties, int my_rank,
+                                  uint32_t value) {
+  const int t = threadIdx.x;
+  fence_acq_rel_sys();
+  if (t < n_parties && t != my_rank)
+    st_release_sys_u32(reinterpret_cast<uint32_t*>(arrive.p[t]) + my_rank, value);
+}
+
 // K5: N-party device barrier (replaces the reference's ping loop,
 // fed/proxy/barriers.py:497-523, once the symmetric heap is up).
 __global__ void fed_barrier_kernel(const __grid_constant__ AggArgs a) { cta_party_barrier(a, a.epoch + 1); }
@@ -473,8 +486,11 @@ static int lean_grid(const AggArgs* a) {
   }
   const unsigned long long nvec = a->shard_len >> 3;
   long long want = (long long)((nvec + 511) / 512);
-  long long cap = (long long)sms * 2;
-  if (const char* e = getenv("RAYFED_B200_AGG_CTAS_PER_SM")) cap = (long long)sms * atoi(e);
+  // One CTA per SM by default: the kernel spins in cross-party barriers, and half of every SM's
+  // registers / thread slots stay free for whatever else this GPU has queued (measured at N=2:
+  // 1 and 2 CTAs per SM are both link-bound, 115 us).  RAYFED_B200_AGG_CTAS_PER_SM=2 fills the SMs.
+  long long cap = (long long)sms;
+  if (const char* e = getenv("RAYFED_B200_AGG_CTAS_PER_SM")) cap = (long long)sms * (atoi(e) > 0 ? atoi(e) : 1);
   if (a->grid_cap > 0 && a->grid_cap < cap) cap = a->grid_cap;
   long long g = want < cap ? want : cap;
   if (g > 1024) g = 1024;
@@ -543,9 +559,16 @@ cudaError_t fedk_preload_aggregate() {
   FEDK_PRELOAD((fed_allreduce_avg_kernel<false, 2, 4>));
   FEDK_PRELOAD((fed_allreduce_avg_kernel<false, 4, 2>));
   FEDK_PRELOAD((fed_allreduce_avg_kernel<false, 8, 1>));
+  FEDK_PRELOAD(fed_signal_kernel);
   FEDK_PRELOAD(fed_barrier_kernel);
   FEDK_PRELOAD(fed_local_sgd_kernel);
   return cudaSuccess;
+}
+
+cudaError_t fedk_launch_signal(const PeerPtrs* arrive, int n_parties, int my_rank, uint32_t value,
+                               cudaStream_t stream) {
+  fed_signal_kernel<<<1, 32, 0, stream>>>(*arrive, n_parties, my_rank, value);
+  return cudaGetLastError();
 }
 
 cudaError_t fedk_launch_barrier(const AggArgs* a, cudaStream_t stream) {

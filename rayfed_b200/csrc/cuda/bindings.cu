@@ -638,6 +638,15 @@ PYBIND11_MODULE(_fedcuda, m) {
            py::arg("epoch"), py::arg("lr"), py::arg("bias_c1"), py::arg("bias_c2"), py::arg("stream"));
 
   m.def(
+      "signal_peers",
+      [](const std::vector<uint64_t>& arrive_ptrs, int my_rank, uint32_t value, uint64_t stream) {
+        PeerPtrs pp{};
+        fill_peers(pp, arrive_ptrs);
+        check(fedk_launch_signal(&pp, (int)arrive_ptrs.size(), my_rank, value, (cudaStream_t)(uintptr_t)stream),
+              "fed_signal launch");
+      },
+      py::arg("arrive_ptrs"), py::arg("my_rank"), py::arg("value"), py::arg("stream"));
+  m.def(
       "barrier",
       [](int n_parties, int my_rank, uint64_t sig, const std::vector<uint64_t>& sig_peers, uint32_t epoch,
          uint64_t status, long long timeout_ns, uint64_t stream) {

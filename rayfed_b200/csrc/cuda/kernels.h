@@ -147,6 +147,7 @@ cudaError_t fedk_preload_push();       // force the (lazy) load of every kernel 
 cudaError_t fedk_preload_aggregate();  // a first launch must never happen while a stream wait is parked
 cudaError_t fedk_preload_lora();
 cudaError_t fedk_launch_aggregate(const AggArgs* a, int blocks, cudaStream_t stream);
+cudaError_t fedk_launch_signal(const PeerPtrs* arrive, int n_parties, int my_rank, uint32_t value, cudaStream_t stream);
 cudaError_t fedk_launch_barrier(const AggArgs* a, cudaStream_t stream);
 cudaError_t fedk_launch_local_sgd(const LocalSgdArgs* a, int blocks, cudaStream_t stream);
 }

@@ -107,6 +107,9 @@ class FedAggregator:
             assert heap is not None, "multi-party aggregation needs the symmetric heap"
             self._pad = heap.alloc(f"aggpad/{bucket.name}/{kind}", 64 * 1024)
             sig_ptr, sig_peers = self._pad.local_ptr, list(self._pad.peer_ptrs)
+            # arrival words of the pre-launch rendezvous: the last 64 bytes of the pad (per-CTA barrier
+            # slots occupy 64 B per CTA from the start; grids never reach CTA 1023)
+            self._arrive_off = 64 * 1024 - 64
         else:
             self._pad_t = torch.zeros(16384, dtype=torch.int32, device=self.dev)
             sig_ptr, sig_peers = self._pad_t.data_ptr(), [self._pad_t.data_ptr()]
@@ -153,9 +156,19 @@ class FedAggregator:
             timeout_ns=self._timeout_ns, device_index=self.dev.index or 0,
         )
 
+    def _rendezvous(self, stream):
+        """Everybody reaches the collective before anybody launches the spinning kernel (stream
+        memory operations: no SM waits).  Skipped under CUDA-graph capture, where the in-kernel
+        entry barrier alone orders the parties (the caller then owns the no-starvation argument)."""
+        if self.group.size > 1 and not torch.cuda.is_current_stream_capturing():
+            off = self._arrive_off
+            K.rendezvous(arrive_peers=[p + off for p in self._pad.peer_ptrs], arrive_local=self._pad.local_ptr + off,
+                         my_rank=self.group.rank, value=self.step_count, stream=stream)
+
     def aggregate(self, stream=None, lr: Optional[float] = None):
         """Enqueue the fused aggregate on ``stream`` (default: current). Collective."""
         self.step_count += 1
+        self._rendezvous(stream)
         tl = _tracing._TRACER
         if tl is None or torch.cuda.is_current_stream_capturing():
             self._plan.launch(0, self.step_count, lr, stream)

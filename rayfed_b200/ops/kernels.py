@@ -212,6 +212,21 @@ class AggregatePlan:
         launch_counter.add("fed_aggregate")
 
 
+def rendezvous(*, arrive_peers: Sequence[int], arrive_local: int, my_rank: int, value: int, stream=None) -> None:
+    """SM-free N-party rendezvous in front of a collective kernel: one tiny kernel tells every peer
+    "party `my_rank` is here" (``st.release.sys`` into word ``my_rank`` of each peer's arrival array),
+    then the stream parks on its own arrival words with ``cuStreamWaitValue32`` — no SM is occupied
+    while waiting, so the collective kernel (which spins in its in-kernel barriers) is not launched
+    before every party has reached it and cannot starve local kernels a late party depends on."""
+    ext = cuda_ext()
+    sh = _stream_handle(stream)
+    ext.signal_peers([int(p) for p in arrive_peers], int(my_rank), int(value) & 0xFFFFFFFF, sh)
+    launch_counter.add("fed_signal")
+    for r in range(len(arrive_peers)):
+        if r != my_rank:
+            ext.stream_wait_value32(sh, int(arrive_local) + 4 * r, int(value) & 0xFFFFFFFF)
+
+
 def barrier(*, n_parties: int, my_rank: int, sig_ptr: int, sig_peers: Sequence[int], epoch: int, status_ptr: int = 0,
             timeout_ns: int = 0, stream=None) -> None:
     """K5."""

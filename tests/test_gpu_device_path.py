@@ -373,3 +373,49 @@ def _mixed_cpu_gpu(party, addresses):
 def test_mixed_cpu_and_gpu_parties_fall_back_to_the_host_path():
     addresses = make_addresses(["alice", "bob"])
     run_parties(_mixed_cpu_gpu, ["alice", "bob"], args=(addresses,), timeout=120)
+
+
+def _agg_behind_pushes(party, addresses):
+    """Regression (N=8 bench hang, round 2): the owner of a broadcast races ahead and launches the
+    cross-party aggregate while its pushes to the last receivers are still queued.  The aggregate
+    kernel spins in its barriers with every SM occupied; without the SM-free rendezvous in front of
+    it those pushes starve, the last receivers never reach the aggregate, and everybody deadlocks."""
+    import rayfed_b200 as fed
+    from rayfed_b200.fl import FedAggregator, FlatBucket, device_context
+
+    fed, dev = _init(party, addresses, device_arena_bytes=512 << 20)
+    parties = list(addresses)
+
+    @fed.remote
+    class W:
+        def __init__(self, rank):
+            self.group, self.heap, self.channel = device_context()
+            m = torch.nn.Linear(4096, 4096, bias=False, device="cuda", dtype=torch.bfloat16)
+            with torch.no_grad():
+                m.weight.fill_(float(rank + 1))
+            self.m = m
+            self.bucket = FlatBucket(m, self.heap, name="w", n_parties=self.group.size)
+            self.agg = FedAggregator(self.bucket, self.group, self.channel, kind="fedavg", heap=self.heap)
+            self.big = torch.ones(96 << 20, dtype=torch.uint8, device="cuda")
+
+        def burst(self):
+            return self.big  # 96 MiB, pushed to every other party by fed.get
+
+        def aggregate(self):
+            self.agg.aggregate()
+            torch.cuda.current_stream().synchronize()
+            return float(self.bucket.flat_w.float().mean())
+
+    ws = {p: W.party(p).remote(i) for i, p in enumerate(parties)}
+    for rep in range(3):
+        for _ in range(3):
+            got = fed.get(ws[parties[0]].burst.remote())  # owner returns at once; pushes still queued
+            assert got.numel() == 96 << 20
+        means = fed.get([ws[p].aggregate.remote() for p in parties])
+        assert means == [1.5, 1.5] or all(abs(m - means[0]) < 1e-6 for m in means), means
+    fed.shutdown()
+
+
+def test_aggregate_launched_behind_queued_pushes_does_not_deadlock():
+    addresses = make_addresses(["alice", "bob"])
+    run_parties(_agg_behind_pushes, ["alice", "bob"], args=(addresses,), timeout=180)
