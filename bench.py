@@ -626,8 +626,10 @@ def run_ours(args):
                     exp = torch.stack([b.float() for b in bs]).mean(0)
                     a0 = as_[0].float()
                     max_err = float((a0 - exp).abs().max())
-                    # one bf16 ulp of the result is the resolution of the stored weights
-                    ulp = float((exp.abs().max() * 2.0 ** -8))
+                    # one bf16 ulp (8 significant bits) at the largest magnitude: 2^(floor(log2 max) - 7)
+                    import math
+
+                    ulp = 2.0 ** (math.floor(math.log2(max(float(exp.abs().max()), 1e-30))) - 7)
                     equal = all(bool(torch.equal(as_[0], x)) for x in as_[1:])
                     return {"parties_equal": equal, "max_err": max_err, "bf16_ulp_at_max": ulp,
                             "within_1ulp": max_err <= ulp, "n_params": int(exp.numel())}

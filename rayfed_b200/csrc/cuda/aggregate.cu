@@ -491,6 +491,10 @@ static int lean_grid(const AggArgs* a) {
   // 1 and 2 CTAs per SM are both link-bound, 115 us).  RAYFED_B200_AGG_CTAS_PER_SM=2 fills the SMs.
   long long cap = (long long)sms;
   if (const char* e = getenv("RAYFED_B200_AGG_CTAS_PER_SM")) cap = (long long)sms * (atoi(e) > 0 ? atoi(e) : 1);
+  // NVLS (multimem.ld_reduce / multimem.st) wants FEW CTAs: measured at N=8, 51 MB: 163 us with 32
+  // CTAs, 169 with 16 or 64, 190 with 148 (the switch's reduction engines, not the SMs, do the work;
+  // more CTAs only add contention and a longer per-CTA tail in the exit barrier).
+  if (a->mc_in != nullptr && a->mc_out != nullptr && !getenv("RAYFED_B200_AGG_CTAS_PER_SM") && cap > 32) cap = 32;
   if (a->grid_cap > 0 && a->grid_cap < cap) cap = a->grid_cap;
   long long g = want < cap ? want : cap;
   if (g > 1024) g = 1024;
