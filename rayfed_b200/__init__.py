@@ -21,8 +21,25 @@ _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 # module loading, the *first* launch of any kernel has to load its module, which synchronises
 # with the context — i.e. blocks the launching host thread for as long as a wait is parked
 # (measured on B200: profiles/README.md "stream memory operations").  Between two parties that is
-# a deadlock in the first round.  Load everything up front instead.
-_os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+# a deadlock in the first round.  EAGER loading removes the hazard but costs tens of seconds of
+# start-up (every cubin of torch / cuDNN / cuBLAS is loaded up front), so it is switched on only
+# where a multi-party device job is evident — a torchrun / launcher environment with more than one
+# rank — or when asked for (RAYFED_B200_EAGER_MODULES=1; =0 never).  Whatever the outcome, the
+# device channel asks the driver which mode it really got and, under LAZY loading, gates each
+# receive on the host (it polls the flag and only then enqueues the — already satisfied — stream
+# wait), so no wait is ever parked and nothing can deadlock.
+def _want_eager_modules() -> bool:
+    flag = _os.environ.get("RAYFED_B200_EAGER_MODULES")
+    if flag is not None:
+        return flag != "0"
+    try:
+        return int(_os.environ.get("WORLD_SIZE", "1")) > 1 or bool(_os.environ.get("RAYFED_B200_PARTY"))
+    except ValueError:
+        return False
+
+
+if _want_eager_modules():
+    _os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 from .api import get, init, kill, remote, shutdown  # noqa: E402,F401
 from .exceptions import FedRemoteError, FedTaskError  # noqa: E402,F401

@@ -98,6 +98,7 @@ class FedAggregator:
                 self.var = torch.zeros_like(self.master)
         self.out_fp8 = out_fp8
         self._timeout_ns = int(timeout_s * 1e9)  # device waits use %globaltimer (ns)
+        self._host_gate = None  # decided at the first rendezvous from the driver's module-loading mode
         # A private signal pad per aggregator (symmetric when there are peers) and a
         # device-resident epoch: the launch is identical every round => graph-replayable.
         heap = heap or (channel.heap if channel is not None else None)
@@ -162,8 +163,16 @@ class FedAggregator:
         entry barrier alone orders the parties (the caller then owns the no-starvation argument)."""
         if self.group.size > 1 and not torch.cuda.is_current_stream_capturing():
             off = self._arrive_off
+            if self._host_gate is None:
+                mode = os.environ.get("RAYFED_B200_DEVICE_WAIT", "auto")  # auto | stream | host
+                try:
+                    lazy = K.cuda_ext().module_loading_mode() != "eager"
+                except Exception:  # noqa: BLE001
+                    lazy = True
+                self._host_gate = mode == "host" or (mode == "auto" and lazy)
             K.rendezvous(arrive_peers=[p + off for p in self._pad.peer_ptrs], arrive_local=self._pad.local_ptr + off,
-                         my_rank=self.group.rank, value=self.step_count, stream=stream)
+                         my_rank=self.group.rank, value=self.step_count, stream=stream, host_gate=self._host_gate,
+                         timeout_s=max(600.0, self._timeout_ns / 1e9))
 
     def aggregate(self, stream=None, lr: Optional[float] = None):
         """Enqueue the fused aggregate on ``stream`` (default: current). Collective."""

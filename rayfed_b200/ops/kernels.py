@@ -212,7 +212,11 @@ class AggregatePlan:
         launch_counter.add("fed_aggregate")
 
 
-def rendezvous(*, arrive_peers: Sequence[int], arrive_local: int, my_rank: int, value: int, stream=None) -> None:
+_gate_streams = {}
+
+
+def rendezvous(*, arrive_peers: Sequence[int], arrive_local: int, my_rank: int, value: int, stream=None,
+               host_gate: bool = False, timeout_s: float = 600.0) -> None:
     """SM-free N-party rendezvous in front of a collective kernel: one tiny kernel tells every peer
     "party `my_rank` is here" (``st.release.sys`` into word ``my_rank`` of each peer's arrival array),
     then the stream parks on its own arrival words with ``cuStreamWaitValue32`` — no SM is occupied
@@ -222,6 +226,31 @@ def rendezvous(*, arrive_peers: Sequence[int], arrive_local: int, my_rank: int, 
     sh = _stream_handle(stream)
     ext.signal_peers([int(p) for p in arrive_peers], int(my_rank), int(value) & 0xFFFFFFFF, sh)
     launch_counter.add("fed_signal")
+    if host_gate:
+        # lazy CUDA module loading: a parked stream wait would block first-time kernel launches of
+        # this process (see proxy/nvlink/channel.py), so the host waits instead — tiny D2H reads of
+        # the arrival words on a private stream; the stream waits below are then already satisfied
+        import time as _time
+
+        import torch
+
+        dev = torch.cuda.current_device()
+        gs = _gate_streams.get(dev)
+        if gs is None:
+            gs = _gate_streams[dev] = ext.stream_create(0)
+        want = int(value) & 0xFFFFFFFF
+        deadline = _time.monotonic() + timeout_s
+        pause = 5e-6
+        n = len(arrive_peers)
+        while True:
+            words = ext.read_u64s(int(arrive_local), (n + 1) // 2, gs)
+            vals = [(words[r // 2] >> (32 * (r % 2))) & 0xFFFFFFFF for r in range(n)]
+            if all(r == my_rank or ((vals[r] - want) & 0xFFFFFFFF) < 0x80000000 for r in range(n)):
+                break
+            if _time.monotonic() > deadline:
+                raise TimeoutError("a party never reached the collective (host-gated rendezvous)")
+            _time.sleep(pause)
+            pause = min(pause * 1.5, 2e-4)
     for r in range(len(arrive_peers)):
         if r != my_rank:
             ext.stream_wait_value32(sh, int(arrive_local) + 4 * r, int(value) & 0xFFFFFFFF)

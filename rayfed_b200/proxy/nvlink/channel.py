@@ -44,6 +44,7 @@ from __future__ import annotations
 
 import collections
 import logging
+import os
 import struct
 import threading
 import time
@@ -273,15 +274,20 @@ class DeviceChannel:
         self._ext = K.cuda_ext()
         with torch.cuda.device(self.device_index):
             self._ext.preload_kernels()  # no first launch (= lazy module load) under a parked wait
+            # LAZY module loading: the first launch of any kernel blocks its host thread while a stream
+            # wait is parked (measured), which can deadlock two parties in their first round.  Then
+            # receives are gated on the host: the flag is polled (tiny D2H reads on a private stream)
+            # and the — by then satisfied — stream wait is enqueued afterwards; nothing ever parks.
+            # With CUDA_MODULE_LOADING=EAGER the stream waits are enqueued at once (no host in the path).
+            mode = os.environ.get("RAYFED_B200_DEVICE_WAIT", "auto")  # auto | stream | host
             try:
-                if self._ext.module_loading_mode() != "eager":
-                    logger.warning(
-                        "CUDA module loading is LAZY (the driver was initialised before `import rayfed_b200` could "
-                        "set CUDA_MODULE_LOADING=EAGER): the first launch of any kernel blocks its host thread "
-                        "while a device receive is parked on a peer's flag, which can deadlock the first round "
-                        "between parties. Export CUDA_MODULE_LOADING=EAGER for this process.")
+                lazy = self._ext.module_loading_mode() != "eager"
             except Exception:  # noqa: BLE001  (old driver without the query)
-                pass
+                lazy = True
+            self._host_gate = (mode == "host") or (mode == "auto" and lazy)
+            if self._host_gate:
+                logger.info("device channel: CUDA module loading is lazy -> receives are host-gated "
+                            "(set CUDA_MODULE_LOADING=EAGER before the first CUDA call for parked stream waits)")
         self._timeout_s = float(timeout_s)
         self._timeout_ns = int(timeout_s * 1e9)  # device waits use %globaltimer (ns)
         # A parked receive legitimately lasts as long as the producer's device work (the metadata
@@ -302,12 +308,14 @@ class DeviceChannel:
         # -- receive side: one raw (non-pool) stream per source, so a parked wait on one source
         # never delays deliveries from another
         self._recv_lock = threading.Lock()
+        self._gate_lock = threading.Lock()
         with torch.cuda.device(self.device_index):
             self._recv_streams = [self._ext.stream_create(0) if s != group.rank else 0 for s in range(n)]
             self._recv_tstreams = [torch.cuda.ExternalStream(h, device=self._dev) if h else None
                                    for h in self._recv_streams]
             self._credit_stream = self._ext.stream_create(0)
             self._poll_stream = self._ext.stream_create(0)
+            self._gate_stream = self._ext.stream_create(0)
         self._view_bytes = [0] * n  # bytes currently handed out as zero-copy views, per source
         self._freed_idx = [0] * n  # entries I appended to freed_ring[me] in source s's block
         self._bfreed_idx = [0] * n
@@ -613,6 +621,8 @@ class DeviceChannel:
         parts = meta["parts"]
         sh = self._recv_streams[src_rank]
         ts = self._recv_tstreams[src_rank]
+        if self._host_gate:
+            self._gate(flag, seq, src_rank)
         with self._recv_lock:
             # K4: the stream — not a thread, not an SM — waits for the producer's release flag
             ext.stream_wait_value32(sh, flag, seq & 0xFFFFFFFF)
@@ -681,6 +691,28 @@ class DeviceChannel:
         self.stats["messages_received"] += 1
         self.stats["bytes_received"] += sum(p["pay"] + p["scales"] for p in parts)
         return out, ev, sh
+
+    def _gate(self, flag_ptr: int, seq: int, src_rank: int):
+        """Host gate (lazy module loading only): return once flags[src] >= seq is visible."""
+        ext = self._ext
+        word = flag_ptr & ~7
+        shift = 32 if (flag_ptr & 4) else 0
+        deadline = time.monotonic() + self._wait_timeout_s
+        pause = 5e-6
+        while True:
+            with self._gate_lock:
+                v = (ext.read_u64s(word, 1, self._gate_stream)[0] >> shift) & 0xFFFFFFFF
+            if ((v - (seq & 0xFFFFFFFF)) & 0xFFFFFFFF) < 0x80000000:
+                return
+            if time.monotonic() > deadline:
+                logger.error(f"device receive from party #{src_rank} (message {seq}) timed out after "
+                             f"{self._wait_timeout_s:.0f}s")
+                self._status_host[0] = 1
+                self.stats["forced_releases"] += 1
+                ext.write_u32(flag_ptr, seq & 0xFFFFFFFF)
+                return
+            time.sleep(pause)
+            pause = min(pause * 1.5, 5e-4)
 
     # -- flow control + watchdog (off the data path) --------------------------------------
     def _credit_loop(self):

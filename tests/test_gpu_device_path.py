@@ -74,6 +74,28 @@ def test_received_tensors_are_zero_copy_views_of_the_arena():
     run_parties(_zero_copy, ["alice", "bob"], args=(addresses,), timeout=120)
 
 
+def _host_gated(party, addresses):
+    """The fallback for lazy CUDA module loading: receives and the aggregate rendezvous are gated on
+    the host (no stream wait is ever parked); same results, same zero-copy views."""
+    os.environ["RAYFED_B200_DEVICE_WAIT"] = "host"
+    _zero_copy(party, addresses)
+
+
+def test_host_gated_receive_mode():
+    addresses = make_addresses(["alice", "bob"])
+    run_parties(_host_gated, ["alice", "bob"], args=(addresses,), timeout=120)
+
+
+def _host_gated_aggregate(party, addresses):
+    os.environ["RAYFED_B200_DEVICE_WAIT"] = "host"
+    _fused_aggregate(party, addresses)
+
+
+def test_host_gated_aggregate_rendezvous():
+    addresses = make_addresses(["alice", "bob"])
+    run_parties(_host_gated_aggregate, ["alice", "bob"], args=(addresses,), timeout=180)
+
+
 def _descriptor(party, addresses):
     import rayfed_b200 as fed
     from rayfed_b200.proxy.nvlink import channel as C
