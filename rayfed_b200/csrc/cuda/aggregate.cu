@@ -28,15 +28,20 @@ namespace fedk {
 // are final" (stream order + release).  Exit: "my reads of your inputs and my
 // writes of your outputs are done".
 __device__ __forceinline__ void cta_party_barrier(const AggArgs& a, uint32_t value) {
-  fence_acq_rel_sys();
+  // bar.sync orders every thread's earlier accesses before the signalling threads' fence at CTA
+  // scope; their fence.acq_rel.sys + st.release.sys then publishes them system-wide (the memory
+  // model's causality order is cumulative) — one system fence per signalling thread instead of one
+  // per thread of the CTA (a MEMBAR.SYS costs microseconds).
   __syncthreads();
   const int t = threadIdx.x;
   if (t < a.n_parties && t != a.my_rank) {
+    fence_acq_rel_sys();
     uint32_t* remote = reinterpret_cast<uint32_t*>(a.sig_peers.p[t]) + (size_t)blockIdx.x * kMaxParties + a.my_rank;
     st_release_sys_u32(remote, value);
     const uint32_t* mine = a.sig + (size_t)blockIdx.x * kMaxParties + t;
     if (!spin_wait_ge(mine, value, a.timeout_ns) && a.status)
       asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.status), "r"(2u) : "memory");
+    fence_acq_rel_sys();  // acquire side: peers' writes that preceded their signal are visible to the CTA
   }
   __syncthreads();
 }
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(512) fed_aggregate_kernel(const __grid_constan
   // graph-replayable epoch (kept in a register: writing to the parameter struct would
   // force a local-memory copy of all 700+ bytes of it)
   const uint32_t epoch = a.epoch_dev ? ld_relaxed_sys_u32(a.epoch_dev) : a.epoch;
-  cta_party_barrier(a, epoch + 1);
+  if (!a.entry_ordered) cta_party_barrier(a, epoch + 1);
 
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -342,7 +347,9 @@ __global__ void __launch_bounds__(512, 2) fed_allreduce_avg_kernel(const __grid_
   const uint32_t epoch = a.epoch_dev ? ld_relaxed_sys_u32(a.epoch_dev) : a.epoch;
   unsigned long long* ts = a.phase_ts ? a.phase_ts + (size_t)blockIdx.x * 4 : nullptr;
   if (ts && threadIdx.x == 0) ts[0] = global_ns();
-  cta_party_barrier(a, epoch + 1);
+  // With the pre-launch rendezvous (FedAggregator._rendezvous) every party's inputs are final before
+  // any party's kernel starts: the entry barrier has nothing left to order.
+  if (!a.entry_ordered) cta_party_barrier(a, epoch + 1);
   if (ts && threadIdx.x == 0) ts[1] = global_ns();
 
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

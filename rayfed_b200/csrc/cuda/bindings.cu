@@ -622,6 +622,7 @@ PYBIND11_MODULE(_fedcuda, m) {
            py::arg("lr"), py::arg("momentum"), py::arg("weight_decay"), py::arg("beta1"), py::arg("beta2"),
            py::arg("eps"), py::arg("sig"), py::arg("sig_peers"), py::arg("epoch_dev"), py::arg("agg_done"),
            py::arg("status"), py::arg("timeout_ns"), py::arg("blocks"))
+      .def("set_entry_ordered", [](AggPlan& p, bool v) { p.a.entry_ordered = v ? 1 : 0; })
       .def("set_force_generic", [](AggPlan& p, bool v) { p.a.force_generic = v ? 1 : 0; })
       .def("set_grid_cap", [](AggPlan& p, int n) { p.a.grid_cap = n; })
       .def("set_phase_ts", [](AggPlan& p, uint64_t ptr) { p.a.phase_ts = P<unsigned long long>(ptr); },

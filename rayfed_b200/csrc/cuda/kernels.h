@@ -100,6 +100,7 @@ struct AggArgs {
   uint32_t* agg_done;      // device counter for "last CTA" detection (zero between launches)
   uint32_t* status;
   long long timeout_ns;
+  int entry_ordered;             // 1: a pre-launch rendezvous already ordered the parties (skip the entry barrier)
   int force_generic;             // experiments: 1 = never take the pipelined FedAvg kernel
   int grid_cap;                  // experiments: upper bound on the pipelined kernel's grid (0: 2 CTAs per SM)
   unsigned long long* phase_ts;  // debug: per CTA {start, entry barrier done, loop done, exit barrier done}

@@ -99,6 +99,7 @@ class FedAggregator:
         self.out_fp8 = out_fp8
         self._timeout_ns = int(timeout_s * 1e9)  # device waits use %globaltimer (ns)
         self._host_gate = None  # decided at the first rendezvous from the driver's module-loading mode
+        self._entry_ordered = False
         # A private signal pad per aggregator (symmetric when there are peers) and a
         # device-resident epoch: the launch is identical every round => graph-replayable.
         heap = heap or (channel.heap if channel is not None else None)
@@ -161,7 +162,11 @@ class FedAggregator:
         """Everybody reaches the collective before anybody launches the spinning kernel (stream
         memory operations: no SM waits).  Skipped under CUDA-graph capture, where the in-kernel
         entry barrier alone orders the parties (the caller then owns the no-starvation argument)."""
-        if self.group.size > 1 and not torch.cuda.is_current_stream_capturing():
+        ordered = self.group.size > 1 and not torch.cuda.is_current_stream_capturing()
+        if ordered != self._entry_ordered:
+            self._plan.set_entry_ordered(ordered)
+            self._entry_ordered = ordered
+        if ordered:
             off = self._arrive_off
             if self._host_gate is None:
                 mode = os.environ.get("RAYFED_B200_DEVICE_WAIT", "auto")  # auto | stream | host
