@@ -264,8 +264,50 @@ def test_two_virtual_parties_on_one_gpu_rendezvous_in_kernel():
     assert torch.equal(bufs[0], ref) and torch.equal(bufs[1], ref)
 
 
+@pytest.mark.parametrize("nv", [4, 8])
+def test_virtual_parties_on_one_gpu_pipelined_fedavg(nv):
+    """N 'parties' = N streams on one GPU, each launching the pipelined FedAvg kernel of its rank
+    (`fed_allreduce_avg_kernel<false, 4, 2>` / `<false, 8, 1>`): weighted mean, in place, identical
+    result in every party's buffer."""
+    per = 32 * 512  # elements per shard
+    n = per * nv
+    xs = [torch.randn(n, device=DEV).to(torch.bfloat16) for _ in range(nv)]
+    bufs = [x.clone() for x in xs]
+    pads = [torch.zeros(16384, dtype=torch.int32, device=DEV) for _ in range(nv)]
+    ext = K.cuda_ext()
+    ext.preload_kernels()
+    streams = [ext.stream_create(0) for _ in range(nv)]
+    weights = [(i + 1.0) for i in range(nv)]
+    tot = sum(weights)
+    weights = [w / tot for w in weights]
+    torch.cuda.synchronize()
+    for r in range(nv):
+        K.aggregate(inputs=[b.data_ptr() for b in bufs], outputs=[b.data_ptr() for b in bufs], my_rank=r,
+                    shard_start=r * per, shard_len=per, kind=K.AGG_AVG, weights=weights, sig_ptr=pads[r].data_ptr(),
+                    sig_peers=[p.data_ptr() for p in pads], epoch=0, status_ptr=pads[r].data_ptr() + 60000,
+                    timeout_ns=int(3e9), stream=streams[r], blocks=4)
+    torch.cuda.synchronize()
+    for h in streams:
+        ext.stream_destroy(h)
+    if any(p[15000].item() for p in pads):
+        pytest.skip("the virtual parties' streams could not co-run on this GPU")
+    ref = torch.zeros(n, device=DEV)
+    for shard in range(nv):
+        sl = slice(shard * per, (shard + 1) * per)
+        a = torch.zeros(per, device=DEV)
+        for j in range(nv):
+            k = (shard + j) % nv  # the owner of a shard sums the parties in rotation order from itself
+            a += weights[k] * xs[k][sl].float()
+        ref[sl] = a
+    for b in bufs[1:]:
+        assert torch.equal(b, bufs[0])  # every party holds the same bits
+    # fp32 accumulation in the same order, but FFMA vs mul+add: allow the last bf16 bit
+    err = (bufs[0].float() - ref).abs()
+    assert bool((err <= ref.abs() * 2.0 ** -7 + 1e-6).all()), float(err.max())
+
+
 # -- K3: tcgen05/TMEM LoRA merge -----------------------------------------------------------------
-@pytest.mark.parametrize("impl", ["staged", "tma", "direct"])
+@pytest.mark.parametrize("impl", ["staged3", "staged", "tma", "direct"])
 @pytest.mark.parametrize("parties,r,m,n", [(2, 16, 256, 256), (8, 16, 512, 384), (4, 32, 128, 1024), (1, 64, 200, 96),
                                            (8, 16, 200, 192)])
 def test_lora_merge_tcgen05_matches_torch(parties, r, m, n, impl):

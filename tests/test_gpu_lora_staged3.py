@@ -1,6 +1,7 @@
-"""Single-GPU tests of code written after this round's GPU budget was spent (NOT yet executed on
-hardware).  Each case runs in a child process with a hard timeout: an unvalidated tcgen05 pipeline
-that deadlocks must cost one test, not the whole GPU session.  The module sorts last on purpose."""
+"""The `staged3` LoRA-merge pipeline (3-deep W ring decoupled from the 2-deep operand ring; the
+default implementation since round 2) against the fp32 reference and, bit for bit, against the
+`staged` pipeline.  Each case runs in a child process with a hard timeout: a tcgen05/mbarrier
+pipeline that deadlocks costs one test, not the GPU session."""
 import os
 import subprocess
 import sys
@@ -12,9 +13,6 @@ pytestmark = pytest.mark.gpu
 
 if not torch.cuda.is_available():
     pytest.skip("CUDA device required", allow_module_level=True)
-if os.environ.get("RAYFED_B200_NEXT_ROUND_TESTS") != "1":
-    pytest.skip("not yet executed on hardware: opt in with RAYFED_B200_NEXT_ROUND_TESTS=1 "
-                "(tools/round_first_call.sh and tools/round_multi_gpu_call.sh do)", allow_module_level=True)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
