@@ -614,7 +614,8 @@ class DeviceChannel:
 
         ext = self._ext
         bcast = bool(meta.get("bcast"))
-        seq, bid, off, total = meta["seq"], meta["bid"], meta["off"], meta["total"]
+        seq, bid, off, total = int(meta["seq"]), int(meta["bid"]), int(meta["off"]), int(meta["total"])
+        self._validate_meta(meta, off, total)
         region = (self._barena_off if bcast else OFF_ARENA) + src_rank * self.region_bytes
         block = self._local(region + off)
         flag = self._local((OFF_BFLAGS if bcast else OFF_FLAGS) + 4 * src_rank)
@@ -713,6 +714,36 @@ class DeviceChannel:
                 return
             time.sleep(pause)
             pause = min(pause * 1.5, 5e-4)
+
+    def _validate_meta(self, meta: dict, off: int, total: int):
+        """The metadata frame comes from a peer: never build a view or launch a copy from numbers
+        that do not describe a block inside that peer's region."""
+        import torch
+
+        if not (0 <= off and HEADER <= total and off % ALIGN == 0 and off + total <= self.region_bytes):
+            raise ValueError(f"device message outside the arena region: off={off} total={total}")
+        for p in meta["parts"]:
+            toff, pay, pad, scales = int(p["toff"]), int(p["pay"]), int(p["pad"]), int(p["scales"])
+            if not (HEADER <= toff and toff % 16 == 0 and 0 <= pay <= pad and 0 <= scales
+                    and toff + pad + scales <= total):
+                raise ValueError(f"device message part outside its block: {p}")
+            dtype = getattr(torch, str(p["dtype"]), None)
+            if not isinstance(dtype, torch.dtype):
+                raise ValueError(f"unknown dtype in device message: {p['dtype']!r}")
+            numel = 1
+            for d in p["shape"]:
+                numel *= int(d)
+            ne, e0 = int(p["ne"]), int(p["e0"])
+            if numel != int(p["numel"]) or not (0 <= e0 and 0 <= ne and e0 + ne <= numel):
+                raise ValueError(f"inconsistent tensor geometry in device message: {p}")
+            if p["whole"] and (e0 != 0 or ne != numel):
+                raise ValueError("a whole-tensor part must cover the tensor")
+            itemsize = torch.empty((), dtype=dtype).element_size()
+            mode = int(p["mode"])
+            want = ne * itemsize if mode == K.MODE_COPY else (ne * 2 if mode == K.MODE_F32_TO_BF16 else ne)
+            if pay != want or (mode == K.MODE_BF16_TO_FP8 and scales != ne // 32) or \
+                    mode not in (K.MODE_COPY, K.MODE_F32_TO_BF16, K.MODE_BF16_TO_FP8, K.MODE_BF16_SCALE):
+                raise ValueError(f"payload size does not match the tensor geometry: {p}")
 
     # -- flow control + watchdog (off the data path) --------------------------------------
     def _credit_loop(self):

@@ -121,3 +121,29 @@ def test_planner_respects_the_segment_limit_and_wire_formats():
     assert m[0]["mode"] == K.MODE_BF16_TO_FP8 and m[0]["pay"] == 4096 and m[0]["scales"] == 4096 // 32
     (m,) = plan8([torch.zeros(100, dtype=torch.bfloat16)])  # not a multiple of 32: plain copy
     assert m[0]["mode"] == K.MODE_COPY
+
+
+def test_receiver_validates_peer_supplied_metadata():
+    stub = types.SimpleNamespace(region_bytes=1 << 20)
+    check = lambda meta: C.DeviceChannel._validate_meta(stub, meta, int(meta["off"]), int(meta["total"]))  # noqa: E731
+    good = {"off": 0, "total": C.HEADER + 4096, "parts": [
+        {"t": 0, "e0": 0, "ne": 1024, "mode": K.MODE_COPY, "pay": 4096, "pad": 4096, "scales": 0, "toff": C.HEADER,
+         "whole": True, "numel": 1024, "dtype": "float32", "shape": [32, 32]}]}
+    check(good)
+    import copy
+
+    for mutate in (
+        lambda m: m.update(off=(1 << 20) - 256),                 # block runs past the region
+        lambda m: m.update(off=-256),
+        lambda m: m["parts"][0].update(toff=64),                  # inside the header
+        lambda m: m["parts"][0].update(toff=C.HEADER + 4096),     # past the block
+        lambda m: m["parts"][0].update(shape=[64, 64]),           # geometry does not match numel
+        lambda m: m["parts"][0].update(pay=8192, pad=8192),       # payload bigger than the tensor
+        lambda m: m["parts"][0].update(dtype="os"),               # not a dtype
+        lambda m: m["parts"][0].update(ne=512),                   # "whole" but partial
+        lambda m: m["parts"][0].update(mode=9),
+    ):
+        bad = copy.deepcopy(good)
+        mutate(bad)
+        with pytest.raises(ValueError):
+            check(bad)

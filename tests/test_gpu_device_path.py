@@ -321,7 +321,8 @@ def _overlap(party, addresses):
     t0 = time.time()
     assert fed.get(got) == 2.0
     if party == "bob":
-        assert t_local < 0.5, f"the local task waited for the in-flight push ({t_local:.2f}s)"
+        # had it waited for the push it would have taken the producer's full second of device time
+        assert t_local < 0.8, f"the local task waited for the in-flight push ({t_local:.2f}s)"
     fed.shutdown()
 
 
