@@ -473,6 +473,24 @@ class DeviceChannel:
         flush()
         return messages
 
+    @staticmethod
+    def layout_parts(parts: List[dict]) -> int:
+        """Place the parts behind the block header; returns the block size."""
+        toff = HEADER
+        for p in parts:
+            p["toff"] = toff
+            p["pad"] = _pad(p["pay"])
+            toff += p["pad"] + _pad(p["scales"])
+        return toff
+
+    @staticmethod
+    def part_meta(p: dict) -> dict:
+        """What the host frame says about one part (the receiver validates it, `_validate_meta`)."""
+        t = p.pop("tensor")
+        return {"t": p["t"], "e0": p["e0"], "ne": p["ne"], "mode": p["mode"], "pay": p["pay"],
+                "pad": p["pad"], "scales": p["scales"], "toff": p["toff"], "whole": p["whole"],
+                "numel": t.numel(), "dtype": str(t.dtype)[6:], "shape": list(t.shape)}
+
     def can_bcast(self, tensors) -> bool:
         """K1b applies to plain byte copies whose sizes the 16-byte multimem stores cover exactly."""
         if not self.can_multicast or self.wire_dtype is not None:
@@ -497,13 +515,8 @@ class DeviceChannel:
 
         bcast = dest_rank is None
         ext = self._ext
-        toff = HEADER
         metas = []
-        for p in parts:
-            p["toff"] = toff
-            p["pad"] = _pad(p["pay"])
-            toff += p["pad"] + _pad(p["scales"])
-        total = toff
+        total = self.layout_parts(parts)
         with self._send_lock:
             bid, off = self._alloc_block(dest_rank, total)
             if bcast:
@@ -583,10 +596,7 @@ class DeviceChannel:
             st["bytes_sent"] += nbytes_all
         st["messages_sent"] += 1
         for p in parts:
-            t = p.pop("tensor")
-            metas.append({"t": p["t"], "e0": p["e0"], "ne": p["ne"], "mode": p["mode"], "pay": p["pay"],
-                          "pad": p["pad"], "scales": p["scales"], "toff": p["toff"], "whole": p["whole"],
-                          "numel": t.numel(), "dtype": str(t.dtype)[6:], "shape": list(t.shape)})
+            metas.append(self.part_meta(p))
         return {"bid": bid, "off": off, "seq": seq, "total": total, "bcast": bcast, "parts": metas,
                 "desc": desc.hex()}
 
@@ -742,7 +752,7 @@ class DeviceChannel:
             mode = int(p["mode"])
             want = ne * itemsize if mode == K.MODE_COPY else (ne * 2 if mode == K.MODE_F32_TO_BF16 else ne)
             if pay != want or (mode == K.MODE_BF16_TO_FP8 and scales != ne // 32) or \
-                    mode not in (K.MODE_COPY, K.MODE_F32_TO_BF16, K.MODE_BF16_TO_FP8, K.MODE_BF16_SCALE):
+                    mode not in (K.MODE_COPY, K.MODE_F32_TO_BF16, K.MODE_BF16_TO_FP8):
                 raise ValueError(f"payload size does not match the tensor geometry: {p}")
 
     # -- flow control + watchdog (off the data path) --------------------------------------

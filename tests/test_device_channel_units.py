@@ -147,3 +147,29 @@ def test_receiver_validates_peer_supplied_metadata():
         mutate(bad)
         with pytest.raises(ValueError):
             check(bad)
+
+
+@pytest.mark.parametrize("wire", [None, "bf16", "fp8_e4m3"])
+def test_every_planned_message_passes_the_receivers_validation(wire):
+    """Sender-side planning and receiver-side validation must agree for whole tensors, packed
+    objects and chunked tensors in every wire format (CPU tensors stand in: only geometry matters)."""
+    import torch
+
+    region = 8 << 20
+    stub = types.SimpleNamespace(wire_dtype=wire, max_message_bytes=max(region // 4, 1 << 20), region_bytes=region)
+    stub._plan_tensor = lambda t: C.DeviceChannel._plan_tensor(stub, t)
+    tensors = [torch.zeros(1024, dtype=torch.float32), torch.zeros(33, 7, dtype=torch.bfloat16),
+               torch.zeros(4096, dtype=torch.bfloat16), torch.zeros(3 << 20, dtype=torch.bfloat16),
+               torch.zeros(700_001, dtype=torch.float32), torch.zeros(5, dtype=torch.int64),
+               torch.zeros(64, 64, dtype=torch.uint8), torch.zeros(16, dtype=torch.bool)]
+    messages = C.DeviceChannel.plan_messages(stub, tensors)
+    assert len(messages) > 2          # the two big tensors are chunked
+    covered = {}
+    for parts in messages:
+        total = C.DeviceChannel.layout_parts(parts)
+        assert total <= stub.max_message_bytes
+        meta = {"off": 0, "total": total, "parts": [C.DeviceChannel.part_meta(p) for p in parts]}
+        C.DeviceChannel._validate_meta(stub, meta, 0, total)
+        for p in meta["parts"]:
+            covered[p["t"]] = covered.get(p["t"], 0) + p["ne"]
+    assert covered == {i: t.numel() for i, t in enumerate(tensors)}
