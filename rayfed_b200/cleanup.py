@@ -17,8 +17,8 @@ from __future__ import annotations
 import logging
 import os
 import signal
-import threading
 import time
+import weakref
 
 from ._private.message_queue import MessageQueueManager
 from .exceptions import FedRemoteError, FedTaskError
@@ -39,15 +39,20 @@ class CleanupManager:
         self._last_sending_error = None
         self._exit_on_sending_failure = False
         self._expose_error_trace = False
-        # sends whose outcome is not known yet; success is retired by a completion
-        # callback, only failures are handed to the queue threads
-        self._pending = 0
-        self._pending_err = 0
-        self._pending_cv = threading.Condition()
-        self._draining = False  # a stop() is waiting: completions must notify
-        # sends whose completion callback has not run yet (id -> ref); lets stop() close the
-        # window between "the future resolved" and "its failure was queued"
-        self._watch = {}
+        # Sends whose outcome is not known yet are counted by a native tracker: an acknowledged
+        # send is retired on the transport thread without the GIL (csrc/core/send_tracker.h); only
+        # failures — and outcomes that are Python objects — come back through `_on_settled`.
+        from .core import native
+
+        # the tracker keeps its handler alive from C++ (invisible to the GC): hand it a weak method
+        weak = weakref.WeakMethod(self._on_settled)
+
+        def handler(r, pack, is_error):
+            m = weak()
+            if m is not None:
+                m(r, pack, is_error)
+
+        self._tracker = native().SendTracker(handler)
 
     def start(self, exit_on_sending_failure=False, expose_error_trace=False):
         self._exit_on_sending_failure = exit_on_sending_failure
@@ -65,21 +70,22 @@ class CleanupManager:
         otherwise a party that shuts down right after a failure would leave its
         peers waiting for data that will never come.
         """
-        self._draining = True
-        # A send future may have resolved an instant ago on another thread while its
-        # completion callback (which queues a failure) is still running: let it settle.
+        tracker = self._tracker
+        tracker.set_draining(True)
+        # A send future may have resolved an instant ago on another thread while its settle step
+        # (which queues a failure) is still running: let it finish.
         deadline = time.monotonic() + 2.0
-        while time.monotonic() < deadline and any(r.done() for r in list(self._watch.values())):
+        while time.monotonic() < deadline and tracker.settling():
             time.sleep(0.0005)
         if wait_for_sending:
-            with self._pending_cv:
-                self._pending_cv.wait_for(lambda: self._pending <= 0 or not self._sending_data_q.is_started(),
-                                          timeout=drain_timeout_s)
+            deadline = time.monotonic() + drain_timeout_s
+            while self._sending_data_q.is_started() and not tracker.wait_idle(0.05) and time.monotonic() < deadline:
+                pass
         # Data queue first: draining it may enqueue replacement errors.
         self._sending_data_q.stop(wait_for_sending=True)
-        with self._pending_cv:
-            self._pending_cv.wait_for(lambda: self._pending_err <= 0, timeout=error_drain_timeout_s)
+        tracker.wait_idle(error_drain_timeout_s, True)
         self._sending_error_q.stop(wait_for_sending=wait_for_sending)
+        tracker.bury()
 
     def push_to_sending(self, obj_ref, dest_party: str = None, upstream_seq_id=-1, downstream_seq_id=-1,
                         is_error: bool = False):
@@ -87,41 +93,28 @@ class CleanupManager:
         replacement error has to be shipped under the same key.
 
         Unlike the reference (one ``ray.get`` per send on a polling thread,
-        fed/cleanup.py:150-152) a successful send is retired by its completion
-        callback; only failures go through the queue thread."""
-        pack = (obj_ref, dest_party, upstream_seq_id, downstream_seq_id)
-        with self._pending_cv:
-            self._pending += 1
-            if is_error:
-                self._pending_err += 1
-        q = self._sending_error_q if is_error else self._sending_data_q
-        key = id(pack)
-        self._watch[key] = obj_ref
+        fed/cleanup.py:150-152) an acknowledged send is retired natively on the thread that
+        received the acknowledgement; only failures go through the queue thread."""
+        self._tracker.watch(obj_ref, (obj_ref, dest_party, upstream_seq_id, downstream_seq_id), bool(is_error))
 
-        def on_done(r):
-            self._watch.pop(key, None)
+    def _on_settled(self, r, pack, is_error):
+        """Slow path of the tracker (GIL held): the send did not resolve to a plain acknowledgement."""
+        ok = False
+        try:
+            ok = r.exception() is None and bool(r.result())
+        except BaseException:  # noqa: BLE001
             ok = False
-            try:
-                ok = r.exception() is None and bool(r.result())
-            except BaseException:  # noqa: BLE001
-                ok = False
-            if ok or not q.is_started():
-                self._retire(is_error)
-            else:
-                q.append(pack)
-
-        obj_ref.add_done_callback(on_done)
+        q = self._sending_error_q if is_error else self._sending_data_q
+        if ok or not q.is_started():
+            self._tracker.retire(is_error)
+        else:
+            q.append(pack)
 
     def _retire(self, is_error: bool = False):
-        with self._pending_cv:
-            self._pending -= 1
-            if is_error:
-                self._pending_err -= 1
-            if self._draining:  # nobody waits on the hot path: skip the notify
-                self._pending_cv.notify_all()
+        self._tracker.retire(is_error)
 
     def pending_sends(self) -> int:
-        return self._pending
+        return self._tracker.pending()
 
     def get_last_sending_error(self):
         return self._last_sending_error

@@ -274,12 +274,25 @@ class Executor : public std::enable_shared_from_this<Executor> {
   }
 
   static void worker_loop(LanePtr& lane, std::shared_ptr<ExecStats>& stats, py::object& wrap) {
+    AdaptiveSpin idle;  // a lane that is called every few hundred us stays awake between calls
     for (;;) {
       TaskPtr t;
-      spin_until([&] { return lane->qsize.load(std::memory_order_acquire) > 0 || lane->wake.load(std::memory_order_relaxed); });
+      auto idle_t0 = std::chrono::steady_clock::now();
+      {
+        auto pred = [&] { return lane->qsize.load(std::memory_order_acquire) > 0 || lane->wake.load(std::memory_order_relaxed); };
+        const int base = spin_budget_us(), budget = idle.budget_us();
+        if (budget > base) {
+          LongSpinSlot slot;
+          slot.ok ? spin_long(pred, budget) : spin_for(pred, base);
+        } else {
+          spin_for(pred, budget);
+        }
+      }
       {
         std::unique_lock<std::mutex> lk(lane->mu);
         lane->cv.wait(lk, [&] { return lane->stopping || lane->killed || !lane->q.empty(); });
+        // the whole idle period (spin + park) drives the next spin budget
+        idle.observe(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - idle_t0).count());
         if (lane->killed) return;
         if (lane->q.empty()) {
           if (lane->stopping) return;

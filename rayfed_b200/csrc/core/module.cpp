@@ -11,6 +11,7 @@
 #include "executor.h"
 #include "mailbox.h"
 #include "ref.h"
+#include "send_tracker.h"
 #include "transport.h"
 
 namespace py = pybind11;
@@ -157,7 +158,29 @@ PYBIND11_MODULE(_fedcore, m) {
            })
       .def("set_decoder", &Ref::set_decoder)
       .def("set_decoded_exc_is_error", &Ref::set_decoded_exc_is_error)
+      .def("set_ack_mode", &Ref::set_ack_mode, py::arg("on") = true)
+      .def("forward_to", &Ref::forward_to, py::arg("dst"),
+           "complete `dst` with this Ref's outcome (native continuation; raw outcomes never take the GIL)")
       .def("add_done_callback", &Ref::add_done_callback);
+
+  py::class_<SendTracker, std::shared_ptr<SendTracker>>(m, "SendTracker")
+      .def(py::init<py::object>(), py::arg("handler"))
+      .def("watch", &SendTracker::watch, py::arg("ref"), py::arg("pack"), py::arg("is_error") = false)
+      .def("retire", &SendTracker::retire, py::arg("is_error") = false)
+      .def("pending", &SendTracker::pending)
+      .def("pending_errors", &SendTracker::pending_errors)
+      .def("fast_retired", &SendTracker::fast_retired)
+      .def("slow_settled", &SendTracker::slow_settled)
+      .def("set_draining", &SendTracker::set_draining)
+      .def("settling", &SendTracker::settling)
+      .def("bury", &SendTracker::bury)
+      .def(
+          "wait_idle",
+          [](SendTracker& t, double timeout, bool errors_only) {
+            py::gil_scoped_release rel;
+            return t.wait_idle(timeout, errors_only);
+          },
+          py::arg("timeout") = -1.0, py::arg("errors_only") = false);
 
   py::class_<DeviceValue>(m, "DeviceValue",
                           "value + the CUDA event (and stream) that orders it; a Ref completed with one "
@@ -203,6 +226,17 @@ PYBIND11_MODULE(_fedcore, m) {
     return out;
   }, py::arg("clear") = false);
 
+  m.def("spin_info", [] {
+    py::dict d;
+    d["usable_cpus"] = usable_cpus();
+    d["base_spin_us"] = spin_budget_us();
+    d["adaptive_cap_us"] = adaptive_spin_cap_us();
+    d["max_long_spinners"] = max_long_spinners();
+    d["long_spinners_now"] = g_long_spinners.load();
+    d["preemptions_seen"] = g_long_spin_preemptions.load();
+    d["pause_ms"] = g_long_spin_pause_ms.load();
+    return d;
+  }, "adaptive-spin configuration and counters of this process");
   m.def("wait_refs", &wait_refs, py::arg("refs"), py::arg("num_ready") = 1, py::arg("timeout") = -1.0);
 
   py::class_<SeqCounter>(m, "SeqCounter")
@@ -293,7 +327,11 @@ PYBIND11_MODULE(_fedcore, m) {
           [](SocketTransport& t, const std::string& dest, const std::string& up, const std::string& down,
              py::bytes data, bool is_error, py::object decoder) {
             auto ack = std::make_shared<Ref>();
-            if (!decoder.is_none()) ack->set_decoder(decoder);
+            if (!decoder.is_none()) {
+              ack->set_decoder(decoder);
+            } else {
+              ack->set_ack_mode(true);  // True / RuntimeError(text), decoded without a Python object
+            }
             std::string payload(data);
             bool ok;
             {
@@ -305,6 +343,34 @@ PYBIND11_MODULE(_fedcore, m) {
           },
           py::arg("dest"), py::arg("up"), py::arg("down"), py::arg("data"), py::arg("is_error") = false,
           py::arg("decoder") = py::none())
+      .def(
+          "send_many",
+          // one payload to several parties (fed.get's broadcast): the GIL is dropped ONCE around all
+          // the writes, so the driver thread can go on while the frames leave
+          [](SocketTransport& t, const std::vector<std::string>& dests, const std::string& up,
+             const std::string& down, py::bytes data, bool is_error) {
+            std::vector<RefPtr> acks;
+            acks.reserve(dests.size());
+            for (size_t i = 0; i < dests.size(); ++i) {
+              acks.push_back(std::make_shared<Ref>());
+              acks.back()->set_ack_mode(true);
+            }
+            std::string payload(data);
+            std::string missing;
+            {
+              py::gil_scoped_release rel;
+              for (size_t i = 0; i < dests.size(); ++i) {
+                std::string copy = i + 1 == dests.size() ? std::move(payload) : payload;
+                if (!t.send(dests[i], up, down, std::move(copy), is_error, acks[i])) {
+                  if (missing.empty()) missing = dests[i];
+                  acks[i]->set_raw("unknown destination party '" + dests[i] + "'", true);
+                }
+              }
+            }
+            if (!missing.empty()) throw py::key_error("unknown destination party '" + missing + "'");
+            return acks;
+          },
+          py::arg("dests"), py::arg("up"), py::arg("down"), py::arg("data"), py::arg("is_error") = false)
       .def("set_max_message_bytes", &SocketTransport::set_max_message_bytes)
       .def("max_message_bytes", &SocketTransport::max_message_bytes)
       .def(

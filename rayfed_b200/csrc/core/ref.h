@@ -13,10 +13,13 @@
 #pragma once
 #include <pybind11/pybind11.h>
 
+#include <sched.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <functional>
 #include <thread>
@@ -114,19 +117,156 @@ inline bool spin_until(Pred&& pred) {
   }
 }
 
-// Adaptive spinning for waits on a Ref (the driver in fed.get, an actor lane parked on its
-// inputs): when this thread's recent waits were short, spin about that long before falling back
-// to the futex — the kernel wake-up it avoids costs more than the wait itself in tiny-task
-// loops.  Long waits (GPU work, slow peers) push the average up and the spin falls back to the
-// base budget, so nothing burns a core while real work is pending.  OFF by default
-// (RAYFED_B200_ADAPTIVE_SPIN_US = cap in microseconds, 0 = off): to be tuned on the target host.
-inline int adaptive_spin_cap_us() {
+// Adaptive spinning.  A futex / poll wake-up costs 10-50 us — more than a tiny fed task — and
+// the thread that has to ring the sleeper pays a system call on top.  So a waiter whose recent
+// waits were SHORT keeps spinning for about that long before it parks: the driver in fed.get, an
+// actor lane between two calls, a shared-memory ring reader between two frames.  Long waits (GPU
+// work, slow peers, a training step between messages) push the average above the cap and the
+// waiter falls back to the base budget, so nothing burns a core unless messages really arrive
+// every few hundred microseconds.  The number of threads that may spin long at once is bounded
+// per process.  RAYFED_B200_ADAPTIVE_SPIN_US = cap in microseconds (default 500, 0 = off);
+// RAYFED_B200_MAX_SPINNERS = concurrent long spinners per process (default: hardware threads / 4,
+// clamped to [2, 16]).
+// CPUs this process may really use: the affinity mask, cut down by a cgroup CPU quota if any.
+inline int usable_cpus() {
   static int v = [] {
-    const char* e = std::getenv("RAYFED_B200_ADAPTIVE_SPIN_US");
-    return e ? std::atoi(e) : 0;
+    int n = (int)std::thread::hardware_concurrency();
+#if defined(__linux__)
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+      int c = CPU_COUNT(&set);
+      if (c > 0) n = c;
+    }
+    // cgroup v2: "max 100000" or "<quota> <period>"; cgroup v1: cfs_quota_us / cfs_period_us
+    auto quota_cpus = [](const char* path_q, const char* path_p) -> double {
+      FILE* f = std::fopen(path_q, "r");
+      if (!f) return -1.0;
+      char a[64] = {0}, b[64] = {0};
+      int got = std::fscanf(f, "%63s %63s", a, b);
+      std::fclose(f);
+      if (got < 1 || a[0] == 'm') return -1.0;  // "max"
+      double q = std::atof(a), p = 0;
+      if (path_p) {
+        FILE* g = std::fopen(path_p, "r");
+        if (!g) return -1.0;
+        if (std::fscanf(g, "%63s", b) != 1) b[0] = 0;
+        std::fclose(g);
+      }
+      p = std::atof(b);
+      return (q > 0 && p > 0) ? q / p : -1.0;
+    };
+    double q = quota_cpus("/sys/fs/cgroup/cpu.max", nullptr);
+    if (q < 0) q = quota_cpus("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "/sys/fs/cgroup/cpu/cpu.cfs_period_us");
+    if (q > 0 && q < n) n = std::max(1, (int)q);
+#endif
+    return std::max(1, n);
   }();
   return v;
 }
+
+// Default: on (cap 500 us) where cores are plentiful — a B200 host has 100+ hardware threads
+// for 8 parties — and off on small machines, where a spinning thread takes the core (or the
+// hyper-thread sibling) another party needs (measured: 8 vCPUs, 4 parties: 520 -> 770 us/iter).
+inline int adaptive_spin_cap_us() {
+  static int v = [] {
+    const char* e = std::getenv("RAYFED_B200_ADAPTIVE_SPIN_US");
+    if (e) return std::max(0, std::atoi(e));
+    return usable_cpus() >= 32 ? 500 : 0;
+  }();
+  return v;
+}
+
+inline int max_long_spinners() {
+  static int v = [] {
+    const char* e = std::getenv("RAYFED_B200_MAX_SPINNERS");
+    if (e) return std::max(0, std::atoi(e));
+    return std::min(8, std::max(2, usable_cpus() / 16));
+  }();
+  return v;
+}
+
+inline std::atomic<int> g_long_spinners{0};
+
+// Self-limiting: a long spin only pays when there is a core to burn.  A spinner that notices a
+// hole in its own time line (it was descheduled: more runnable threads than cores, or a cgroup
+// CPU quota throttling the process) switches long spins off for the whole process for a while;
+// repeated offences double the pause (2 ms .. 256 ms), clean spins shrink it again.
+inline std::atomic<int64_t> g_long_spin_off_until_ns{0};
+inline std::atomic<int> g_long_spin_pause_ms{2};
+inline std::atomic<long> g_long_spin_preemptions{0};
+
+inline int64_t mono_ns() {
+  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch())
+      .count();
+}
+
+inline std::atomic<int64_t> g_long_spin_last_hole_ns{0};
+
+inline void long_spin_preempted() {
+  const int64_t now = mono_ns();
+  const int64_t prev = g_long_spin_last_hole_ns.exchange(now, std::memory_order_relaxed);
+  int pause = g_long_spin_pause_ms.load(std::memory_order_relaxed);
+  // an isolated hole (hypervisor steal, a stray interrupt storm) costs a short pause; holes in
+  // quick succession mean the cores are oversubscribed: escalate
+  pause = (now - prev < (int64_t)20 * pause * 1000000) ? std::min(256, pause * 2) : 2;
+  g_long_spin_pause_ms.store(pause, std::memory_order_relaxed);
+  g_long_spin_off_until_ns.store(now + (int64_t)pause * 1000000, std::memory_order_relaxed);
+  g_long_spin_preemptions.fetch_add(1, std::memory_order_relaxed);
+}
+
+inline void long_spin_clean() {}
+
+// RAII claim on one of the process's long-spin slots.
+struct LongSpinSlot {
+  bool ok;
+  LongSpinSlot() {
+    ok = g_long_spinners.fetch_add(1, std::memory_order_acq_rel) < max_long_spinners() &&
+         mono_ns() >= g_long_spin_off_until_ns.load(std::memory_order_relaxed);
+    if (!ok) g_long_spinners.fetch_sub(1, std::memory_order_acq_rel);
+  }
+  ~LongSpinSlot() {
+    if (ok) g_long_spinners.fetch_sub(1, std::memory_order_acq_rel);
+  }
+  LongSpinSlot(const LongSpinSlot&) = delete;
+  LongSpinSlot& operator=(const LongSpinSlot&) = delete;
+};
+
+// Spin on `pred` for up to `budget_us`, giving up (and pausing long spins process-wide) when this
+// thread was descheduled in between.  Returns pred's last value.
+template <typename Pred>
+inline bool spin_long(Pred&& pred, int budget_us) {
+  constexpr int64_t kHoleNs = 200 * 1000;  // above any interrupt, below any scheduler time slice
+  const int64_t t0 = mono_ns();
+  int64_t last = t0;
+  for (;;) {
+    if (pred()) {
+      long_spin_clean();
+      return true;
+    }
+    for (int i = 0; i < 32; ++i) cpu_relax();
+    int64_t now = mono_ns();
+    if (now - last > kHoleNs) {
+      long_spin_preempted();
+      return pred();
+    }
+    last = now;
+    if (now - t0 > (int64_t)budget_us * 1000) return pred();
+  }
+}
+
+// Per-waiter state (one thread at a time): exponential average of recent wait durations.
+struct AdaptiveSpin {
+  double ema_us = 1e12;
+  // How long to spin before parking, given the history.
+  int budget_us() const {
+    const int base = spin_budget_us();
+    const int cap = adaptive_spin_cap_us();
+    if (cap <= 0 || base <= 0 || ema_us >= (double)cap) return base;
+    return std::max(base, std::min(cap, (int)(2.0 * ema_us) + 1));
+  }
+  void observe(double waited_us) { ema_us = ema_us > 1e11 ? waited_us : 0.75 * ema_us + 0.25 * waited_us; }
+};
 
 template <typename Pred>
 inline bool spin_for(Pred&& pred, int budget_us) {
@@ -137,6 +277,24 @@ inline bool spin_for(Pred&& pred, int budget_us) {
     for (int i = 0; i < 32; ++i) cpu_relax();
     if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(budget_us)) return pred();
   }
+}
+
+// spin (adaptively) on `pred`, then `park()` — which must return pred's final value.
+template <typename Pred, typename Park>
+inline bool adaptive_wait(AdaptiveSpin& hist, Pred&& pred, Park&& park) {
+  const int base = spin_budget_us();
+  int budget = hist.budget_us();
+  auto t0 = std::chrono::steady_clock::now();
+  bool ok;
+  if (budget > base) {
+    LongSpinSlot slot;
+    ok = slot.ok ? spin_long(pred, budget) : spin_for(pred, base);
+  } else {
+    ok = spin_for(pred, budget);
+  }
+  if (!ok) ok = park();
+  hist.observe(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+  return ok;
 }
 
 inline bool interpreter_alive() {
@@ -222,21 +380,9 @@ class Ref : public std::enable_shared_from_this<Ref> {
   // hold the GIL (bindings release it).
   bool wait(double timeout_s) {
     if (done()) return true;
-    const int cap = adaptive_spin_cap_us();
-    if (cap <= 0) {
-      if (timeout_s != 0 && spin_until([&] { return done(); })) return true;
-      return block(timeout_s);
-    }
-    // adaptive: spin ~2x this thread's recent wait time, bounded by [base budget, cap]
-    static thread_local double ema_us = 1e12;
-    auto t0 = std::chrono::steady_clock::now();
-    int budget = spin_budget_us();
-    if (ema_us < (double)cap) budget = std::max(budget, std::min(cap, (int)(2.0 * ema_us) + 1));
-    bool ok = timeout_s != 0 && spin_for([&] { return done(); }, budget);
-    if (!ok) ok = block(timeout_s);
-    double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
-    ema_us = ema_us > 1e11 ? us : 0.75 * ema_us + 0.25 * us;
-    return ok;
+    if (timeout_s == 0) return false;
+    static thread_local AdaptiveSpin hist;
+    return adaptive_wait(hist, [&] { return done(); }, [&] { return block(timeout_s); });
   }
 
   bool block(double timeout_s) {
@@ -288,7 +434,17 @@ class Ref : public std::enable_shared_from_this<Ref> {
     py::object out;
     bool err = raw_is_error_;
     try {
-      out = decoder_ ? decoder_(b, err) : py::object(b);
+      if (!decoder_ && ack_mode_) {
+        // transport acknowledgement, decoded natively: True, or the failure text as an error
+        if (err) {
+          out = py::reinterpret_steal<py::object>(PyObject_CallOneArg(PyExc_RuntimeError, py::str(raw_).ptr()));
+          if (!out) throw py::error_already_set();
+        } else {
+          out = py::bool_(true);
+        }
+      } else {
+        out = decoder_ ? decoder_(b, err) : py::object(b);
+      }
     } catch (py::error_already_set& e) {
       // decoding failed (e.g. whitelist violation): surface as the error value
       out = py::reinterpret_borrow<py::object>(e.value());
@@ -327,6 +483,28 @@ class Ref : public std::enable_shared_from_this<Ref> {
   }
 
   void set_decoded_exc_is_error(bool v) { decoded_exc_is_error_ = v; }
+
+  // Acknowledgement futures of the native transport: the raw frame decodes to True (or to a
+  // RuntimeError carrying the failure text) without a Python decoder object — so such a Ref can
+  // be completed, forwarded, watched and destroyed on transport threads without the GIL.
+  void set_ack_mode(bool v) { ack_mode_ = v; }
+  bool ack_mode() const { return ack_mode_; }
+  // No GIL needed. True: resolved to an un-decoded, non-error acknowledgement frame.
+  bool raw_ack_ok() const {
+    return ack_mode_ && state_.load(std::memory_order_acquire) == (int)RefState::kRaw && !raw_is_error_;
+  }
+
+  // Complete `dst` with this Ref's outcome as soon as there is one.  A native continuation: a raw
+  // outcome (bytes from a transport thread) is handed over without touching the interpreter; only
+  // Python-object outcomes take the GIL.  Call with the GIL held (the decoder is shared here).
+  void forward_to(std::shared_ptr<Ref> dst) {
+    if (!dst || dst.get() == this) return;
+    if (decoder_) dst->decoder_ = decoder_;
+    dst->ack_mode_ = ack_mode_;
+    dst->decoded_exc_is_error_ = decoded_exc_is_error_;
+    auto self = shared_from_this();
+    on_done([self, dst] { self->copy_outcome_to(*dst); });
+  }
 
   // ---- device ordering -------------------------------------------------------
   // Attach BEFORE completing the Ref (the executor does) or from the decoder.
@@ -371,6 +549,36 @@ class Ref : public std::enable_shared_from_this<Ref> {
     return true;
   }
 
+  // Any thread, GIL held or not.
+  void copy_outcome_to(Ref& dst) {
+    {
+      // vs. a concurrent materialize(): it holds decode_mu_ while running Python, so never
+      // block on it with the GIL held
+      std::unique_lock<std::mutex> lk(decode_mu_, std::defer_lock);
+      if (Py_IsInitialized() && PyGILState_Check()) {
+        py::gil_scoped_release rel;
+        lk.lock();
+      } else {
+        lk.lock();
+      }
+      if (state_.load(std::memory_order_acquire) == (int)RefState::kRaw) {
+        std::string raw = raw_;
+        bool e = raw_is_error_;
+        lk.unlock();
+        dst.set_raw(std::move(raw), e);
+        return;
+      }
+    }
+    if (!interpreter_alive()) return;
+    py::gil_scoped_acquire gil;
+    if (DeviceEventPtr ev = device_event()) dst.set_device_event(ev);
+    if (state_.load(std::memory_order_acquire) == (int)RefState::kError) {
+      dst.set_error(value_);
+    } else {
+      dst.complete(RefState::kValue, value_, std::string(), false);
+    }
+  }
+
   // GIL held. `v` may be a DeviceValue: keep the plain value, adopt the event.
   void adopt_device_value(py::object& v) {
     if (!v || !py::isinstance<DeviceValue>(v)) return;
@@ -396,6 +604,7 @@ class Ref : public std::enable_shared_from_this<Ref> {
   std::string raw_;
   bool raw_is_error_ = false;
   bool decoded_exc_is_error_ = false;
+  bool ack_mode_ = false;
   std::vector<std::function<void()>> callbacks_;
   std::vector<py::object> py_callbacks_;
 };

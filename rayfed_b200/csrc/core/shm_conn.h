@@ -235,6 +235,19 @@ class Conn {
 
   // 1: data available, 0: timeout, -1: connection closed / error.  timeout_ms < 0: no limit.
   int wait_readable(int timeout_ms) {
+    if (!rx_) return wait_readable_impl(timeout_ms);
+    auto t0 = std::chrono::steady_clock::now();
+    int r = wait_readable_impl(timeout_ms);
+    if (r == 1)  // how long this side sat idle before the frame came: drives the adaptive spin
+      idle_.observe(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+    return r;
+  }
+
+  // Receivers nobody waits for (acknowledgement readers) never spin longer than the base budget.
+  void set_latency_critical(bool v) { latency_critical_ = v; }
+
+ private:
+  int wait_readable_impl(int timeout_ms) {
     if (!rx_) {
       for (;;) {
         pollfd p{fd_, POLLIN, 0};
@@ -250,16 +263,16 @@ class Conn {
     for (;;) {
       if (ready()) return 1;
       if (dead()) return -1;
-      // bounded user-space spin (same budget as every other wait of the runtime)
-      const int budget = spin_budget_us();
-      if (budget > 0) {
-        auto t0 = std::chrono::steady_clock::now();
-        while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(budget)) {
-          for (int i = 0; i < 64; ++i) {
-            if (ready()) return 1;
-            cpu_relax();
-          }
-        }
+      // bounded user-space spin (same budget as every other wait of the runtime); a receive
+      // side whose frames arrive every few hundred us keeps spinning between them (adaptive):
+      // the producer then never pays the doorbell system call and the frame is seen at once
+      const int base = spin_budget_us();
+      int budget = latency_critical_ ? idle_.budget_us() : base;
+      if (budget > base) {
+        LongSpinSlot slot;
+        if (slot.ok ? spin_long(ready, budget) : spin_for(ready, base)) return 1;
+      } else if (spin_for(ready, budget)) {
+        return 1;
       }
       // announce the sleep, re-check (Dekker), then block on the socket: the producer rings
       // the doorbell (one byte) when it sees the announcement; EOF means the peer went away
@@ -325,6 +338,8 @@ class Conn {
   }
 
   int fd_;
+  AdaptiveSpin idle_;              // reader thread only
+  bool latency_critical_ = true;  // reader thread only
   std::atomic<bool> dead_{false};
   void* map_ = nullptr;
   size_t map_len_ = 0;

@@ -400,6 +400,7 @@ class Peer {
 
   void reader_loop(std::shared_ptr<Conn> c) {
     const int fd = c->fd();
+    c->set_latency_critical(false);  // nobody waits for an acknowledgement on the hot path
     for (;;) {
       int pr = c->wait_readable(100);
       if (pr < 0) break;

@@ -489,7 +489,7 @@ def send(dest_party, data, upstream_seq_id, downstream_seq_id, is_error=False, c
                 except BaseException as ex:  # noqa: BLE001
                     result.set_error(ex)
                     return
-                inner.add_done_callback(lambda a: _copy_outcome(a, result))
+                inner.forward_to(result)  # native continuation: an ack never takes the GIL
 
             data.add_done_callback(on_ready)
     else:
@@ -537,7 +537,7 @@ def send_broadcast(dest_parties, data, upstream_seq_id, downstream_seq_id):
                 r.set_error(e)
             return
         for d, ack in acks.items():
-            ack.add_done_callback(lambda a, r=results[d]: _copy_outcome(a, r))
+            ack.forward_to(results[d])
 
     if is_ref(data):
         if data.done():

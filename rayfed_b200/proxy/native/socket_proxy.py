@@ -43,6 +43,7 @@ def _retry_from_config(cfg: CrossSiloMessageConfig) -> dict:
 
 
 def _ack_decoder(data: bytes, is_error: bool):
+    """Python flavour of the ack decoding (the transport's default is the native one)."""
     if is_error:
         raise RuntimeError(data.decode("utf-8", "replace"))
     return True
@@ -93,9 +94,10 @@ class NativeSenderProxy(SenderProxy):
             raise RuntimeError(
                 f"message of {len(payload)} bytes exceeds messages_max_size_in_bytes={self._max_bytes}"
             )
+        # the ack future decodes natively (True / RuntimeError(text)): no Python decoder object, so
+        # transport threads complete, forward and drop it without the GIL
         return self._transport.send(
-            dest_party, str(upstream_seq_id), str(downstream_seq_id), payload, isinstance(data, FedRemoteError),
-            _ack_decoder,
+            dest_party, str(upstream_seq_id), str(downstream_seq_id), payload, isinstance(data, FedRemoteError)
         )
 
     # -- owner -> all-parties broadcast (fed.get): serialise ONCE, N-1 native sends ------------
@@ -110,9 +112,10 @@ class NativeSenderProxy(SenderProxy):
             raise RuntimeError(
                 f"message of {len(payload)} bytes exceeds messages_max_size_in_bytes={self._max_bytes}"
             )
-        up, down, is_err = str(upstream_seq_id), str(downstream_seq_id), isinstance(data, FedRemoteError)
-        send = self._transport.send
-        return {d: send(d, up, down, payload, is_err, _ack_decoder) for d in dest_parties}
+        dest_parties = list(dest_parties)
+        acks = self._transport.send_many(dest_parties, str(upstream_seq_id), str(downstream_seq_id), payload,
+                                         isinstance(data, FedRemoteError))
+        return dict(zip(dest_parties, acks))
 
     def drain(self, timeout: float = 60.0) -> bool:
         return self._transport.drain(timeout)

@@ -333,7 +333,7 @@ class DeviceChannel:
         self.stats = {"tensors_sent": 0, "bytes_sent": 0, "messages_sent": 0, "tensors_received": 0,
                       "bytes_received": 0, "messages_received": 0, "zero_copy_tensors": 0, "copied_tensors": 0,
                       "credit_stalls": 0, "bcast_tensors_sent": 0, "bcast_bytes_sent": 0, "blocks_released": 0,
-                      "forced_releases": 0}
+                      "forced_releases": 0, "wait_mode": "host" if self._host_gate else "stream"}
 
     # -- addresses ---------------------------------------------------------------
     def _peer(self, party_rank: int, off: int) -> int:

@@ -34,7 +34,7 @@ from ..._private.serialization import Deserializer, _RestrictedUnpickler
 from ...config import CrossSiloMessageConfig
 from ...core.runtime import DeviceValue, is_device_value
 from ...exceptions import FedRemoteError, FedTaskError
-from ..native.socket_proxy import NativeReceiverProxy, NativeSenderProxy, _ack_decoder
+from ..native.socket_proxy import NativeReceiverProxy, NativeSenderProxy
 
 logger = logging.getLogger(__name__)
 
@@ -153,7 +153,7 @@ class NvlinkSenderProxy(NativeSenderProxy):
     def _meta_frame(self, dest, meta, last, n_tensors):
         k = self._next_k(dest)
         meta = dict(meta, last=bool(last), n=n_tensors)
-        self._transport.send(dest, f"{_DEVQ}/{self._party}", str(k), json.dumps(meta).encode(), False, _ack_decoder)
+        self._transport.send(dest, f"{_DEVQ}/{self._party}", str(k), json.dumps(meta).encode(), False)
         return k
 
     def send(self, dest_party, data, upstream_seq_id, downstream_seq_id):
@@ -168,7 +168,7 @@ class NvlinkSenderProxy(NativeSenderProxy):
         up, down = str(upstream_seq_id), str(downstream_seq_id)
         if not tensors:
             frame = pickle.dumps((_TAG, 0, skeleton), protocol=5) if small else skeleton
-            return self._transport.send(dest_party, up, down, frame, False, _ack_decoder)
+            return self._transport.send(dest_party, up, down, frame, False)
         dest_rank = channel.group.parties.index(dest_party)
         with self._order_lock:
             # one metadata frame per arena block, sent the moment its push kernel is *launched*
@@ -177,13 +177,13 @@ class NvlinkSenderProxy(NativeSenderProxy):
                 meta = channel.push_message(dest_rank, messages[0], (up, down), event, pstream)
                 meta.update(last=True, n=len(tensors))
                 frame = pickle.dumps((_TAG1, json.dumps(meta).encode(), skeleton), protocol=5)
-                return self._transport.send(dest_party, up, down, frame, False, _ack_decoder)
+                return self._transport.send(dest_party, up, down, frame, False)
             k = 0
             for i, parts in enumerate(messages):
                 meta = channel.push_message(dest_rank, parts, (up, down), event, pstream)
                 k = self._meta_frame(dest_party, meta, i == len(messages) - 1, len(tensors))
         frame = pickle.dumps((_TAG, k, skeleton), protocol=5)
-        return self._transport.send(dest_party, up, down, frame, False, _ack_decoder)
+        return self._transport.send(dest_party, up, down, frame, False)
 
     # -- K1b: owner -> all-parties broadcast (fed.get, weight redistribution) -------------------
     def can_broadcast(self) -> bool:
@@ -203,9 +203,13 @@ class NvlinkSenderProxy(NativeSenderProxy):
         skeleton, tensors, small = self._serialise(data, owner)
         up, down = str(upstream_seq_id), str(downstream_seq_id)
         send = self._transport.send
+        dest_parties = list(dest_parties)
+
+        def send_all(frame):  # one GIL release around the N-1 writes
+            return dict(zip(dest_parties, self._transport.send_many(dest_parties, up, down, frame, False)))
+
         if not tensors:
-            frame = pickle.dumps((_TAG, 0, skeleton), protocol=5) if small else skeleton
-            return {d: send(d, up, down, frame, False, _ack_decoder) for d in dest_parties}
+            return send_all(pickle.dumps((_TAG, 0, skeleton), protocol=5) if small else skeleton)
         if not (_MC_PUSH_ENABLED and channel.can_bcast(tensors)):
             return {d: self.send(d, orig, upstream_seq_id, downstream_seq_id) for d in dest_parties}
         ks = {}
@@ -214,13 +218,12 @@ class NvlinkSenderProxy(NativeSenderProxy):
             if len(messages) == 1 and sum(p["pay"] + p["scales"] for p in messages[0]) <= _INLINE_MAX_BYTES:
                 meta = channel.push_message(None, messages[0], (up, down), event, pstream)
                 meta.update(last=True, n=len(tensors))
-                frame = pickle.dumps((_TAG1, json.dumps(meta).encode(), skeleton), protocol=5)
-                return {d: send(d, up, down, frame, False, _ack_decoder) for d in dest_parties}
+                return send_all(pickle.dumps((_TAG1, json.dumps(meta).encode(), skeleton), protocol=5))
             for i, parts in enumerate(messages):
                 meta = channel.push_message(None, parts, (up, down), event, pstream)
                 for d in dest_parties:
                     ks[d] = self._meta_frame(d, meta, i == len(messages) - 1, len(tensors))
-        return {d: send(d, up, down, pickle.dumps((_TAG, ks[d], skeleton), protocol=5), False, _ack_decoder)
+        return {d: send(d, up, down, pickle.dumps((_TAG, ks[d], skeleton), protocol=5), False)
                 for d in dest_parties}
 
 

@@ -146,7 +146,7 @@ def test_sender_reconnects_after_the_receiver_restarts():
     assert not rx1.listen(addr)
     tx = nat.SocketTransport("alice", "job", nat.Mailbox())
     tx.add_peer("bob", addr, 40, 0.05, 0.2, 1.5, 5.0)
-    assert tx.send("bob", "1", "a", b"x", False, None).result(5.0) == b"OK"
+    assert tx.send("bob", "1", "a", b"x", False, None).result(5.0) is True
     rx1.stop()
     time.sleep(0.2)
     mb2 = nat.Mailbox()
@@ -190,7 +190,7 @@ def test_shared_memory_data_path_is_negotiated_and_streams_large_messages(monkey
     smalls = [os.urandom(1 + (i * 37) % 900) for i in range(3000)]
     acks += [tx.send("bob", f"s{i}", "2", b, False, None) for i, b in enumerate(smalls)]
     for a in acks:
-        assert a.result(20.0) == b"OK"
+        assert a.result(20.0) is True
     got = mb.claim("big", "1").result(5.0)
     assert hashlib.sha256(got).digest() == hashlib.sha256(big).digest()
     for i in (0, 1, 1499, 2999):
@@ -223,7 +223,7 @@ def test_shared_memory_offer_is_refused_politely_when_the_server_has_it_off(monk
     ack = tx.send("bob", "a", "b", b"payload", False, None)
     # ... the serve thread reads the env when the offer arrives; make it see "off"
     monkeypatch.delenv("RAYFED_B200_SHM", raising=False)
-    assert ack.result(10.0) == b"OK" and mb.claim("a", "b").result(5.0) == b"payload"
+    assert ack.result(10.0) is True and mb.claim("a", "b").result(5.0) == b"payload"
     assert rx.stats()["shm_conns"] in (0, 1)  # env is process-wide: the race decides, both must work
     tx.stop()
     rx.stop()
