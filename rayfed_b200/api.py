@@ -139,6 +139,7 @@ def init(
     if tls_config:
         assert "cert" in tls_config and "key" in tls_config, "Cert or key are not in tls_config."
 
+    _configure_spinning(addresses, party)
     fed_kv._init_internal_kv(job_name)
     cluster_config = {
         constants.KEY_OF_CLUSTER_ADDRESSES: addresses,
@@ -214,6 +215,32 @@ def init(
 
     if config.get("barrier_on_initializing", False):
         ping_others(addresses=addresses, self_party=party, max_retries=3600)
+
+
+def _local_party_count(addresses: Dict, party: str) -> int:
+    """Parties of this job whose address is on this party's host (they share its CPUs)."""
+    def host_of(addr: str) -> str:
+        addr = str(addr)
+        if addr.startswith("unix:") or "/" in addr:
+            return "localhost"
+        host = addr.rsplit(":", 1)[0].strip("[]").lower()
+        return "localhost" if host in ("127.0.0.1", "::1", "localhost", "0.0.0.0", "") else host
+
+    mine = host_of(addresses.get(party, ""))
+    return max(1, sum(1 for a in addresses.values() if host_of(a) == mine))
+
+
+def _configure_spinning(addresses: Dict, party: str) -> None:
+    """Adaptive spinning (csrc/core/ref.h) needs CPUs to burn: give every party on this host an
+    equal share of half the usable CPUs, and leave it off below two spinners per party.
+    `RAYFED_B200_ADAPTIVE_SPIN_US` / `RAYFED_B200_MAX_SPINNERS` override."""
+    try:
+        from .core import native
+
+        native().set_spin_policy_auto(_local_party_count(addresses, party))
+        logger.debug(f"spin policy: {native().spin_info()}")
+    except Exception:  # noqa: BLE001  (a tuning knob must never fail init)
+        logger.debug("could not configure adaptive spinning", exc_info=True)
 
 
 def _host_identity() -> str:
@@ -381,6 +408,12 @@ def _shutdown(intended=True):
     if coll is not None:
         coll.reset(job_name_at_exit)
     _teardown_runtime(wait_for_sending)
+    try:
+        from .core import native
+
+        native().set_spin_policy(-1, -1)  # back to "not configured" (off)
+    except Exception:  # noqa: BLE001
+        pass
     trace_file = _tracing.disable(dump=True)
     if trace_file:
         logger.info(f"Wrote the fed timeline to {trace_file}.")

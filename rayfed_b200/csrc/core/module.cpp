@@ -226,6 +226,12 @@ PYBIND11_MODULE(_fedcore, m) {
     return out;
   }, py::arg("clear") = false);
 
+  m.def("set_spin_policy", [](int cap_us, int max_spinners) {
+    g_adaptive_cap_us.store(cap_us, std::memory_order_relaxed);
+    g_max_long_spinners.store(max_spinners, std::memory_order_relaxed);
+  }, py::arg("cap_us"), py::arg("max_spinners"), "explicit adaptive-spin policy (environment variables still win)");
+  m.def("set_spin_policy_auto", &set_spin_policy_auto, py::arg("local_parties") = 1,
+        "derive the adaptive-spin policy from the usable CPUs and the number of parties on this host");
   m.def("spin_info", [] {
     py::dict d;
     d["usable_cpus"] = usable_cpus();

@@ -165,25 +165,46 @@ inline int usable_cpus() {
   return v;
 }
 
-// Default: on (cap 500 us) where cores are plentiful — a B200 host has 100+ hardware threads
-// for 8 parties — and off on small machines, where a spinning thread takes the core (or the
-// hyper-thread sibling) another party needs (measured: 8 vCPUs, 4 parties: 520 -> 770 us/iter).
+// Policy.  Environment variables win; otherwise long spins are OFF until somebody who knows the
+// deployment switches them on: `fed.init` does (set_spin_policy), from the CPUs this process may
+// use and the number of parties that share the host.  Measured on the B200 host (128 hardware
+// threads behind a 16-CPU cgroup quota), many_tiny_tasks per iteration, off -> on:
+// 2 parties 164-193 -> 54-80 us, 4 parties 101-122 -> 87-113 us, 8 parties 181-186 -> 222-241 us
+// (16 spinning threads eat the quota) — hence "at least two spinners' worth of CPU per party".
+inline std::atomic<int> g_adaptive_cap_us{-1};   // -1: not configured
+inline std::atomic<int> g_max_long_spinners{-1};
+
 inline int adaptive_spin_cap_us() {
-  static int v = [] {
+  static const int env = [] {
     const char* e = std::getenv("RAYFED_B200_ADAPTIVE_SPIN_US");
-    if (e) return std::max(0, std::atoi(e));
-    return usable_cpus() >= 32 ? 500 : 0;
+    return e ? std::max(0, std::atoi(e)) : -1;
   }();
-  return v;
+  if (env >= 0) return env;
+  int v = g_adaptive_cap_us.load(std::memory_order_relaxed);
+  return v < 0 ? 0 : v;
 }
 
 inline int max_long_spinners() {
-  static int v = [] {
+  static const int env = [] {
     const char* e = std::getenv("RAYFED_B200_MAX_SPINNERS");
-    if (e) return std::max(0, std::atoi(e));
-    return std::min(8, std::max(2, usable_cpus() / 16));
+    return e ? std::max(0, std::atoi(e)) : -1;
   }();
-  return v;
+  if (env >= 0) return env;
+  int v = g_max_long_spinners.load(std::memory_order_relaxed);
+  return v < 0 ? 2 : v;
+}
+
+// `local_parties`: fed parties (processes) that share this host.  Each gets an equal share of
+// half the usable CPUs for long spinners; with less than two per party the feature stays off.
+inline void set_spin_policy_auto(int local_parties) {
+  if (local_parties < 1) local_parties = 1;
+  int per_party = usable_cpus() / (2 * local_parties);
+  if (per_party >= 2) {
+    g_max_long_spinners.store(std::min(8, per_party), std::memory_order_relaxed);
+    g_adaptive_cap_us.store(500, std::memory_order_relaxed);
+  } else {
+    g_adaptive_cap_us.store(0, std::memory_order_relaxed);
+  }
 }
 
 inline std::atomic<int> g_long_spinners{0};

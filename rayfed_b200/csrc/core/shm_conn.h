@@ -5,13 +5,16 @@
 // `RAYFED_B200_SHM=1`, the DATA moves through a pair of single-producer/single-consumer byte
 // rings in a POSIX shared-memory segment instead (this is the "HostRing" of SURVEY §7.1): a
 // frame costs two memcpys and no system call, and a spinning reader sees it without a kernel
-// wake-up.  The socket then only carries (a) the one-frame handshake that hands the segment
-// name to the server, (b) a one-byte doorbell when the consumer announced it was going to
-// sleep in poll(), (c) EOF when a side goes away.  The creator unlinks the segment name as
+// wake-up.  A consumer that goes to sleep announces it in the ring header and blocks on that word
+// (cross-process futex); the producer that sees the announcement wakes it.  The socket then only
+// carries (a) the one-frame handshake that hands the segment name to the server and (b) EOF when
+// a side goes away.  The creator unlinks the segment name as
 // soon as the peer has mapped it, so nothing is left in /dev/shm even after a crash.
 #pragma once
 #include <fcntl.h>
+#include <linux/futex.h>
 #include <poll.h>
+#include <sys/syscall.h>
 #include <sys/mman.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
@@ -33,7 +36,7 @@ static constexpr uint32_t kShmMagic = 0x52424653;  // "SFBR"
 struct ShmRing {  // in shared memory
   alignas(64) std::atomic<uint64_t> head;             // bytes produced
   alignas(64) std::atomic<uint64_t> tail;             // bytes consumed
-  alignas(64) std::atomic<uint32_t> consumer_asleep;  // consumer is (about to be) blocked in poll()
+  alignas(64) std::atomic<uint32_t> consumer_asleep;  // consumer is (about to be) blocked on this word (futex)
 };
 
 struct ShmHeader {
@@ -88,6 +91,19 @@ inline bool fd_read_all(int fd, void* buf, size_t n) {
     n -= (size_t)r;
   }
   return true;
+}
+
+// Cross-process futex on a word in the shared segment (no FUTEX_PRIVATE_FLAG): the doorbell of a
+// ring.  A wake is ~1-2 us; the one-byte TCP/Unix send it replaces cost 7-8 us on the B200 host,
+// paid by the PRODUCER on the critical path of every hop (and 7 times in a row by a fed.get
+// broadcast at 8 parties).
+inline int futex_wait_shared(std::atomic<uint32_t>* addr, uint32_t expected, int timeout_ms) {
+  timespec ts{timeout_ms / 1000, (long)(timeout_ms % 1000) * 1000000L};
+  return (int)::syscall(SYS_futex, reinterpret_cast<uint32_t*>(addr), FUTEX_WAIT, expected,
+                        timeout_ms >= 0 ? &ts : nullptr, nullptr, 0);
+}
+inline void futex_wake_shared(std::atomic<uint32_t>* addr) {
+  ::syscall(SYS_futex, reinterpret_cast<uint32_t*>(addr), FUTEX_WAKE, 1, nullptr, nullptr, 0);
 }
 
 class Conn {
@@ -238,6 +254,7 @@ class Conn {
     if (!rx_) return wait_readable_impl(timeout_ms);
     auto t0 = std::chrono::steady_clock::now();
     int r = wait_readable_impl(timeout_ms);
+    if (r == 1) lazy_polls_ = 0;
     if (r == 1)  // how long this side sat idle before the frame came: drives the adaptive spin
       idle_.observe(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
     return r;
@@ -266,41 +283,63 @@ class Conn {
       // bounded user-space spin (same budget as every other wait of the runtime); a receive
       // side whose frames arrive every few hundred us keeps spinning between them (adaptive):
       // the producer then never pays the doorbell system call and the frame is seen at once
-      const int base = spin_budget_us();
-      int budget = latency_critical_ ? idle_.budget_us() : base;
+      const int base = latency_critical_ ? spin_budget_us() : 0;  // acks: nobody waits, do not spin
+      int budget = latency_critical_ ? idle_.budget_us() : 0;
       if (budget > base) {
         LongSpinSlot slot;
         if (slot.ok ? spin_long(ready, budget) : spin_for(ready, base)) return 1;
       } else if (spin_for(ready, budget)) {
         return 1;
       }
-      // announce the sleep, re-check (Dekker), then block on the socket: the producer rings
-      // the doorbell (one byte) when it sees the announcement; EOF means the peer went away
-      rx_->consumer_asleep.store(1, std::memory_order_seq_cst);
-      if (ready()) {
-        rx_->consumer_asleep.store(0, std::memory_order_seq_cst);
-        return 1;
+      if (!latency_critical_ && lazy_polls_ < kLazyPolls) {
+        // Nobody waits for what this side receives (acknowledgements): do not announce a sleep —
+        // the producer then never pays a wake-up — and look again in a moment.  After a quiet
+        // while fall through to the announced sleep so that an idle connection costs nothing.
+        ++lazy_polls_;
+        std::this_thread::sleep_for(std::chrono::microseconds(kLazyPollUs));
+        if (ready()) {
+          lazy_polls_ = 0;
+          return 1;
+        }
+        if (timeout_ms >= 0) {
+          auto spent = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - start).count();
+          if (spent >= timeout_ms) return 0;
+        }
+        continue;
       }
-      pollfd p{fd_, POLLIN, 0};
+      // announce the sleep, re-check (Dekker), then block on the futex word: the producer clears
+      // it and wakes us when it sees the announcement.  Peer death is noticed on the socket (EOF)
+      // between slices; our own side calls wake_reader() when it closes the connection.
       int slice = 100;
       if (timeout_ms >= 0) {
         auto spent = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - start).count();
-        if (spent >= timeout_ms) {
-          rx_->consumer_asleep.store(0, std::memory_order_seq_cst);
-          return ready() ? 1 : 0;
-        }
+        if (spent >= timeout_ms) return ready() ? 1 : 0;
         slice = (int)std::min<long long>(100, timeout_ms - spent);
       }
-      int pr = ::poll(&p, 1, slice);
-      rx_->consumer_asleep.store(0, std::memory_order_seq_cst);
-      if (pr > 0) {
-        char sink[64];
-        ssize_t r = ::recv(fd_, sink, sizeof(sink), MSG_DONTWAIT);
-        if (r == 0) return ready() ? 1 : -1;  // EOF: drain what is already in the ring first
-        if (r < 0 && errno != EAGAIN && errno != EWOULDBLOCK && errno != EINTR) return ready() ? 1 : -1;
-      } else if (pr < 0 && errno != EINTR) {
-        return -1;
+      rx_->consumer_asleep.store(1, std::memory_order_seq_cst);
+      if (ready()) {
+        rx_->consumer_asleep.store(0, std::memory_order_seq_cst);
+        lazy_polls_ = 0;
+        return 1;
       }
+      futex_wait_shared(&rx_->consumer_asleep, 1, slice);
+      rx_->consumer_asleep.store(0, std::memory_order_seq_cst);
+      if (ready()) {
+        lazy_polls_ = 0;
+        return 1;
+      }
+      if (dead()) return -1;
+      if (peer_closed()) return ready() ? 1 : -1;  // EOF: drain what is already in the ring first
+    }
+  }
+
+ public:
+  // Our side is closing the connection: get a reader that sleeps on the ring out of its wait.
+  void wake_reader() {
+    mark_dead();
+    if (rx_) {
+      rx_->consumer_asleep.store(0, std::memory_order_seq_cst);
+      futex_wake_shared(&rx_->consumer_asleep);
     }
   }
 
@@ -324,10 +363,10 @@ class Conn {
     }
   }
   void ring_doorbell() {
-    if (tx_->consumer_asleep.load(std::memory_order_seq_cst)) {
-      char b = 1;
-      (void)::send(fd_, &b, 1, MSG_NOSIGNAL | MSG_DONTWAIT);
-    }
+    // exchange: one wake per sleep, however many writes follow before the consumer is back
+    if (tx_->consumer_asleep.load(std::memory_order_seq_cst) &&
+        tx_->consumer_asleep.exchange(0, std::memory_order_seq_cst) == 1)
+      futex_wake_shared(&tx_->consumer_asleep);
   }
   bool peer_closed() {
     // POLLRDHUP: the peer shut its side down (FIN) — a server that refused a frame and left, a
@@ -340,6 +379,9 @@ class Conn {
   int fd_;
   AdaptiveSpin idle_;              // reader thread only
   bool latency_critical_ = true;  // reader thread only
+  int lazy_polls_ = 0;            // reader thread only
+  static constexpr int kLazyPolls = 50;     // x kLazyPollUs of silence before the announced sleep
+  static constexpr int kLazyPollUs = 200;
   std::atomic<bool> dead_{false};
   void* map_ = nullptr;
   size_t map_len_ = 0;

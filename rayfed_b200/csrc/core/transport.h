@@ -279,7 +279,7 @@ class Peer {
   // on a number that was closed — and possibly reused — under it.
   void close_conn() {
     int fd = fd_.exchange(-1);
-    if (auto c = std::atomic_load(&conn_)) c->mark_dead();
+    if (auto c = std::atomic_load(&conn_)) c->wake_reader();  // marks it dead; a ring reader sleeps on a futex
     if (fd >= 0) ::shutdown(fd, SHUT_RDWR);
   }
 
@@ -610,6 +610,7 @@ class SocketTransport {
     }
     for (auto& kv : peers) kv.second->stop();
     for (auto& c : conns) {
+      if (c.conn) c.conn->wake_reader();
       ::shutdown(c.fd, SHUT_RDWR);
     }
     for (auto& c : conns) {
@@ -657,10 +658,12 @@ class SocketTransport {
       ServerConn c;
       c.fd = cfd;
       c.done = std::make_shared<std::atomic<bool>>(false);
+      c.conn = std::make_shared<Conn>(cfd);
       auto done = c.done;
-      c.th = std::thread([this, cfd, done] {
+      auto conn = c.conn;
+      c.th = std::thread([this, cfd, done, conn] {
         try {
-          serve(cfd);
+          serve(*conn);
         } catch (...) {  // nothing may escape a std::thread (std::terminate): drop the connection
           stats_.rejected.fetch_add(1, std::memory_order_relaxed);
         }
@@ -673,8 +676,8 @@ class SocketTransport {
     }
   }
 
-  void serve(int fd) {
-    Conn c(fd);
+  void serve(Conn& c) {
+    const int fd = c.fd();
     for (;;) {
       FrameHeader h{};
       if (!c.read_all(&h, sizeof(h))) return;
@@ -757,6 +760,7 @@ class SocketTransport {
     int fd = -1;
     std::thread th;
     std::shared_ptr<std::atomic<bool>> done;
+    std::shared_ptr<Conn> conn;  // stop() wakes a reader that sleeps on its ring
   };
   std::vector<ServerConn> conns_;
   std::atomic<int> listen_fd_{-1};
