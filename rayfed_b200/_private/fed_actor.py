@@ -35,7 +35,12 @@ class FedActorHandle:
         # Raises AttributeError for unknown methods — in every party.
         getattr(self._body, method_name)
         # actor-level options apply to every method (reference: fed_actor.py:67,76)
-        return FedActorMethod(self._addresses, self._party, self._node_party, self, method_name, self._options)
+        method = FedActorMethod(self._addresses, self._party, self._node_party, self, method_name, self._options)
+        if not method_name.startswith("_"):
+            # `actor.method` is looked up once: later accesses find the bound method in the instance
+            # dict and never come back here (`.options()` hands out a copy, so sharing it is safe)
+            self.__dict__[method_name] = method
+        return method
 
     def _execute_impl(self, cls_args, cls_kwargs):
         """Instantiate — owner party only."""
@@ -71,9 +76,11 @@ class FedActorMethod:
         return self._fed_call_holder.internal_remote(*args, **kwargs)
 
     def options(self, **options):
-        self._options = options
-        self._fed_call_holder.options(**options)
-        return self
+        """A method bound with call options (``num_returns=...``).  Returns a NEW bound method: the
+        one cached on the actor handle stays as it is (in the reference every attribute access
+        makes a fresh object, fed_actor.py:62-80, so options never leak between calls either)."""
+        return FedActorMethod(self._addresses, self._party, self._node_party, self._fed_actor_handle,
+                              self._method_name, options)
 
     def _execute_impl(self, args, kwargs):
         return self._fed_actor_handle._execute_remote_method(self._method_name, self._options, args, kwargs)

@@ -29,6 +29,9 @@ class GlobalContext:
         self._job_name = job_name
         self._current_party = current_party
         self._seq = native().SeqCounter()
+        # the mint is called once per fed call in every party: bind the native method directly
+        # (no Python frame in between)
+        self.next_seq_id = self._seq.next
         self._sending_failure_handler = sending_failure_handler
         self._exit_on_sending_failure = exit_on_sending_failure
         self._atomic_shutdown_flag_lock = threading.Lock()

@@ -56,6 +56,30 @@ class Mailbox {
     return s.ref;
   }
 
+  // Several claims that share the downstream id (the arguments of one task): one lock, one call.
+  std::vector<RefPtr> claim_many(const std::vector<std::string>& ups, const std::string& down) {
+    std::vector<RefPtr> out;
+    out.reserve(ups.size());
+    std::lock_guard<std::mutex> lk(mu_);
+    for (const auto& up : ups) {
+      stats_.claimed.fetch_add(1, std::memory_order_relaxed);
+      std::string key = make_key(up, down);
+      auto it = slots_.find(key);
+      if (it != slots_.end()) {
+        RefPtr r = it->second.ref;
+        if (it->second.filled) slots_.erase(it);
+        out.push_back(std::move(r));
+        continue;
+      }
+      Slot s;
+      s.ref = std::make_shared<Ref>();
+      s.claimed = true;
+      out.push_back(s.ref);
+      slots_.emplace(std::move(key), std::move(s));
+    }
+    return out;
+  }
+
   // Transport side (no GIL): bytes arrive.
   void deliver_raw(const std::string& up, const std::string& down, std::string bytes, bool is_error) {
     RefPtr ref = take_for_delivery(up, down);

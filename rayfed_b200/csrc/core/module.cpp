@@ -279,6 +279,15 @@ PYBIND11_MODULE(_fedcore, m) {
   py::class_<Mailbox, std::shared_ptr<Mailbox>>(m, "Mailbox")
       .def(py::init<>())
       .def("claim", &Mailbox::claim)
+      .def(
+          "claim_many",
+          [](Mailbox& mb, const std::vector<std::string>& ups, const std::string& down, py::object decoder) {
+            std::vector<RefPtr> refs = mb.claim_many(ups, down);
+            if (!decoder.is_none())
+              for (auto& r : refs) r->set_decoder(decoder);
+            return refs;
+          },
+          py::arg("ups"), py::arg("down"), py::arg("decoder") = py::none())
       .def("deliver_obj", &Mailbox::deliver_obj, py::arg("up"), py::arg("down"), py::arg("obj"),
            py::arg("is_error") = false)
       .def(

@@ -291,6 +291,16 @@ class ProxyHost:
         self._into_ref(out, result, on_value)
         return result
 
+    def get_data_many(self, items, curr_seq_id):
+        """Batch flavour of `get_data` for the remote arguments of one task ([(src, upstream id)]);
+        None when the proxy has no batch entry point (the caller falls back to single claims)."""
+        many = getattr(self._proxy_instance, "get_data_many", None) if self._native_refs else None
+        if many is None:
+            return None
+        for _ in items:
+            self._recv_seen = next(self._recv_ops)
+        return many(items, curr_seq_id)
+
     def _get_stats(self):
         stats = {}
         if self._send_ops is not None:
@@ -578,6 +588,16 @@ def recv(party: str, src_party: str, upstream_seq_id, curr_seq_id):
     if _tracing._TRACER is not None:
         _tracing.trace_ref("recv", ref, seq_id=f"{upstream_seq_id}->{curr_seq_id}", src=src_party)
     return ref
+
+
+def recv_many(party: str, items, curr_seq_id):
+    """`recv` for several (src_party, upstream_seq_id) pairs that feed one task: one call into the
+    transport instead of one per argument.  Returns the list of `Ref`s."""
+    host: ProxyHost = _HOSTS["receiver"] or get_runtime().get_named(receiver_proxy_actor_name())
+    refs = host.get_data_many(items, curr_seq_id) if _tracing._TRACER is None else None
+    if refs is None:
+        return [recv(party, src, up, curr_seq_id) for src, up in items]
+    return refs
 
 
 def pending_summary(limit: int = 16):

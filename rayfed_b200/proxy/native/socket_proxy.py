@@ -164,6 +164,11 @@ class NativeReceiverProxy(ReceiverProxy):
         ref.set_decoder(self._decoder)
         return ref
 
+    def get_data_many(self, items, curr_seq_id):
+        """``items``: [(src_party, upstream_seq_id)] — the remote arguments of one task; one native
+        call claims them all."""
+        return self._mailbox.claim_many([str(up) for _, up in items], str(curr_seq_id), self._decoder)
+
     @property
     def mailbox(self):
         return self._mailbox

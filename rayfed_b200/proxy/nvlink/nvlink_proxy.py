@@ -232,6 +232,7 @@ class NvlinkReceiverProxy(NativeReceiverProxy):
                  proxy_config: Dict = None):
         super().__init__(listening_address, party, job_name, tls_config, proxy_config)
         self._loads = Deserializer(self._proxy_config.serializing_allowed_list)
+        self._decoders = {}  # src party -> decoder closure
         self._ready = {}  # (src, k of the object's last block) -> (tensors, event, stream)
         self._cv = threading.Condition()
         self._threads = []
@@ -302,8 +303,11 @@ class NvlinkReceiverProxy(NativeReceiverProxy):
             raise out
         return out
 
-    def get_data(self, src_party, upstream_seq_id, curr_seq_id):
-        ref = self._mailbox.claim(str(upstream_seq_id), str(curr_seq_id))
+    def _decoder_for(self, src_party):
+        """Bytes -> value for messages of ``src_party`` (built once per source)."""
+        dec = self._decoders.get(src_party)
+        if dec is not None:
+            return dec
         loads = self._loads
 
         def decode(data: bytes, is_error: bool):
@@ -336,8 +340,19 @@ class NvlinkReceiverProxy(NativeReceiverProxy):
                 raise FedTaskError(obj, "", "recv")
             return obj
 
-        ref.set_decoder(decode)
+        self._decoders[src_party] = decode
+        return decode
+
+    def get_data(self, src_party, upstream_seq_id, curr_seq_id):
+        ref = self._mailbox.claim(str(upstream_seq_id), str(curr_seq_id))
+        ref.set_decoder(self._decoder_for(src_party))
         return ref
+
+    def get_data_many(self, items, curr_seq_id):
+        refs = self._mailbox.claim_many([str(up) for _, up in items], str(curr_seq_id))
+        for (src, _), ref in zip(items, refs):
+            ref.set_decoder(self._decoder_for(src))
+        return refs
 
     def stop(self):
         self._stopping = True

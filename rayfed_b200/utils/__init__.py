@@ -58,7 +58,21 @@ def resolve_dependencies(current_party, current_fed_task_id, *args, **kwargs):
     recv = _recv_fn()
 
     if not has_containers(args, kwargs):
-        # hot path: flat argument list, no pytree walk
+        # hot path: flat argument list, no pytree walk.  Several remote arguments (a fan-in: the
+        # aggregator of N parties) are claimed with one call into the transport.
+        pending = [a for a in args if type(a) is FedObject and a._node_party != current_party and a._ref is None]
+        if len(pending) > 1 and not kwargs:
+            from ..proxy.barriers import recv_many
+
+            seen, items, objs = set(), [], []
+            for a in pending:
+                if id(a) not in seen:
+                    seen.add(id(a))
+                    items.append((a._node_party, a.get_fed_task_id()))
+                    objs.append(a)
+            for a, ref in zip(objs, recv_many(current_party, items, current_fed_task_id)):
+                a._cache_ref(ref)
+
         def resolve(arg):
             if type(arg) is not FedObject:
                 return arg

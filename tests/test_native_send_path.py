@@ -180,3 +180,39 @@ def test_cleanup_manager_counts_through_the_tracker():
         assert cm.pending_sends() == 0
     finally:
         cm.stop(wait_for_sending=True)
+
+
+def test_claim_many_matches_single_claims():
+    n = native()
+    mb = n.Mailbox()
+    mb.deliver_obj("1#0", "9", "early", False)          # arrived before anybody asked
+    refs = mb.claim_many(["1#0", "2#0", "3#0"], "9", None)
+    assert refs[0].result(1) == "early" and not refs[1].done() and not refs[2].done()
+    mb.deliver_obj("3#0", "9", "late", False)
+    assert refs[2].result(1) == "late"
+    # a second claim of a pending key shares the future; decoders are attached to all
+    again = mb.claim_many(["2#0"], "9", lambda data, is_error: data.decode() + "!")
+    mb2 = n.Mailbox()
+    r = mb2.claim_many(["a"], "b", lambda data, is_error: data.decode() + "!")[0]
+    r.set_raw(b"x", False)
+    assert r.result(1) == "x!"
+    mb.deliver_obj("2#0", "9", 5, False)
+    assert refs[1].result(1) == 5 and again[0].result(1) == 5
+    assert mb.pending() == 0
+
+
+def test_actor_methods_are_cached_and_options_do_not_leak():
+    from rayfed_b200._private.fed_actor import FedActorHandle
+
+    class Body:
+        def work(self):
+            return 1
+
+    h = FedActorHandle(1, {"alice": "127.0.0.1:1", "bob": "127.0.0.1:2"}, Body, "alice", "bob", {})
+    m = h.work
+    assert h.work is m                                   # looked up once
+    two = m.options(num_returns=2)
+    assert two is not m and two._options == {"num_returns": 2}
+    assert m._options == {} and h.work._options == {}    # the cached method is untouched
+    with pytest.raises(AttributeError):
+        h.no_such_method
