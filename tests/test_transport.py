@@ -333,6 +333,14 @@ def test_nvlink_receiver_applies_the_allow_list_to_the_skeleton():
         ok = pickle.dumps(("fedcuda", 0, pickle.dumps({"a": 1})))
         rx.mailbox.deliver_raw("3", "4", ok, False)
         assert rx.get_data("alice", "3", "4").result(5) == {"a": 1}
+        # the batch entry point (the remote arguments of one task) decodes the same frames, one
+        # decoder per source party
+        rx.mailbox.deliver_raw("5#0", "9", pickle.dumps(("fedcuda", 0, pickle.dumps([1, 2]))), False)
+        refs = rx.get_data_many([("alice", "5#0"), ("carol", "6#0")], "9")
+        rx.mailbox.deliver_raw("6#0", "9", pickle.dumps("plain"), False)
+        assert [r.result(5) for r in refs] == [[1, 2], "plain"]
+        assert rx._decoder_for("alice") is rx._decoder_for("alice")
+        assert rx._decoder_for("alice") is not rx._decoder_for("carol")
     finally:
         rx.stop()
 
