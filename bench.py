@@ -664,8 +664,15 @@ def many_tiny_tasks(fed, parties, iters=2000):
         fed.get(actors[parties[0]].agg.remote(*[actors[p].f.remote() for p in parties]))
     dt = time.perf_counter() - t0
     n = len(parties)
+    try:
+        from rayfed_b200.core import native
+
+        spin = native().spin_info()
+    except Exception:  # noqa: BLE001
+        spin = None
     return {
         "iterations": iters,
+        "spin_policy": spin,  # what fed.init picked from usable CPUs and parties per host
         "per_iteration_ms": dt / iters * 1e3,
         "tasks_per_sec": (n + 1) * iters / dt,
         "tasks_per_iteration": n + 1,
