@@ -363,6 +363,10 @@ class Conn {
     }
   }
   void ring_doorbell() {
+    // Dekker: our `head` store (release = a plain store on x86) must be globally visible before we
+    // read the consumer's announcement, or both sides can miss each other — the consumer sleeps on
+    // a frame that is already there and nobody wakes it until its 100 ms slice ends.
+    std::atomic_thread_fence(std::memory_order_seq_cst);
     // exchange: one wake per sleep, however many writes follow before the consumer is back
     if (tx_->consumer_asleep.load(std::memory_order_seq_cst) &&
         tx_->consumer_asleep.exchange(0, std::memory_order_seq_cst) == 1)

@@ -227,3 +227,40 @@ def test_shared_memory_offer_is_refused_politely_when_the_server_has_it_off(monk
     assert rx.stats()["shm_conns"] in (0, 1)  # env is process-wide: the race decides, both must work
     tx.stop()
     rx.stop()
+
+
+def test_ring_reader_never_misses_a_doorbell_around_the_sleep_boundary():
+    """Messages spaced right around the reader's spin budget hit the window where the consumer
+    announces its sleep while the producer publishes a frame (Dekker: store; fence; load on both
+    sides).  A missed wake-up shows as a delivery that takes the reader's whole 100 ms slice."""
+    import random
+    import time
+
+    from party_utils import free_ports
+    from rayfed_b200.core import native
+
+    nat = native()
+    addr = f"127.0.0.1:{free_ports(1)[0]}"
+    mb = nat.Mailbox()
+    rx = nat.SocketTransport("bob", "job", mb)
+    assert not rx.listen(addr)
+    tx = nat.SocketTransport("alice", "job", nat.Mailbox())
+    tx.add_peer("bob", addr, 20, 0.05, 0.2, 1.5, 10.0)
+    try:
+        tx.send("bob", "warm", "up", b"x").result(10.0)
+        assert rx.stats()["shm_conns"] == 1
+        rng = random.Random(7)
+        worst = 0.0
+        for i in range(4000):
+            gap = rng.uniform(20e-6, 70e-6)      # the base spin budget is 40 us
+            end = time.perf_counter() + gap
+            while time.perf_counter() < end:
+                pass
+            t0 = time.perf_counter()
+            tx.send("bob", str(i), "k", b"p")
+            assert mb.claim(str(i), "k").result(5.0) == b"p"
+            worst = max(worst, time.perf_counter() - t0)
+        assert worst < 0.08, f"a delivery took {worst * 1e3:.1f} ms: missed wake-up"
+    finally:
+        tx.stop()
+        rx.stop()
