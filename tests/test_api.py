@@ -219,3 +219,36 @@ def test_config_from_dict_drops_unknown_keys():
     assert c.timeout_in_ms == 7 and not hasattr(c, "bogus")
     g = GrpcCrossSiloMessageConfig.from_dict({"grpc_retry_policy": {"maxAttempts": 2}, "http_header": {"a": "b"}})
     assert g.grpc_retry_policy == {"maxAttempts": 2} and g.http_header == {"a": "b"}
+
+
+def test_init_picks_the_spin_policy_from_cpus_and_parties_per_host(monkeypatch):
+    """Adaptive spinning needs CPUs to burn: `fed.init` gives every party on this host an equal
+    share of half the usable CPUs and leaves long spins off below two spinners per party
+    (csrc/core/ref.h; measured on the B200 host: profiles/README.md R2.2b)."""
+    from rayfed_b200.api import _local_party_count
+    from rayfed_b200.core import native
+
+    assert _local_party_count({"a": "127.0.0.1:1", "b": "localhost:2", "c": "10.0.0.5:3"}, "a") == 2
+    assert _local_party_count({"a": "10.0.0.4:1", "b": "10.0.0.4:2", "c": "10.0.0.5:3"}, "c") == 1
+    assert _local_party_count({"a": "[::1]:1", "b": "127.0.0.1:2"}, "b") == 2
+
+    monkeypatch.delenv("RAYFED_B200_ADAPTIVE_SPIN_US", raising=False)
+    monkeypatch.delenv("RAYFED_B200_MAX_SPINNERS", raising=False)
+    nat = native()
+    before = nat.spin_info()
+    if "RAYFED_B200_ADAPTIVE_SPIN_US" in __import__("os").environ:
+        pytest.skip("policy overridden by the environment")
+    assert before["adaptive_cap_us"] == 0            # nothing configured outside a job
+    _init()
+    during = nat.spin_info()
+    share = during["usable_cpus"] // 2               # one party on this host
+    if share >= 2:
+        assert during["adaptive_cap_us"] == 500 and during["max_long_spinners"] == min(8, share)
+    else:
+        assert during["adaptive_cap_us"] == 0
+    fed.shutdown()
+    assert nat.spin_info()["adaptive_cap_us"] == 0
+    # many parties on a small host: off
+    nat.set_spin_policy_auto(during["usable_cpus"])
+    assert nat.spin_info()["adaptive_cap_us"] == 0
+    nat.set_spin_policy(-1, -1)
