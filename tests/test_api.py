@@ -232,12 +232,12 @@ def test_init_picks_the_spin_policy_from_cpus_and_parties_per_host(monkeypatch):
     assert _local_party_count({"a": "10.0.0.4:1", "b": "10.0.0.4:2", "c": "10.0.0.5:3"}, "c") == 1
     assert _local_party_count({"a": "[::1]:1", "b": "127.0.0.1:2"}, "b") == 2
 
-    monkeypatch.delenv("RAYFED_B200_ADAPTIVE_SPIN_US", raising=False)
-    monkeypatch.delenv("RAYFED_B200_MAX_SPINNERS", raising=False)
+    import os
+
+    if "RAYFED_B200_ADAPTIVE_SPIN_US" in os.environ or "RAYFED_B200_MAX_SPINNERS" in os.environ:
+        pytest.skip("policy overridden by the environment (read once per process by the native module)")
     nat = native()
     before = nat.spin_info()
-    if "RAYFED_B200_ADAPTIVE_SPIN_US" in __import__("os").environ:
-        pytest.skip("policy overridden by the environment")
     assert before["adaptive_cap_us"] == 0            # nothing configured outside a job
     _init()
     during = nat.spin_info()
