@@ -116,6 +116,13 @@ class CleanupManager:
     def pending_sends(self) -> int:
         return self._tracker.pending()
 
+    def stats(self) -> dict:
+        """Sends being watched and how the finished ones were settled: ``acked_natively`` never
+        touched the interpreter, ``settled_in_python`` are failures and Python-object outcomes."""
+        t = self._tracker
+        return {"pending": t.pending(), "pending_errors": t.pending_errors(),
+                "acked_natively": t.fast_retired(), "settled_in_python": t.slow_settled()}
+
     def get_last_sending_error(self):
         return self._last_sending_error
 
