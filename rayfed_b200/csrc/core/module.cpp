@@ -374,6 +374,7 @@ PYBIND11_MODULE(_fedcore, m) {
             std::string missing;
             {
               py::gil_scoped_release rel;
+              DoorbellBatch batch;  // sleeping receivers are woken together, with ONE futex call
               for (size_t i = 0; i < dests.size(); ++i) {
                 std::string copy = i + 1 == dests.size() ? std::move(payload) : payload;
                 if (!t.send(dests[i], up, down, std::move(copy), is_error, acks[i])) {
@@ -409,6 +410,7 @@ PYBIND11_MODULE(_fedcore, m) {
         d["bytes_received"] = s.bytes_received.load();
         d["rejected"] = s.rejected.load();
         d["shm_conns"] = s.shm_conns.load();
+        d["paged_conns"] = s.paged_conns.load();
         return d;
       });
 }

@@ -16,14 +16,17 @@
 #include <poll.h>
 #include <sys/syscall.h>
 #include <sys/mman.h>
+#include <time.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
 #include <atomic>
 #include <chrono>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 
@@ -106,11 +109,110 @@ inline void futex_wake_shared(std::atomic<uint32_t>* addr) {
   ::syscall(SYS_futex, reinterpret_cast<uint32_t*>(addr), FUTEX_WAKE, 1, nullptr, nullptr, 0);
 }
 
+// Absolute-deadline wait with a wake mask: several consumers (one per receiving party) sleep on
+// ONE word of the sender's doorbell page, each with its own bit; the sender wakes any subset of
+// them with a single system call (a fed.get broadcast to N-1 parties: 1 wake instead of N-1).
+inline int futex_wait_bitset_shared(std::atomic<uint32_t>* addr, uint32_t expected, int timeout_ms, uint32_t mask) {
+  timespec ts{};
+  ::clock_gettime(CLOCK_MONOTONIC, &ts);  // FUTEX_WAIT_BITSET takes an ABSOLUTE CLOCK_MONOTONIC deadline
+  ts.tv_sec += timeout_ms / 1000;
+  ts.tv_nsec += (long)(timeout_ms % 1000) * 1000000L;
+  if (ts.tv_nsec >= 1000000000L) {
+    ts.tv_sec += 1;
+    ts.tv_nsec -= 1000000000L;
+  }
+  return (int)::syscall(SYS_futex, reinterpret_cast<uint32_t*>(addr), FUTEX_WAIT_BITSET, expected,
+                        timeout_ms >= 0 ? &ts : nullptr, nullptr, mask);
+}
+inline void futex_wake_bitset_shared(std::atomic<uint32_t>* addr, uint32_t mask) {
+  ::syscall(SYS_futex, reinterpret_cast<uint32_t*>(addr), FUTEX_WAKE_BITSET, INT32_MAX, nullptr, nullptr, mask);
+}
+
+// One page per sending transport, mapped by every same-host receiver of that sender.
+static constexpr uint32_t kPageMagic = 0x50424653;  // "SFBP"
+struct DoorbellPage {
+  uint32_t magic;
+  alignas(64) std::atomic<uint32_t> seq;  // bumped before every wake: a consumer that read the old
+                                          // value and then calls futex_wait returns at once
+};
+static constexpr size_t kDoorbellPageBytes = 4096;
+
+class DoorbellPageOwner {
+ public:
+  DoorbellPageOwner() = default;
+  ~DoorbellPageOwner() {
+    if (map_) ::munmap(map_, kDoorbellPageBytes);
+    if (fd_ >= 0) ::close(fd_);
+  }
+  DoorbellPageOwner(const DoorbellPageOwner&) = delete;
+  DoorbellPageOwner& operator=(const DoorbellPageOwner&) = delete;
+  // "<pid>:<fd>" of an anonymous memory file (memfd): a same-host peer of the same user maps it
+  // through /proc/<pid>/fd/<fd> during the handshake.  Nothing is ever visible in /dev/shm, so
+  // nothing can be left behind by a crash.  "" when unavailable: the rings use their own words.
+  const std::string& ensure() {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (map_ || failed_) return desc_;
+    int fd = (int)::syscall(SYS_memfd_create, "rfb.doorbell", 1u /* MFD_CLOEXEC */);
+    if (fd < 0 || ::ftruncate(fd, (off_t)kDoorbellPageBytes) != 0) {
+      if (fd >= 0) ::close(fd);
+      failed_ = true;
+      return desc_;
+    }
+    void* m = ::mmap(nullptr, kDoorbellPageBytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (m == MAP_FAILED) {
+      ::close(fd);
+      failed_ = true;
+      return desc_;
+    }
+    auto* pg = new (m) DoorbellPage();
+    pg->seq.store(0);
+    pg->magic = kPageMagic;
+    map_ = m;
+    fd_ = fd;
+    desc_ = std::to_string((long)getpid()) + ":" + std::to_string(fd);
+    return desc_;
+  }
+  std::atomic<uint32_t>* seq() { return map_ ? &reinterpret_cast<DoorbellPage*>(map_)->seq : nullptr; }
+
+ private:
+  std::mutex mu_;
+  std::string desc_;
+  void* map_ = nullptr;
+  int fd_ = -1;
+  bool failed_ = false;
+};
+
+// Thread-local collector: while one is active, doorbells that go through the given page are not
+// rung one by one but OR-ed into a mask and rung together when the scope ends.
+struct DoorbellBatch {
+  std::atomic<uint32_t>* seq = nullptr;
+  uint32_t mask = 0;
+  static DoorbellBatch*& current() {
+    static thread_local DoorbellBatch* cur = nullptr;
+    return cur;
+  }
+  DoorbellBatch() { current() = this; }
+  ~DoorbellBatch() {
+    current() = nullptr;
+    flush();
+  }
+  void flush() {
+    if (seq && mask) {
+      seq->fetch_add(1, std::memory_order_seq_cst);
+      futex_wake_bitset_shared(seq, mask);
+    }
+    mask = 0;
+  }
+  DoorbellBatch(const DoorbellBatch&) = delete;
+  DoorbellBatch& operator=(const DoorbellBatch&) = delete;
+};
+
 class Conn {
  public:
   explicit Conn(int fd) : fd_(fd) {}
   ~Conn() {
     if (map_) ::munmap(map_, map_len_);
+    if (rx_page_map_) ::munmap(rx_page_map_, kDoorbellPageBytes);
   }
   Conn(const Conn&) = delete;
   Conn& operator=(const Conn&) = delete;
@@ -189,6 +291,41 @@ class Conn {
     return true;
   }
 
+  // ---- doorbell page (optional; both sides fall back to the ring's own futex word) ---------------
+  // server side: map the sender's page; this connection's reader then sleeps on its word with `bit`
+  bool attach_rx_page(const std::string& desc, int slot) {
+    if (slot < 0 || slot > 31) return false;
+    // "<pid>:<fd>", digits only: the path below is built from nothing else
+    size_t colon = desc.find(':');
+    if (colon == std::string::npos || colon == 0 || colon + 1 >= desc.size() || desc.size() > 24) return false;
+    if (desc.find_first_not_of("0123456789:") != std::string::npos || desc.find(':', colon + 1) != std::string::npos)
+      return false;
+    std::string path = "/proc/" + desc.substr(0, colon) + "/fd/" + desc.substr(colon + 1);
+    int sfd = ::open(path.c_str(), O_RDWR | O_CLOEXEC);
+    if (sfd < 0) return false;  // another pid namespace / another user: the ring's own word is used
+    struct stat st {};
+    if (::fstat(sfd, &st) != 0 || !S_ISREG(st.st_mode) || (size_t)st.st_size != kDoorbellPageBytes) {
+      ::close(sfd);
+      return false;
+    }
+    void* m = ::mmap(nullptr, kDoorbellPageBytes, PROT_READ | PROT_WRITE, MAP_SHARED, sfd, 0);
+    ::close(sfd);
+    if (m == MAP_FAILED) return false;
+    if (reinterpret_cast<DoorbellPage*>(m)->magic != kPageMagic) {
+      ::munmap(m, kDoorbellPageBytes);
+      return false;
+    }
+    rx_page_map_ = m;
+    rx_bit_ = 1u << slot;
+    rx_page_seq_.store(&reinterpret_cast<DoorbellPage*>(m)->seq, std::memory_order_release);
+    return true;
+  }
+  // client side: the server sleeps on our page; ring its doorbell there
+  void set_tx_page(std::atomic<uint32_t>* seq, int slot) {
+    tx_bit_ = 1u << slot;
+    tx_page_seq_ = seq;
+  }
+
   // ---- byte stream -------------------------------------------------------------------------------
   bool write_all(const void* buf, size_t n) {
     if (!tx_) return fd_write_all(fd_, buf, n);
@@ -201,7 +338,7 @@ class Conn {
       uint64_t space = cap - (head - tail);
       if (space == 0) {
         if (dead()) return false;
-        ring_doorbell();  // the consumer may be asleep with a full ring in front of it
+        ring_doorbell(/*now=*/true);  // the consumer may be asleep with a full ring in front of it
         if (++idle < 2000) {
           cpu_relax();
         } else {
@@ -316,13 +453,21 @@ class Conn {
         if (spent >= timeout_ms) return ready() ? 1 : 0;
         slice = (int)std::min<long long>(100, timeout_ms - spent);
       }
+      std::atomic<uint32_t>* page = rx_page_seq_.load(std::memory_order_acquire);
       rx_->consumer_asleep.store(1, std::memory_order_seq_cst);
+      // read the page word BEFORE the last look at the ring: a producer that bumps it after this
+      // point makes the wait below return at once; one that bumped it before has published its
+      // frame before that, so the look sees the frame
+      const uint32_t seen = page ? page->load(std::memory_order_seq_cst) : 0;
       if (ready()) {
         rx_->consumer_asleep.store(0, std::memory_order_seq_cst);
         lazy_polls_ = 0;
         return 1;
       }
-      futex_wait_shared(&rx_->consumer_asleep, 1, slice);
+      if (page)
+        futex_wait_bitset_shared(page, seen, slice, rx_bit_);
+      else
+        futex_wait_shared(&rx_->consumer_asleep, 1, slice);
       rx_->consumer_asleep.store(0, std::memory_order_seq_cst);
       if (ready()) {
         lazy_polls_ = 0;
@@ -339,7 +484,12 @@ class Conn {
     mark_dead();
     if (rx_) {
       rx_->consumer_asleep.store(0, std::memory_order_seq_cst);
-      futex_wake_shared(&rx_->consumer_asleep);
+      if (std::atomic<uint32_t>* page = rx_page_seq_.load(std::memory_order_acquire)) {
+        page->fetch_add(1, std::memory_order_seq_cst);
+        futex_wake_bitset_shared(page, rx_bit_);
+      } else {
+        futex_wake_shared(&rx_->consumer_asleep);
+      }
     }
   }
 
@@ -362,15 +512,28 @@ class Conn {
       rx_data_ = base;
     }
   }
-  void ring_doorbell() {
+  // `now`: never defer into a DoorbellBatch (the caller is about to wait for this consumer).
+  void ring_doorbell(bool now = false) {
     // Dekker: our `head` store (release = a plain store on x86) must be globally visible before we
     // read the consumer's announcement, or both sides can miss each other — the consumer sleeps on
     // a frame that is already there and nobody wakes it until its 100 ms slice ends.
     std::atomic_thread_fence(std::memory_order_seq_cst);
     // exchange: one wake per sleep, however many writes follow before the consumer is back
-    if (tx_->consumer_asleep.load(std::memory_order_seq_cst) &&
-        tx_->consumer_asleep.exchange(0, std::memory_order_seq_cst) == 1)
+    if (!tx_->consumer_asleep.load(std::memory_order_seq_cst) ||
+        tx_->consumer_asleep.exchange(0, std::memory_order_seq_cst) != 1)
+      return;
+    if (tx_page_seq_) {
+      DoorbellBatch* batch = now ? nullptr : DoorbellBatch::current();
+      if (batch && (batch->seq == nullptr || batch->seq == tx_page_seq_)) {
+        batch->seq = tx_page_seq_;  // rung with the others when the batch ends
+        batch->mask |= tx_bit_;
+        return;
+      }
+      tx_page_seq_->fetch_add(1, std::memory_order_seq_cst);
+      futex_wake_bitset_shared(tx_page_seq_, tx_bit_);
+    } else {
       futex_wake_shared(&tx_->consumer_asleep);
+    }
   }
   bool peer_closed() {
     // POLLRDHUP: the peer shut its side down (FIN) — a server that refused a frame and left, a
@@ -394,6 +557,11 @@ class Conn {
   char* tx_data_ = nullptr;
   ShmRing* rx_ = nullptr;
   char* rx_data_ = nullptr;
+  std::atomic<std::atomic<uint32_t>*> rx_page_seq_{nullptr};  // set once by the serve thread, read by wake_reader()
+  void* rx_page_map_ = nullptr;
+  uint32_t rx_bit_ = 0;
+  std::atomic<uint32_t>* tx_page_seq_ = nullptr;  // set before the connection is published
+  uint32_t tx_bit_ = 0;
   void* pending_map_ = nullptr;
   size_t pending_len_ = 0;
   std::string pending_name_;

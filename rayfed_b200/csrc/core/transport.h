@@ -110,6 +110,7 @@ struct TransportStats {
   std::atomic<uint64_t> bytes_received{0};
   std::atomic<uint64_t> rejected{0};
   std::atomic<uint64_t> shm_conns{0};  // connections whose data path is the shared-memory rings
+  std::atomic<uint64_t> paged_conns{0};  // ... whose reader sleeps on the sender's doorbell page
 };
 
 // ---------------------------------------------------------------------------
@@ -125,9 +126,9 @@ class Peer {
   };
 
   Peer(std::string name, std::string addr, std::string job, RetryPolicy retry, double timeout_s,
-       TransportStats* stats)
+       TransportStats* stats, DoorbellPageOwner* page = nullptr, int slot = -1)
       : name_(std::move(name)), addr_(std::move(addr)), job_(std::move(job)), retry_(retry),
-        timeout_s_(timeout_s), stats_(stats) {
+        timeout_s_(timeout_s), stats_(stats), page_(page), slot_(slot) {
     writer_ = std::thread([this] {
       try {
         writer_loop();
@@ -293,12 +294,24 @@ class Peer {
   bool offer_shm(Conn& c) {
     std::string name = c.create_segment();
     if (name.empty()) return true;  // no /dev/shm: plain socket
+    // "<ring segment>\n<doorbell page>\n<slot>": the page is shared by all receivers of this
+    // transport, so that one wake reaches any subset of them (shm_conn.h, DoorbellPage)
+    std::string hello = name;
+    // Opt-in (RAYFED_B200_DOORBELL_PAGE=1).  One FUTEX_WAKE_BITSET for N sleepers saves N-1 system
+    // calls, but the kernel's work per woken task stays: on the development VM a 7-receiver
+    // broadcast costs 125 us either way, and the B200 host was not measured with it.
+    static const bool page_enabled = [] {
+      const char* e = std::getenv("RAYFED_B200_DOORBELL_PAGE");
+      return e && e[0] == '1';
+    }();
+    const bool with_page = page_enabled && page_ && slot_ >= 0 && slot_ < 32 && !page_->ensure().empty();
+    if (with_page) hello += "\n" + page_->ensure() + "\n" + std::to_string(slot_);
     FrameHeader h{};
     h.magic = kMagic;
     h.type = kFrameHello;
-    h.data_len = name.size();
+    h.data_len = hello.size();
     std::string out((const char*)&h, sizeof(h));
-    out += name;
+    out += hello;
     bool io_ok = fd_write_all(c.fd(), out.data(), out.size());
     bool accepted = false;
     if (io_ok) {
@@ -310,7 +323,11 @@ class Peer {
         std::string skip(a.data_len, '\0');
         io_ok = a.data_len <= 4096 && fd_read_all(c.fd(), &skip[0], a.data_len);
       }
-      accepted = io_ok && a.code == 200;
+      accepted = io_ok && (a.code == 200 || a.code == 201);
+      if (accepted && a.code == 201 && with_page) {
+        c.set_tx_page(page_->seq(), slot_);  // the server sleeps on our page
+        stats_->paged_conns.fetch_add(1, std::memory_order_relaxed);
+      }
     }
     c.finish_create(accepted);
     if (accepted) stats_->shm_conns.fetch_add(1, std::memory_order_relaxed);
@@ -490,6 +507,8 @@ class Peer {
   RetryPolicy retry_;
   double timeout_s_;
   TransportStats* stats_;
+  DoorbellPageOwner* page_ = nullptr;  // the owning transport's doorbell page (outlives the peer)
+  int slot_ = -1;                      // this peer's bit in it
   std::mutex mu_;
   std::condition_variable cv_;
   std::deque<std::shared_ptr<Outgoing>> q_;
@@ -567,7 +586,8 @@ class SocketTransport {
 
   void add_peer(const std::string& name, const std::string& addr, RetryPolicy retry, double timeout_s) {
     std::lock_guard<std::mutex> lk(mu_);
-    peers_[name] = std::make_unique<Peer>(name, addr, job_, retry, timeout_s, &stats_);
+    int slot = next_slot_ < 32 ? next_slot_++ : -1;  // one wake bit per peer; beyond 32 the ring's own word
+    peers_[name] = std::make_unique<Peer>(name, addr, job_, retry, timeout_s, &stats_, &page_, slot);
   }
 
   // GIL-free hot path; `ack` resolves raw: b"OK" or error text.
@@ -686,8 +706,21 @@ class SocketTransport {
         // shm upgrade offer: data = segment name.  Answered on the socket; afterwards both
         // directions of this connection use the rings (or stay on the socket when refused).
         if (h.data_len == 0 || h.data_len > 255 || c.uses_shm()) return;
-        std::string name(h.data_len, '\0');
-        if (!c.read_all(&name[0], h.data_len)) return;
+        std::string hello(h.data_len, '\0');
+        if (!c.read_all(&hello[0], h.data_len)) return;
+        // "<ring segment>[\n<doorbell page>\n<slot>]"
+        std::string name = hello, page;
+        int slot = -1;
+        size_t nl = hello.find('\n');
+        if (nl != std::string::npos) {
+          name = hello.substr(0, nl);
+          size_t nl2 = hello.find('\n', nl + 1);
+          if (nl2 != std::string::npos) {
+            page = hello.substr(nl + 1, nl2 - nl - 1);
+            const std::string s = hello.substr(nl2 + 1);
+            if (!s.empty() && s.size() <= 2 && s.find_first_not_of("0123456789") == std::string::npos) slot = std::atoi(s.c_str());
+          }
+        }
         FrameHeader a{};
         a.magic = kMagic;
         a.type = kFrameAck;
@@ -695,7 +728,9 @@ class SocketTransport {
         // reply BEFORE switching the receive side (the client reads the answer on the socket)
         ok = ok && c.attach_segment(name);
         if (ok) stats_.shm_conns.fetch_add(1, std::memory_order_relaxed);
-        a.code = ok ? 200 : 501;
+        const bool paged = ok && !page.empty() && c.attach_rx_page(page, slot);
+        if (paged) stats_.paged_conns.fetch_add(1, std::memory_order_relaxed);
+        a.code = ok ? (paged ? 201 : 200) : 501;
         if (!fd_write_all(fd, &a, sizeof(a))) return;
         continue;
       }
@@ -763,6 +798,8 @@ class SocketTransport {
     std::shared_ptr<Conn> conn;  // stop() wakes a reader that sleeps on its ring
   };
   std::vector<ServerConn> conns_;
+  DoorbellPageOwner page_;  // sender role: the word all same-host receivers of this transport sleep on
+  int next_slot_ = 0;
   std::atomic<int> listen_fd_{-1};
   std::atomic<bool> stopped_{false};
   std::thread accept_thread_;

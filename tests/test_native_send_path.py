@@ -216,3 +216,46 @@ def test_actor_methods_are_cached_and_options_do_not_leak():
     assert m._options == {} and h.work._options == {}    # the cached method is untouched
     with pytest.raises(AttributeError):
         h.no_such_method
+
+
+def test_doorbell_page_wakes_several_sleeping_receivers_with_one_call(tmp_path):
+    """Opt-in path (RAYFED_B200_DOORBELL_PAGE=1): the receivers of one sender sleep on ONE futex
+    word of the sender's anonymous doorbell page, each with its own wake bit; a broadcast rings
+    them together.  Runs in a subprocess because the switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    import textwrap
+
+    code = textwrap.dedent("""
+        import socket, time
+        from rayfed_b200.core import native
+        def fp():
+            s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+        n = native(); names = ["b", "c", "d"]; ports = [fp() for _ in names]; rxs = []
+        for nm, p in zip(names, ports):
+            mb = n.Mailbox(); t = n.SocketTransport(nm, "job", mb); assert not t.listen(f"127.0.0.1:{p}"); rxs.append((t, mb))
+        tx = n.SocketTransport("a", "job", n.Mailbox())
+        for nm, p in zip(names, ports):
+            tx.add_peer(nm, f"127.0.0.1:{p}", 5, 0.05, 0.5, 2.0, 10.0)
+        worst = 0.0
+        for i in range(40):
+            time.sleep(0.01)                       # every reader is asleep again
+            t0 = time.perf_counter()
+            acks = tx.send_many(names, str(i), "k", b"x")
+            for _, mb in rxs:
+                assert mb.claim(str(i), "k").result(5) == b"x"
+            worst = max(worst, time.perf_counter() - t0)
+            assert [a.result(5) for a in acks] == [True] * 3
+        # unicast goes through the page too (exact wake: one bit)
+        time.sleep(0.01)
+        assert tx.send("c", "u", "k", b"y").result(5) is True and rxs[1][1].claim("u", "k").result(5) == b"y"
+        assert tx.stats()["paged_conns"] == 3 and all(t.stats()["paged_conns"] == 1 for t, _ in rxs)
+        assert worst < 0.08, worst                # a missed wake-up would cost a 100 ms slice
+        tx.stop(); [t.stop() for t, _ in rxs]
+        print("OK")
+    """)
+    env = dict(os.environ, RAYFED_B200_DOORBELL_PAGE="1",
+               PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
