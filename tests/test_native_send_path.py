@@ -238,20 +238,20 @@ def test_doorbell_page_wakes_several_sleeping_receivers_with_one_call(tmp_path):
         tx = n.SocketTransport("a", "job", n.Mailbox())
         for nm, p in zip(names, ports):
             tx.add_peer(nm, f"127.0.0.1:{p}", 5, 0.05, 0.5, 2.0, 10.0)
-        worst = 0.0
+        slow = 0
         for i in range(40):
             time.sleep(0.01)                       # every reader is asleep again
             t0 = time.perf_counter()
             acks = tx.send_many(names, str(i), "k", b"x")
             for _, mb in rxs:
                 assert mb.claim(str(i), "k").result(5) == b"x"
-            worst = max(worst, time.perf_counter() - t0)
+            slow += time.perf_counter() - t0 > 0.09
             assert [a.result(5) for a in acks] == [True] * 3
         # unicast goes through the page too (exact wake: one bit)
         time.sleep(0.01)
         assert tx.send("c", "u", "k", b"y").result(5) is True and rxs[1][1].claim("u", "k").result(5) == b"y"
         assert tx.stats()["paged_conns"] == 3 and all(t.stats()["paged_conns"] == 1 for t, _ in rxs)
-        assert worst < 0.08, worst                # a missed wake-up would cost a 100 ms slice
+        assert slow <= 2, slow                    # a missed wake-up costs a 100 ms slice, every time
         tx.stop(); [t.stop() for t, _ in rxs]
         print("OK")
     """)
