@@ -353,7 +353,8 @@ class Conn {
       size_t first = std::min(chunk, (size_t)(cap - off));
       std::memcpy(tx_data_ + off, p, first);
       if (chunk > first) std::memcpy(tx_data_, p + first, chunk - first);
-      tx_->head.store(head + chunk, std::memory_order_release);
+      // seq_cst, not just release: Dekker with the consumer's sleep announcement (ring_doorbell)
+      tx_->head.store(head + chunk, std::memory_order_seq_cst);
       p += chunk;
       n -= chunk;
     }
@@ -514,10 +515,10 @@ class Conn {
   }
   // `now`: never defer into a DoorbellBatch (the caller is about to wait for this consumer).
   void ring_doorbell(bool now = false) {
-    // Dekker: our `head` store (release = a plain store on x86) must be globally visible before we
-    // read the consumer's announcement, or both sides can miss each other — the consumer sleeps on
-    // a frame that is already there and nobody wakes it until its 100 ms slice ends.
-    std::atomic_thread_fence(std::memory_order_seq_cst);
+    // Dekker: our `head` store must be globally visible before we read the consumer's announcement,
+    // or both sides can miss each other — the consumer sleeps on a frame that is already there and
+    // nobody wakes it until its 100 ms slice ends.  Both are seq_cst operations (a release store is
+    // a plain store on x86 and may be reordered after the following load).
     // exchange: one wake per sleep, however many writes follow before the consumer is back
     if (!tx_->consumer_asleep.load(std::memory_order_seq_cst) ||
         tx_->consumer_asleep.exchange(0, std::memory_order_seq_cst) != 1)
