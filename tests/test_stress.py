@@ -265,3 +265,69 @@ def test_ring_reader_never_misses_a_doorbell_around_the_sleep_boundary():
     finally:
         tx.stop()
         rx.stop()
+
+
+def test_send_tracker_under_racing_completions():
+    """Watches and completions race from several threads; acknowledged sends must be retired
+    natively, every failure must reach the Python handler exactly once, and the counters must
+    return to zero (csrc/core/send_tracker.h)."""
+    import random
+    import threading
+
+    from rayfed_b200.core import native
+
+    nat = native()
+    seen = []
+    lock = threading.Lock()
+
+    def handler(ref, pack, is_error):
+        with lock:
+            seen.append(pack)
+        tracker.retire(is_error)
+
+    tracker = nat.SendTracker(handler)
+    n_threads, per_thread = 6, 1500
+    expected_failures = set()
+    refs = [[None] * per_thread for _ in range(n_threads)]
+
+    def producer(t):
+        rng = random.Random(t)
+        for i in range(per_thread):
+            r = nat.Ref()
+            r.set_ack_mode()
+            refs[t][i] = r
+            fail = rng.random() < 0.05
+            if fail:
+                with lock:
+                    expected_failures.add((t, i))
+            if rng.random() < 0.5:          # resolved before it is watched
+                r.set_raw(b"lost" if fail else b"OK", fail)
+                tracker.watch(r, (t, i), False)
+            else:
+                tracker.watch(r, (t, i), False)
+                pending.append((r, fail))
+
+    pending = []                             # appended under the GIL; drained by the completers
+    stop = threading.Event()
+
+    def completer():
+        while not stop.is_set() or pending:
+            try:
+                r, fail = pending.pop()
+            except IndexError:
+                continue
+            r.set_raw(b"lost" if fail else b"OK", fail)
+
+    completers = [threading.Thread(target=completer) for _ in range(3)]
+    producers = [threading.Thread(target=producer, args=(t,)) for t in range(n_threads)]
+    [t.start() for t in completers + producers]
+    [t.join() for t in producers]
+    stop.set()
+    [t.join() for t in completers]
+    tracker.set_draining(True)
+    assert tracker.wait_idle(10.0)
+    assert tracker.pending() == 0 and not tracker.settling()
+    assert sorted(seen) == sorted(expected_failures)
+    assert tracker.fast_retired() == n_threads * per_thread - len(expected_failures)
+    assert tracker.slow_settled() == len(expected_failures)
+    tracker.bury()
