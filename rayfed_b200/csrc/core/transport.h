@@ -381,12 +381,14 @@ class Peer {
     h.up_len = (uint32_t)m->up.size();
     h.down_len = (uint32_t)m->down.size();
     h.data_len = m->data.size();
-    std::string head((const char*)&h, sizeof(h));
+    size_t nbytes = m->data.size();
+    std::string head;
+    head.reserve(sizeof(h) + job_.size() + m->up.size() + m->down.size() + (nbytes <= 4096 ? nbytes : 0));
+    head.append((const char*)&h, sizeof(h));
     head += job_;
     head += m->up;
     head += m->down;
-    size_t nbytes = m->data.size();
-    if (nbytes <= 4096) head += m->data;  // one syscall for small messages
+    if (nbytes <= 4096) head += m->data;  // one write (one syscall on the socket path) for small messages
     RefPtr ack = m->ack;
     uint64_t id = m->id;
     {
