@@ -273,6 +273,44 @@ class Executor : public std::enable_shared_from_this<Executor> {
     }
   }
 
+  // Block until every input is resolved.  A fan-in (the aggregator of N parties) used to wait for
+  // its inputs one after the other — up to N sleeps and N wake-ups when the arrivals are spread
+  // out; with several inputs outstanding the lane thread now sleeps ONCE, on a countdown latch the
+  // inputs' native continuations release.
+  static void wait_inputs(const std::vector<RefPtr>& deps) {
+    size_t outstanding = 0;
+    for (auto& d : deps)
+      if (!d->done()) ++outstanding;
+    if (outstanding == 0) return;
+    if (outstanding == 1) {
+      for (auto& d : deps) d->wait(-1.0);
+      return;
+    }
+    struct Latch {
+      std::atomic<int> left{0};
+      std::mutex mu;
+      std::condition_variable cv;
+    };
+    auto latch = std::make_shared<Latch>();
+    latch->left.store((int)deps.size(), std::memory_order_relaxed);
+    for (auto& d : deps) {
+      d->on_done([latch] {
+        if (latch->left.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+          std::lock_guard<std::mutex> lk(latch->mu);  // pairs with the predicate check of the waiter
+          latch->cv.notify_all();
+        }
+      });
+    }
+    static thread_local AdaptiveSpin hist;
+    adaptive_wait(
+        hist, [&] { return latch->left.load(std::memory_order_acquire) <= 0; },
+        [&] {
+          std::unique_lock<std::mutex> lk(latch->mu);
+          latch->cv.wait(lk, [&] { return latch->left.load(std::memory_order_acquire) <= 0; });
+          return true;
+        });
+  }
+
   static void worker_loop(LanePtr& lane, std::shared_ptr<ExecStats>& stats, py::object& wrap) {
     AdaptiveSpin idle;  // a lane that is called every few hundred us stays awake between calls
     for (;;) {
@@ -305,7 +343,7 @@ class Executor : public std::enable_shared_from_this<Executor> {
       }
       if (lane->ordered) {
         // Actor mailbox: park on the inputs (no GIL held here).
-        for (auto& d : t->deps) d->wait(-1.0);
+        wait_inputs(t->deps);
       }
       if (!interpreter_alive()) return;
       if (lane->init_gen.load(std::memory_order_acquire) != tl_init_gen()) bind_thread(*lane);
