@@ -184,3 +184,44 @@ def test_ref_adopts_the_event_of_a_device_value():
     plain.set_value(3)
     assert plain.cuda_event == 0
     plain.device_sync()  # no event, no hooks: a no-op
+
+
+def test_actor_lane_waits_for_a_fan_in_on_one_latch(rt):
+    """An actor method with many outstanding inputs (the aggregator of N parties) runs exactly when
+    the LAST one resolves, whatever the order and the thread of the completions, and sees every
+    value (csrc/core/executor.h::wait_inputs: one countdown latch instead of N sequential waits)."""
+    import random
+
+    class Agg:
+        def total(self, *xs):
+            return sum(xs)
+
+    h = rt.create_actor(Agg)
+    for round_no in range(20):
+        deps = [core.Ref() for _ in range(9)]
+        deps[3].set_value(100)                                  # some inputs are already there
+        out = h.submit_method("total", tuple(deps) + (deps[0],), {})   # the same input twice
+        order = [i for i in range(9) if i != 3]
+        random.Random(round_no).shuffle(order)
+        last = order.pop()
+
+        def complete(ids):
+            for i in ids:
+                deps[i].set_value(i)
+
+        ts = [threading.Thread(target=complete, args=(order[k::3],)) for k in range(3)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        time.sleep(0.002)
+        assert not out.done()                                   # one input is still missing
+        deps[last].set_value(last)
+        assert out.result(5) == sum(i for i in range(9) if i != 3) + 100 + 0
+    # an input that fails: the error flows along the edge, later calls still run
+    bad, ok = core.Ref(), core.Ref()
+    failing = h.submit_method("total", (bad, ok, 1), {})
+    after = h.submit_method("total", (1, 2), {})
+    ok.set_value(5)
+    bad.set_error(ValueError("boom"))
+    with pytest.raises(Exception, match="boom"):
+        failing.result(5)
+    assert after.result(5) == 3
