@@ -124,9 +124,9 @@ inline bool spin_until(Pred&& pred) {
 // work, slow peers, a training step between messages) push the average above the cap and the
 // waiter falls back to the base budget, so nothing burns a core unless messages really arrive
 // every few hundred microseconds.  The number of threads that may spin long at once is bounded
-// per process.  RAYFED_B200_ADAPTIVE_SPIN_US = cap in microseconds (default 500, 0 = off);
-// RAYFED_B200_MAX_SPINNERS = concurrent long spinners per process (default: hardware threads / 4,
-// clamped to [2, 16]).
+// per process.  RAYFED_B200_ADAPTIVE_SPIN_US = cap in microseconds (0 = off) and
+// RAYFED_B200_MAX_SPINNERS = concurrent long spinners per process override the policy below.
+
 // CPUs this process may really use: the affinity mask, cut down by a cgroup CPU quota if any.
 inline int usable_cpus() {
   static int v = [] {
@@ -169,8 +169,10 @@ inline int usable_cpus() {
 // deployment switches them on: `fed.init` does (set_spin_policy), from the CPUs this process may
 // use and the number of parties that share the host.  Measured on the B200 host (128 hardware
 // threads behind a 16-CPU cgroup quota), many_tiny_tasks per iteration, off -> on:
-// 2 parties 164-193 -> 54-80 us, 4 parties 101-122 -> 87-113 us, 8 parties 181-186 -> 222-241 us
+// 2 parties 164-193 -> 44-80 us, 4 parties 101-122 -> 69-113 us, 8 parties 181-186 -> 222-241 us
 // (16 spinning threads eat the quota) — hence "at least two spinners' worth of CPU per party".
+// Spinning also keeps the 2-party case out of the deep-idle lottery: with sleeping threads the
+// same binary ran at 78 and at 521 us per iteration (profiles/README.md R2.2b).
 inline std::atomic<int> g_adaptive_cap_us{-1};   // -1: not configured
 inline std::atomic<int> g_max_long_spinners{-1};
 
@@ -212,7 +214,7 @@ inline std::atomic<int> g_long_spinners{0};
 // Self-limiting: a long spin only pays when there is a core to burn.  A spinner that notices a
 // hole in its own time line (it was descheduled: more runnable threads than cores, or a cgroup
 // CPU quota throttling the process) switches long spins off for the whole process for a while;
-// repeated offences double the pause (2 ms .. 256 ms), clean spins shrink it again.
+// holes in quick succession double the pause (2 ms .. 256 ms), an isolated one costs 2 ms.
 inline std::atomic<int64_t> g_long_spin_off_until_ns{0};
 inline std::atomic<int> g_long_spin_pause_ms{2};
 inline std::atomic<long> g_long_spin_preemptions{0};
@@ -235,8 +237,6 @@ inline void long_spin_preempted() {
   g_long_spin_off_until_ns.store(now + (int64_t)pause * 1000000, std::memory_order_relaxed);
   g_long_spin_preemptions.fetch_add(1, std::memory_order_relaxed);
 }
-
-inline void long_spin_clean() {}
 
 // RAII claim on one of the process's long-spin slots.
 struct LongSpinSlot {
@@ -261,10 +261,7 @@ inline bool spin_long(Pred&& pred, int budget_us) {
   const int64_t t0 = mono_ns();
   int64_t last = t0;
   for (;;) {
-    if (pred()) {
-      long_spin_clean();
-      return true;
-    }
+    if (pred()) return true;
     for (int i = 0; i < 32; ++i) cpu_relax();
     int64_t now = mono_ns();
     if (now - last > kHoleNs) {
