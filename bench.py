@@ -542,7 +542,35 @@ def run_ours(args):
         "clocks": clocks,
     }
 
+    # The headline is measured; everything below is secondary.  A secondary block may fail (caught
+    # by `guarded`) — and it must not be able to HANG the line away either: past the deadline every
+    # rank leaves, rank 0 printing what it has.
+    secondary_deadline_s = float(os.environ.get("RAYFED_B200_BENCH_SECONDARY_DEADLINE_S", "420"))
+    current_block = ["-"]
+
+    def bail():
+        import copy
+
+        for _ in range(5):
+            try:
+                snap = copy.deepcopy(out)
+                break
+            except RuntimeError:  # the main thread was adding a key
+                time.sleep(0.01)
+        else:
+            snap = {k: out[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step") if k in out}
+        snap["watchdog"] = (f"secondary blocks exceeded {secondary_deadline_s:.0f} s in '{current_block[0]}': "
+                            "partial result, the headline and e2e numbers are complete")
+        if rank == 0:
+            print(json.dumps(snap), flush=True)
+        os._exit(0)
+
+    watchdog = threading.Timer(secondary_deadline_s, bail)
+    watchdog.daemon = True
+    watchdog.start()
+
     def guarded(name, fn):
+        current_block[0] = name
         try:
             out[name] = fn()
         except Exception as e:  # noqa: BLE001  (a secondary metric must never cost the headline)
@@ -638,7 +666,9 @@ def run_ours(args):
 
             guarded("agg_check", agg_check)
     guarded("many_tiny_tasks", lambda: many_tiny_tasks(fed, parties, iters=args.tiny_iters))
+    current_block[0] = "shutdown"
     fed.shutdown()
+    watchdog.cancel()
     if rank == 0:
         print(json.dumps(out), flush=True)
 
