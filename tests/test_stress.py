@@ -331,3 +331,52 @@ def test_send_tracker_under_racing_completions():
     assert tracker.fast_retired() == n_threads * per_thread - len(expected_failures)
     assert tracker.slow_settled() == len(expected_failures)
     tracker.bury()
+
+
+def _ring_peer(addr, ready):
+    import time
+
+    from rayfed_b200.core import native
+
+    nat = native()
+    t = nat.SocketTransport("bob", "job", nat.Mailbox())
+    assert not t.listen(addr)
+    ready.set()
+    time.sleep(60)
+
+
+def test_a_killed_peer_fails_inflight_sends_promptly_over_the_rings():
+    """The shared-memory rings carry no EOF: a reader that sleeps on its ring looks at the socket
+    between 100 ms slices, so a send to a party that was killed fails in a fraction of a second
+    instead of waiting for `timeout_in_ms` (here 30 s)."""
+    import multiprocessing
+    import os
+    import signal
+    import time
+
+    from party_utils import free_ports
+    from rayfed_b200.core import native
+
+    ctx = multiprocessing.get_context("spawn")
+    ready = ctx.Event()
+    addr = f"127.0.0.1:{free_ports(1)[0]}"
+    peer = ctx.Process(target=_ring_peer, args=(addr, ready), daemon=True)
+    peer.start()
+    assert ready.wait(60)
+    nat = native()
+    tx = nat.SocketTransport("alice", "job", nat.Mailbox())
+    tx.add_peer("bob", addr, 2, 0.05, 0.1, 1.5, 30.0)
+    try:
+        assert tx.send("bob", "1", "1", b"x").result(10) is True
+        assert tx.stats()["shm_conns"] == 1
+        time.sleep(0.3)                                # every thread is asleep on its ring
+        os.kill(peer.pid, signal.SIGKILL)
+        time.sleep(0.01)
+        t0 = time.perf_counter()
+        ack = tx.send("bob", "2", "2", b"y")
+        with pytest.raises(RuntimeError, match="closed|lost|connect"):
+            ack.result(20)
+        assert time.perf_counter() - t0 < 5.0
+    finally:
+        tx.stop()
+        peer.join(5)
