@@ -301,6 +301,11 @@ class Conn {
     if (desc.find_first_not_of("0123456789:") != std::string::npos || desc.find(':', colon + 1) != std::string::npos)
       return false;
     std::string path = "/proc/" + desc.substr(0, colon) + "/fd/" + desc.substr(colon + 1);
+    // only an anonymous memory file created by DoorbellPageOwner is acceptable — never a path the
+    // peer could have picked in the file system
+    char target[64] = {0};
+    ssize_t tl = ::readlink(path.c_str(), target, sizeof(target) - 1);
+    if (tl <= 0 || std::strncmp(target, "/memfd:rfb.doorbell", 19) != 0) return false;
     int sfd = ::open(path.c_str(), O_RDWR | O_CLOEXEC);
     if (sfd < 0) return false;  // another pid namespace / another user: the ring's own word is used
     struct stat st {};

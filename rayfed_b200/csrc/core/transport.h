@@ -57,6 +57,17 @@ struct FrameHeader {
 };
 #pragma pack(pop)
 
+// Opt-in on BOTH sides (RAYFED_B200_DOORBELL_PAGE=1).  One FUTEX_WAKE_BITSET for N sleepers saves
+// N-1 system calls, but the kernel's work per woken task stays: on the development VM a 7-receiver
+// broadcast costs 125 us either way, and the B200 host was not measured with it.
+inline bool doorbell_page_enabled() {
+  static const bool v = [] {
+    const char* e = std::getenv("RAYFED_B200_DOORBELL_PAGE");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
 struct RetryPolicy {
   // `proxy_max_restarts` of the reference (fed/proxy/barriers.py:301-307: the sender proxy actor is
   // restarted once and its in-flight sends are retried N times): a message that was written but
@@ -297,14 +308,7 @@ class Peer {
     // "<ring segment>\n<doorbell page>\n<slot>": the page is shared by all receivers of this
     // transport, so that one wake reaches any subset of them (shm_conn.h, DoorbellPage)
     std::string hello = name;
-    // Opt-in (RAYFED_B200_DOORBELL_PAGE=1).  One FUTEX_WAKE_BITSET for N sleepers saves N-1 system
-    // calls, but the kernel's work per woken task stays: on the development VM a 7-receiver
-    // broadcast costs 125 us either way, and the B200 host was not measured with it.
-    static const bool page_enabled = [] {
-      const char* e = std::getenv("RAYFED_B200_DOORBELL_PAGE");
-      return e && e[0] == '1';
-    }();
-    const bool with_page = page_enabled && page_ && slot_ >= 0 && slot_ < 32 && !page_->ensure().empty();
+    const bool with_page = doorbell_page_enabled() && page_ && slot_ >= 0 && slot_ < 32 && !page_->ensure().empty();
     if (with_page) hello += "\n" + page_->ensure() + "\n" + std::to_string(slot_);
     FrameHeader h{};
     h.magic = kMagic;
@@ -730,7 +734,7 @@ class SocketTransport {
         // reply BEFORE switching the receive side (the client reads the answer on the socket)
         ok = ok && c.attach_segment(name);
         if (ok) stats_.shm_conns.fetch_add(1, std::memory_order_relaxed);
-        const bool paged = ok && !page.empty() && c.attach_rx_page(page, slot);
+        const bool paged = ok && !page.empty() && doorbell_page_enabled() && c.attach_rx_page(page, slot);
         if (paged) stats_.paged_conns.fetch_add(1, std::memory_order_relaxed);
         a.code = ok ? (paged ? 201 : 200) : 501;
         if (!fd_write_all(fd, &a, sizeof(a))) return;
