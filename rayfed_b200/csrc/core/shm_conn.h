@@ -340,6 +340,7 @@ class Conn {
     while (n > 0) {
       uint64_t head = tx_->head.load(std::memory_order_relaxed);
       uint64_t tail = tx_->tail.load(std::memory_order_acquire);
+      if (head - tail > cap) return false;  // the peer scribbled over its counter: never index past the ring
       uint64_t space = cap - (head - tail);
       if (space == 0) {
         if (dead()) return false;
@@ -375,6 +376,7 @@ class Conn {
       uint64_t tail = rx_->tail.load(std::memory_order_relaxed);
       uint64_t head = rx_->head.load(std::memory_order_acquire);
       uint64_t avail = head - tail;
+      if (avail > cap) return false;  // a corrupt producer counter must not turn into an out-of-bounds copy
       if (avail == 0) {
         int w = wait_readable(-1);
         if (w < 0) return false;

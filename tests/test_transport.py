@@ -392,3 +392,56 @@ def test_proxy_max_restarts_resends_unacknowledged_messages(max_resends, monkeyp
     finally:
         cli.stop()
         srv.stop()
+
+
+def test_a_peer_that_corrupts_its_ring_counters_is_dropped_not_followed(tmp_path):
+    """The producer side of a shared-memory ring is another process: counters it scribbles over must
+    end the connection, never turn into a copy past the ring (csrc/core/shm_conn.h).  A hand-made
+    client performs the hello handshake with its own segment, then publishes an impossible `head`."""
+    import mmap
+    import os
+    import socket
+    import struct
+    import time
+
+    from rayfed_b200.core import native
+
+    if not os.path.isdir("/dev/shm"):
+        pytest.skip("no /dev/shm")
+    nat = native()
+    port = free_ports(1)[0]
+    mb = nat.Mailbox()
+    rx = nat.SocketTransport("bob", "job", mb)
+    assert not rx.listen(f"127.0.0.1:{port}")
+    cap = 64 * 1024
+    name = f"/rfb.test.{os.getpid()}"
+    path = "/dev/shm" + name
+    hdr = struct.Struct("<IBBHQIIIiQ")                      # FrameHeader, packed
+    try:
+        with open(path, "wb") as f:
+            f.truncate(4096 + 2 * cap)
+        fd = os.open(path, os.O_RDWR)
+        seg = mmap.mmap(fd, 4096 + 2 * cap)
+        os.close(fd)
+        struct.pack_into("<II", seg, 0, 0x52424653, cap)     # magic "SFBR", capacity; counters start at 0
+        s = socket.create_connection(("127.0.0.1", port))
+        s.sendall(hdr.pack(0x42444546, 3, 0, 0, 0, 0, 0, 0, 0, len(name)) + name.encode())
+        ack = s.recv(hdr.size, socket.MSG_WAITALL)
+        assert hdr.unpack(ack)[1] == 2 and hdr.unpack(ack)[8] == 200     # the server switched to the rings
+        struct.pack_into("<Q", seg, 64, 1 << 40)             # c2s.head: a terabyte "available"
+        s.settimeout(5.0)
+        t0 = time.perf_counter()
+        assert s.recv(1) == b""                               # dropped (EOF), within a reader slice or two
+        assert time.perf_counter() - t0 < 3.0
+        s.close()
+        seg.close()
+        # the party is alive and serves well-behaved peers
+        tx = nat.SocketTransport("alice", "job", nat.Mailbox())
+        tx.add_peer("bob", f"127.0.0.1:{port}", 5, 0.05, 0.2, 1.5, 10.0)
+        assert tx.send("bob", "1", "2", b"fine").result(10) is True
+        assert mb.claim("1", "2").result(5) == b"fine"
+        tx.stop()
+    finally:
+        if os.path.exists(path):
+            os.unlink(path)
+        rx.stop()
