@@ -428,11 +428,23 @@ def test_a_peer_that_corrupts_its_ring_counters_is_dropped_not_followed(tmp_path
         s.sendall(hdr.pack(0x42444546, 3, 0, 0, 0, 0, 0, 0, 0, len(name)) + name.encode())
         ack = s.recv(hdr.size, socket.MSG_WAITALL)
         assert hdr.unpack(ack)[1] == 2 and hdr.unpack(ack)[8] == 200     # the server switched to the rings
-        struct.pack_into("<Q", seg, 64, 1 << 40)             # c2s.head: a terabyte "available"
+        # a well-formed frame head that announces a body bigger than the ring ...
+        body = 200 * 1024
+        frame = hdr.pack(0x42444546, 1, 0, 0, 7, 3, 1, 1, 0, body) + b"job" + b"1" + b"2"
+        seg[4096:4096 + len(frame)] = frame
+        struct.pack_into("<Q", seg, 64, len(frame))          # c2s.head: publish it
+        deadline = time.time() + 3
+        while struct.unpack_from("<Q", seg, 128)[0] < len(frame) and time.time() < deadline:
+            time.sleep(0.005)                                 # c2s.tail: the server took the head and waits for the body
+        assert struct.unpack_from("<Q", seg, 128)[0] == len(frame)
+        # ... then a counter that claims a terabyte is available: following it would copy 200 KiB
+        # out of a 64 KiB ring, past the end of the mapping
+        struct.pack_into("<Q", seg, 64, 1 << 40)
         s.settimeout(5.0)
         t0 = time.perf_counter()
         assert s.recv(1) == b""                               # dropped (EOF), within a reader slice or two
         assert time.perf_counter() - t0 < 3.0
+        assert rx.stats()["receive_op_count"] == 0            # ... and nothing was "received" from beyond the ring
         s.close()
         seg.close()
         # the party is alive and serves well-behaved peers
