@@ -213,6 +213,26 @@ def run(args, clock_sampler_cls=None):
                   flush=True)
         return
     torch.cuda.set_device(local_rank)
+    # A hang of the reference (or of the stand-in under it) must not cost the line: past the deadline
+    # every rank leaves; rank 0 prints the device-timed headline if it was already measured.
+    import threading
+
+    deadline_s = float(os.environ.get("RAYFED_B200_REF_ARM_DEADLINE_S", "900"))
+    partial = {}
+
+    def bail():
+        if rank == 0:
+            if "value" in partial:
+                print(json.dumps(dict(partial, watchdog=f"the reference arm exceeded {deadline_s:.0f} s after its "
+                                      "device-timed region: partial result")), flush=True)
+            else:
+                print(json.dumps({"impl": "reference", "unavailable": f"the reference arm did not finish its timed "
+                                  f"region within {deadline_s:.0f} s"}), flush=True)
+        os._exit(0)
+
+    watchdog = threading.Timer(deadline_s, bail)
+    watchdog.daemon = True
+    watchdog.start()
     base = _env_int("MASTER_PORT", 29500) + 300
     parties = [f"p{i}" for i in range(n)]
     me = parties[rank]
@@ -253,6 +273,10 @@ def run(args, clock_sampler_cls=None):
         workers[p].mark.remote("t1")
     ms = fed.get([workers[p].elapsed_ms.remote("t0", "t1") for p in parties])
     dev_ms = max(ms) / K_steps
+    partial.update({"metric": "fedavg_resnet50_bf16_samples_per_sec", "value": n * L * BATCH / (dev_ms * 1e-3),
+                    "unit": "samples/s", "n_gpus": n, "steps": K_steps, "warmup": W, "ms_per_step": dev_ms,
+                    "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "impl": "reference",
+                    "substrate": substrate})
 
     # end to end: wall clock around K rounds incl. the per-round fed.get of the losses
     fed.get([workers[p].sync.remote() for p in parties])
@@ -294,5 +318,6 @@ def run(args, clock_sampler_cls=None):
     }
     fed.shutdown()
     ray.shutdown()
+    watchdog.cancel()
     if rank == 0:
         print(json.dumps(out), flush=True)
