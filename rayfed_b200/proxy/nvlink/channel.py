@@ -748,7 +748,7 @@ class DeviceChannel:
                 raise ValueError(f"inconsistent tensor geometry in device message: {p}")
             if p["whole"] and (e0 != 0 or ne != numel):
                 raise ValueError("a whole-tensor part must cover the tensor")
-            itemsize = torch.empty((), dtype=dtype).element_size()
+            itemsize = dtype.itemsize
             mode = int(p["mode"])
             want = ne * itemsize if mode == K.MODE_COPY else (ne * 2 if mode == K.MODE_F32_TO_BF16 else ne)
             if pay != want or (mode == K.MODE_BF16_TO_FP8 and scales != ne // 32) or \
