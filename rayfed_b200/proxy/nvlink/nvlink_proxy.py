@@ -80,19 +80,34 @@ class _DevicePickler(cloudpickle.Pickler):
         return None
 
 
+def _persistent_load(self, pid):
+    if isinstance(pid, tuple) and len(pid) == 2 and pid[0] == _TAG and isinstance(pid[1], int):
+        return self._resolve(pid[1])
+    if isinstance(pid, tuple) and len(pid) == 2 and pid[0] == _SMALL:
+        return self._rehome(pid[1])
+    raise pickle.UnpicklingError(f"unsupported persistent id {pid!r}")
+
+
+class _DeviceUnpickler(pickle.Unpickler):
+    """Skeleton unpickler without an allow-list."""
+
+    persistent_load = _persistent_load
+
+
+class _RestrictedDeviceUnpickler(_RestrictedUnpickler):
+    """Skeleton unpickler when `serializing_allowed_list` is configured: same `find_class` rules as
+    every other cross-party payload."""
+
+    persistent_load = _persistent_load
+
+
 def _make_unpickler(file, allowed, resolve, rehome):
-    """Skeleton unpickler: the restricted one whenever an allow-list is configured."""
-    base = pickle.Unpickler if allowed is None else _RestrictedUnpickler
-
-    class _DeviceUnpickler(base):
-        def persistent_load(self, pid):
-            if isinstance(pid, tuple) and len(pid) == 2 and pid[0] == _TAG and isinstance(pid[1], int):
-                return resolve(pid[1])
-            if isinstance(pid, tuple) and len(pid) == 2 and pid[0] == _SMALL:
-                return rehome(pid[1])
-            raise pickle.UnpicklingError(f"unsupported persistent id {pid!r}")
-
-    return _DeviceUnpickler(file) if allowed is None else _DeviceUnpickler(file, allowed)
+    """Skeleton unpickler: the restricted one whenever an allow-list is configured.  (The two
+    classes are module-level: building a class per message cost ~14 us on the receive path.)"""
+    u = _DeviceUnpickler(file) if allowed is None else _RestrictedDeviceUnpickler(file, allowed)
+    u._resolve = resolve
+    u._rehome = rehome
+    return u
 
 
 class _ChannelHolder:
