@@ -66,15 +66,18 @@ std::pair<std::vector<RefPtr>, std::vector<RefPtr>> wait_refs(const std::vector<
     std::mutex mu;
     std::condition_variable cv;
     size_t n = 0;
+    size_t need = 0;
   };
   auto sh = std::make_shared<Shared>();
+  sh->need = std::min(num_ready, refs.size());
   for (auto& r : refs) {
     r->on_done([sh]() {
+      bool wake;
       {
         std::lock_guard<std::mutex> lk(sh->mu);
-        sh->n++;
+        wake = ++sh->n >= sh->need;  // the waiter is woken once, when enough of them resolved
       }
-      sh->cv.notify_all();
+      if (wake) sh->cv.notify_all();
     });
   }
   if (num_ready > refs.size()) num_ready = refs.size();
