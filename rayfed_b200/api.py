@@ -160,6 +160,12 @@ def init(
     trace_prefix = config.get("trace") or os.environ.get("RAYFED_B200_TRACE")
     if trace_prefix:
         _tracing.enable(party, str(trace_prefix))
+    metrics_port = config.get("metrics_port", os.environ.get("RAYFED_B200_METRICS_PORT"))
+    if metrics_port not in (None, ""):
+        from .utils import metrics as _metrics
+
+        _metrics.start_exporter(int(metrics_port), party=party, job=job_name,
+                                addr=str(config.get("metrics_addr", "127.0.0.1")))
     logger.info(f"Started rayfed_b200 with {cluster_config}")
 
     if threading.current_thread() is threading.main_thread():
@@ -408,6 +414,9 @@ def _shutdown(intended=True):
     if coll is not None:
         coll.reset(job_name_at_exit)
     _teardown_runtime(wait_for_sending)
+    metrics_mod = sys.modules.get("rayfed_b200.utils.metrics")
+    if metrics_mod is not None:
+        metrics_mod.stop_exporter()
     try:
         from .core import native
 

@@ -257,3 +257,34 @@ def test_reference_arm_runs_the_unmodified_reference():
         assert line.get("reference_importable") is True and line.get("substrate") in ("ray", "ray-shim"), line
     else:
         assert line["metric"] == "fedavg_resnet50_bf16_samples_per_sec" and line["value"] > 0
+
+
+def test_metrics_snapshot_and_prometheus_endpoint():
+    """Beyond the reference (two op counters read with `_get_stats`, fed/proxy/barriers.py:113-183):
+    every counter of the party in one snapshot, and the same numbers on a Prometheus endpoint."""
+    import urllib.request
+
+    import rayfed_b200 as fed
+    from party_utils import comm_config, make_addresses
+    from rayfed_b200.utils import metrics
+
+    addresses = make_addresses(["alice"])
+    fed.init(addresses=addresses, party="alice", logging_level="warning",
+             config={"cross_silo_comm": comm_config("native"), "metrics_port": 0})
+    try:
+        @fed.remote
+        def f(x):
+            return x + 1
+
+        assert fed.get(f.party("alice").remote(1)) == 2
+        snap = metrics.snapshot()
+        assert snap["executor_submitted"] >= 1 and snap["executor_completed"] >= 1
+        assert "sends_pending" in snap and "spin_usable_cpus" in snap and snap["seq_id"] >= 2
+        assert "receiver_receive_op_count" in snap or "receiver_mailbox_delivered" in snap
+        server, _ = metrics._exporter
+        port = server.server_address[1]
+        body = urllib.request.urlopen(f"http://127.0.0.1:{port}/metrics", timeout=5).read().decode()
+        assert 'rayfed_b200_executor_submitted{job_name=' in body and 'party="alice"' in body
+    finally:
+        fed.shutdown()
+    assert metrics._exporter is None
